@@ -1,0 +1,18 @@
+#!/bin/bash
+# Builds libb200grasp.so (sm_100a only) in-tree.  nvcc cross-compiles without a GPU.
+set -e
+cd "$(dirname "$0")/deep-rl-grasping_b200"
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall"
+mkdir -p build
+objs=""
+for f in csrc/*.cu; do
+  o=build/$(basename "${f%.cu}").o
+  if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ csrc/common.cuh -nt "$o" ] || [ ../include/b200grasp.h -nt "$o" ]; then
+    $NVCC $FLAGS -c "$f" -o "$o" &
+  fi
+  objs="$objs $o"
+done
+wait
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o libb200grasp.so $objs -ldl
+echo "built $(pwd)/libb200grasp.so"

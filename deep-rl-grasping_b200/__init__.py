@@ -1,0 +1,10 @@
+"""b200grasp -- B200-native SAC learner behind the stable-baselines model API used by
+BarisYazici/deep-rl-grasping (manipulation_main/training/sb_helper.py:104-128,175).
+
+Import as ``b200grasp`` (``b200grasp.py`` at the repo root aliases this directory, whose name
+``deep-rl-grasping_b200`` is not a Python identifier).
+"""
+from . import _lib, sb_io, synth  # noqa: F401
+from .learner import Learner  # noqa: F401
+
+__all__ = ["Learner", "sb_io", "synth"]

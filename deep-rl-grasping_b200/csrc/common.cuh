@@ -1,0 +1,148 @@
+// Shared declarations of libb200grasp (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+namespace b2g {
+
+// ---------------------------------------------------------------------------------------------
+// Gather-GEMM problem descriptor.  One engine serves every dense contraction on the path:
+//   C[cM[m] + cN[n]]  (=|+=)  epi( sum_r  A[aM[m] + aR[r]] * B[bR[r] + bN[n]] )
+// The offset tables (built once on the host, resident in HBM/L2) encode im2col for the forward
+// convolutions, the transposed/patch-major views for wgrad, and the parity-class gathers over
+// zero-bordered gradient maps for dgrad, so no im2col matrix is ever materialised.
+// ---------------------------------------------------------------------------------------------
+enum GemmFlags : int {
+  GG_A_RVEC = 1 << 0,     // A offsets contiguous along r in aligned groups of 4 (else along m)
+  GG_B_RVEC = 1 << 1,     // B offsets contiguous along r in aligned groups of 4 (else along n)
+  GG_EPI_BIAS_RELU = 1 << 2,
+  GG_EPI_MASK = 1 << 3,   // C = acc * (mask[kM[m] + kN[n]] > 0)
+  GG_EPI_ATOMIC = 1 << 4, // split-R accumulate into pre-zeroed C
+  GG_COLSUM = 1 << 5,     // colsum[n] += sum_r B(r, n)   (bias gradients; tile_m == 0 only)
+};
+
+struct GemmDesc {
+  const float* A;
+  const float* B;
+  float* C;
+  const int* aM; const int* aR;
+  const int* bR; const int* bN;
+  const int* cM; const int* cN;
+  const int* kM; const int* kN;
+  const float* bias;
+  const float* mask;
+  float* colsum;
+  int M, N, R;
+  int flags;
+  int splitR;
+  int tiles_m, tiles_n;
+  int tile_start;   // first flattened CTA index of this problem inside a grouped launch
+  int tile_count;
+};
+
+struct GemmGroup {          // one grouped launch
+  std::string name;
+  std::vector<GemmDesc> host;
+  GemmDesc* dev = nullptr;
+  int total_tiles = 0;
+  double flops = 0;
+};
+
+// engines (gg_simt.cu / gg_tc.cu)
+void gg_simt_launch(const GemmDesc* dev_descs, int ndesc, int total_tiles, cudaStream_t s);
+constexpr int GG_SIMT_BM = 64, GG_SIMT_BN = 64, GG_SIMT_BK = 16;
+
+// ---------------------------------------------------------------------------------------------
+// head "tail" kernel (tail.cu): everything after the fc0 contractions, per sample
+// ---------------------------------------------------------------------------------------------
+struct HeadW {           // pointers into the parameter arena for one MLP head
+  const float* b0;       // fc0 bias [H]
+  const float* k1;       // fc1 kernel [H,H]
+  const float* b1;       // fc1 bias [H]
+  const float* ko;       // output kernel [H, n_out]
+  const float* bo;       // output bias [n_out]
+  const float* k0;       // fc0 kernel [in, H] (qf heads: rows feat_dim.. are the action rows)
+};
+struct HeadG {           // matching gradient-arena pointers (small tensors accumulated by the tail)
+  float* b1; float* ko; float* bo;
+};
+
+struct TailArgs {
+  int B, H, A, feat_dim;
+  float gamma, target_entropy;
+  int grad_scale_B;            // divide means by this batch size (local batch)
+  // fc0 pre-activations (no bias) [B,H] each
+  const float* z0_pi; const float* z0_vf; const float* z0_q1; const float* z0_q2; const float* z0_vt;
+  HeadW pi, vf, q1, q2, vt;
+  const float* ksig; const float* bsig;      // pi: dense_1 (log_std) kernel/bias; pi.ko/bo = dense (mu)
+  HeadG g_pi, g_vf, g_q1, g_q2;
+  float* g_ksig; float* g_bsig;
+  const float* log_alpha; float* g_log_alpha;
+  const float* act;  int act_stride;         // replay actions (inside F_V rows)
+  const float* eps;                          // [B,A]
+  const float* rew; const float* done;       // normalised reward, done [B]
+  // saved for the engine: post-ReLU fc0 activations and gradients
+  float* a0_pi; float* a0_vf; float* a0_q1; float* a0_q2;   // [B,H]
+  float* dz1_pi; float* dz1_vf; float* dz1_q1; float* dz1_q2; // [B,H]
+  float* dz0_pi;                               // [B,H]
+  float* dz0_v3;                               // [B,3H] = vf | q1 | q2
+  float* per_sample;                           // 7 x [B]: q1,q2,v,logp,v_targ,q1_pi,q2_pi
+  float* pi_out;                               // [B,A]
+  float* metrics;                              // accumulators (see MET_* in sac.cu)
+};
+void tail_launch(const TailArgs& a, cudaStream_t s);
+// policy inference tail: tanh(mu) or tanh(mu + eps*std) for the first n rows of z0_pi
+void act_launch(const TailArgs& t, int n, int deterministic, float* act_out, cudaStream_t s);
+
+enum Metric : int {
+  MET_POLICY_LOSS = 0, MET_QF1_LOSS, MET_QF2_LOSS, MET_VALUE_LOSS, MET_ENT_COEF_LOSS, MET_ENTROPY,
+  MET_MEAN_Q1, MET_MEAN_Q2, MET_MEAN_V, MET_MEAN_LOGP, MET_GN_PI, MET_GN_VALUES, MET_COUNT = 16
+};
+
+// ---------------------------------------------------------------------------------------------
+// optimiser (optim.cu): 3x TF-Adam + Polyak over the flat arenas, one launch
+// ---------------------------------------------------------------------------------------------
+struct OptimArgs {
+  float* P; float* Mo; float* Vo; const float* G;   // trainable arenas
+  float* T;                                          // target block (same relative layout as values block)
+  int n_pi, n_values, n_ent;                         // padded segment lengths: [pi | values | ent]
+  int n_target;                                      // padded length of the target block
+  const double* step_consts;                         // [3] lr_t per optimiser (device, written by prep kernel)
+  float tau;
+  float grad_scale;                                  // 1/nranks after a sum all-reduce
+  float* metrics;                                    // MET_GN_* accumulators
+  int apply;                                         // 0 = only grad norms
+};
+void optim_launch(const OptimArgs& a, cudaStream_t s);
+
+struct PrepArgs {          // 1-CTA kernel at the head of every step
+  long long* counters;     // [0..2] Adam t per optimiser, [3] n_updates, [4] rng step counter
+  double* step_consts;     // lr_t x3
+  const float* lr;         // device scalar
+  float* metrics;          // zeroed
+  int* indices; float* eps;// generated when gen != 0
+  int B, A; const long long* replay_size;   // nullptr -> counters[5]
+  unsigned long long seed; int gen; int apply;
+};
+void prep_launch(const PrepArgs& a, cudaStream_t s);
+
+// ---------------------------------------------------------------------------------------------
+// replay gather + VecNormalize + /255 (replay.cu)
+// ---------------------------------------------------------------------------------------------
+struct GatherArgs {
+  const float* obs; const float* next_obs; const float* act; const float* rew; const float* done; // replay or staged batch
+  const int* indices;        // [B] slot per sample (nullptr: identity)
+  const double* mean; const double* var; // [obs_elems]; var[] holds 1/sqrt(var+eps)
+  const double* normc;       // device: {1/sqrt(ret_var+eps), clip_obs, clip_rew, norm_obs, norm_rew}
+  int B, H, W, Cfull;        // CNN: obs [H,W,Cfull]; MLP: H = 0, W = obs_dim
+  float scale;               // 255 for CNN, 1 for MLP
+  float* x_obs; float* x_next;   // CNN: [B,H,W,Cfull-1] image planes (scaled)
+  float* F_pi; float* F_v; float* F_t; int FS; int feat_col; // feature rows: direct feature -> col feat_col; MLP: whole obs -> cols 0..
+  float* rew_out; float* done_out; int n_act;
+};
+void gather_launch(const GatherArgs& a, cudaStream_t s);
+
+}  // namespace b2g

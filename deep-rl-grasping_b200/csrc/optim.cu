@@ -1,0 +1,133 @@
+// Optimiser + bookkeeping kernels: HBM/L2-bound, 128-bit vectorised, one pass over the arenas.
+//
+//  * prep_kernel  : head of every step -- advances the three Adam step counters, evaluates the TF1
+//                   bias-corrected step size lr_t = lr*sqrt(1-b2^t)/(1-b1^t) (tf.train.AdamOptimizer),
+//                   zeroes the metric accumulators and draws replay indices (ReplayBuffer.sample:
+//                   random.randint) and N(0,1) policy noise (tf.random_normal) from Philox4x32-10.
+//  * optim_kernel : policy Adam -> values Adam -> entropy Adam ([SB2] sac.py control-dependency
+//                   order; they touch disjoint variables so one fused pass is equivalent), then the
+//                   Polyak target update theta_T <- (1-tau) theta_T + tau theta_V on the UPDATED
+//                   values_fn ([SB2] target_update_op), plus squared gradient norms per optimiser.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace b2g {
+namespace {
+
+__device__ __forceinline__ void philox_round(uint4& c, uint2& k) {
+  const unsigned hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+  const unsigned hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+  c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+  k.x += 0x9E3779B9u; k.y += 0xBB67AE85u;
+}
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) philox_round(c, k);
+  return c;
+}
+__device__ __forceinline__ float u01(unsigned x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+
+__global__ void prep_kernel(PrepArgs a) {
+  const int tid = threadIdx.x;
+  __shared__ long long s_rng;
+  if (tid == 0) {
+    s_rng = a.counters[4];
+    if (a.apply) {
+      const double lr = (double)a.lr[0];
+      for (int g = 0; g < 3; ++g) {
+        const long long t = ++a.counters[g];
+        a.step_consts[g] = lr * sqrt(1.0 - pow(0.999, (double)t)) / (1.0 - pow(0.9, (double)t));
+      }
+      a.counters[3] += 1;
+    }
+    if (a.gen) a.counters[4] += 1;
+  }
+  if (tid < MET_COUNT) a.metrics[tid] = 0.f;
+  __syncthreads();
+  if (!a.gen) return;
+  const unsigned long long step = (unsigned long long)s_rng;
+  const uint2 key = make_uint2((unsigned)a.seed, (unsigned)(a.seed >> 32));
+  // stream 0: replay indices; stream 1: policy noise
+  const unsigned long long rsz = (unsigned long long)(a.replay_size ? a.replay_size[0] : a.counters[5]);
+  for (int i = tid; i < (a.B + 3) / 4; i += blockDim.x) {
+    const uint4 r = philox4x32_10(make_uint4((unsigned)step, (unsigned)(step >> 32), (unsigned)i, 0u), key);
+    const unsigned v[4] = {r.x, r.y, r.z, r.w};
+    for (int j = 0; j < 4; ++j) {
+      const int b = 4 * i + j;
+      if (b < a.B) a.indices[b] = (int)(((unsigned long long)v[j] * rsz) >> 32);
+    }
+  }
+  const int n_eps = a.B * a.A;
+  for (int i = tid; i < (n_eps + 3) / 4; i += blockDim.x) {
+    const uint4 r = philox4x32_10(make_uint4((unsigned)step, (unsigned)(step >> 32), (unsigned)i, 1u), key);
+    const float r0 = sqrtf(-2.f * logf(u01(r.x))), r1 = sqrtf(-2.f * logf(u01(r.z)));
+    float s0, c0, s1, c1;
+    sincospif(2.f * u01(r.y), &s0, &c0);
+    sincospif(2.f * u01(r.w), &s1, &c1);
+    const float z[4] = {r0 * c0, r0 * s0, r1 * c1, r1 * s1};
+    for (int j = 0; j < 4; ++j)
+      if (4 * i + j < n_eps) a.eps[4 * i + j] = z[j];
+  }
+}
+
+__global__ void __launch_bounds__(256) optim_kernel(OptimArgs a) {
+  const int n_total4 = (a.n_pi + a.n_values + a.n_ent) >> 2;
+  const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
+  const float lrt[3] = {(float)a.step_consts[0], (float)a.step_consts[1], (float)a.step_consts[2]};
+  float ss[2] = {0.f, 0.f};
+  for (int i4 = blockIdx.x * blockDim.x + threadIdx.x; i4 < n_total4; i4 += gridDim.x * blockDim.x) {
+    const int i = i4 << 2;
+    const int grp = i < a.n_pi ? 0 : (i < a.n_pi + a.n_values ? 1 : 2);
+    float4 g = reinterpret_cast<const float4*>(a.G)[i4];
+    g.x *= a.grad_scale; g.y *= a.grad_scale; g.z *= a.grad_scale; g.w *= a.grad_scale;
+    const float s2 = g.x * g.x + g.y * g.y + g.z * g.z + g.w * g.w;
+    if (grp < 2) ss[grp] += s2;
+    if (!a.apply) continue;
+    float4 m = reinterpret_cast<float4*>(a.Mo)[i4], v = reinterpret_cast<float4*>(a.Vo)[i4];
+    float4 p = reinterpret_cast<float4*>(a.P)[i4];
+    const float lr = lrt[grp];
+#define B2G_ADAM(c)                                   \
+  m.c = b1 * m.c + (1.f - b1) * g.c;                  \
+  v.c = b2 * v.c + (1.f - b2) * (g.c * g.c);          \
+  p.c = p.c - lr * m.c / (sqrtf(v.c) + eps);
+    B2G_ADAM(x) B2G_ADAM(y) B2G_ADAM(z) B2G_ADAM(w)
+#undef B2G_ADAM
+    reinterpret_cast<float4*>(a.Mo)[i4] = m;
+    reinterpret_cast<float4*>(a.Vo)[i4] = v;
+    reinterpret_cast<float4*>(a.P)[i4] = p;
+    const int j = i - a.n_pi;
+    if (grp == 1 && j < a.n_target) {
+      float4 tg = reinterpret_cast<float4*>(a.T)[j >> 2];
+      const float tau = a.tau, om = 1.f - a.tau;
+      tg.x = om * tg.x + tau * p.x; tg.y = om * tg.y + tau * p.y;
+      tg.z = om * tg.z + tau * p.z; tg.w = om * tg.w + tau * p.w;
+      reinterpret_cast<float4*>(a.T)[j >> 2] = tg;
+    }
+  }
+  // block reduce of the two squared norms
+  __shared__ float red[2][8];
+  for (int k = 0; k < 2; ++k) {
+    float v = ss[k];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    float v = 0.f;
+    for (int w = 0; w < 8; ++w) v += red[threadIdx.x][w];
+    atomicAdd(a.metrics + MET_GN_PI + threadIdx.x, v);
+  }
+}
+}  // namespace
+
+void prep_launch(const PrepArgs& a, cudaStream_t s) { prep_kernel<<<1, 256, 0, s>>>(a); }
+
+void optim_launch(const OptimArgs& a, cudaStream_t s) {
+  const int n4 = (a.n_pi + a.n_values + a.n_ent) >> 2;
+  int grid = (n4 + 255) / 256;
+  if (grid > 148 * 8) grid = 148 * 8;
+  optim_kernel<<<grid, 256, 0, s>>>(a);
+}
+
+}  // namespace b2g

@@ -1,0 +1,1029 @@
+// libb200grasp: SAC learner handle, HBM layout, offset tables, step orchestration, C ABI.
+//
+// HBM layout (all fp32 unless noted; everything is allocated once in b2g_sac_create):
+//   P  : parameter arena  [ model/pi | model/values_fn | log_ent_coef | target/values_fn ], every
+//        tensor padded to 32 floats, tensor order = SB zip parameter_list
+//   Mo, Vo, G : Adam moments and gradients, same offsets as the trainable part of P
+//   replay  : obs[cap,E] next_obs[cap,E] act[cap,A] rew[cap] done[cap]   (raw, un-normalised)
+//   batch   : x_obs/x_next [B,H,W,C] (normalised, /255), h1/h2/h3 per network, F rows [B,FS]
+//             (512 CNN features | direct feature | replay action | zero pad), gradient maps with
+//             zero borders (dZ3p, dZ2p) so the dgrad gathers need no bounds logic
+// One gradient step = prep -> gather -> zero G -> grouped gather-GEMM launches (forward) -> tail
+// -> grouped gather-GEMM launches (backward) -> [NCCL all-reduce of G] -> optim; captured once in
+// a CUDA graph and replayed.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/b200grasp.h"
+#include "common.cuh"
+
+using namespace b2g;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CK(call)                                                                                  \
+  do {                                                                                            \
+    cudaError_t e_ = (call);                                                                      \
+    if (e_ != cudaSuccess)                                                                        \
+      return fail(B2G_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_) + " @" + __FILE__ + ":" + \
+                                 std::to_string(__LINE__));                                       \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// NCCL through dlopen (no link-time dependency; the library loads on boxes without NCCL/GPU)
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct UId { char b[128]; };   // ncclUniqueId
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, UId, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+
+int load_nccl(const char* path) {
+  if (g_nccl.lib) return 0;
+  const char* cands[] = {path, "libnccl.so.2", "libnccl.so", "/usr/lib/x86_64-linux-gnu/libnccl.so.2"};
+  for (const char* c : cands) {
+    if (!c || !*c) continue;
+    g_nccl.lib = dlopen(c, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.lib) break;
+  }
+  if (!g_nccl.lib) return fail(B2G_ENCCL, std::string("cannot dlopen libnccl: ") + dlerror());
+  g_nccl.GetUniqueId = (int (*)(void*))dlsym(g_nccl.lib, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (int (*)(void**, int, UId, int))dlsym(g_nccl.lib, "ncclCommInitRank");
+  g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(g_nccl.lib, "ncclAllReduce");
+  g_nccl.CommDestroy = (int (*)(void*))dlsym(g_nccl.lib, "ncclCommDestroy");
+  g_nccl.GetErrorString = (const char* (*)(int))dlsym(g_nccl.lib, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce)
+    return fail(B2G_ENCCL, "libnccl is missing symbols");
+  return 0;
+}
+
+struct Tensor {
+  std::string name;
+  int ndim;
+  int64_t shape[4];
+  int64_t numel;
+  int64_t off;    // float offset inside P
+  int group;      // 0 pi, 1 values, 2 ent, 3 target
+};
+
+int64_t pad32(int64_t n) { return (n + 31) / 32 * 32; }
+}  // namespace
+
+struct b2g_sac {
+  b2g_sac_cfg cfg{};
+  bool cnn = false;
+  int B = 0, A = 0, H = 0, E = 0, Cimg = 0, feat_dim = 0, FS = 0;
+  int Hi = 0, Wi = 0, H1 = 0, W1 = 0, H2 = 0, W2 = 0, H3 = 0, W3 = 0;
+  std::vector<Tensor> tensors;
+  std::map<std::string, int> tindex;
+  int64_t n_pi = 0, n_values = 0, n_ent = 0, n_target = 0, n_train = 0, n_all = 0;
+  float *P = nullptr, *Mo = nullptr, *Vo = nullptr, *G = nullptr;   // G has MET_COUNT extra floats (metrics ride the all-reduce)
+  float* metrics = nullptr;
+  cudaStream_t stream = nullptr;
+  std::vector<void*> allocs;
+  // replay
+  float *r_obs = nullptr, *r_next = nullptr, *r_act = nullptr, *r_rew = nullptr, *r_done = nullptr;
+  int64_t r_size = 0, r_pos = 0;
+  // normalisation
+  double *d_mean = nullptr, *d_istd = nullptr, *d_normc = nullptr;   // normc: ret_istd, clip_obs, clip_rew, norm_obs, norm_rew
+  double ret_istd = 1.0, clip_obs = 10.0, clip_rew = 10.0;
+  int norm_obs = 0, norm_rew = 0;
+  // batch buffers
+  float *x_obs = nullptr, *x_next = nullptr;
+  float *h1[3]{}, *h2[3]{}, *h3[3]{}, *F[3]{};
+  float *dZ4[2]{}, *dZ3p[2]{}, *dZ2p[2]{}, *dZ1[2]{};
+  float *z0[5]{}, *a0[4]{}, *dz1[4]{}, *dz0_pi = nullptr, *dz0_v3 = nullptr;
+  float *per_sample = nullptr, *pi_out = nullptr, *eps = nullptr, *rew_n = nullptr, *done_n = nullptr;
+  int* indices = nullptr;
+  float *s_obs = nullptr, *s_next = nullptr, *s_act = nullptr, *s_rew = nullptr, *s_done = nullptr;  // staged explicit batch
+  long long* counters = nullptr;
+  double* step_consts = nullptr;
+  float* d_lr = nullptr;
+  float cur_lr = -1.f;
+  // launches
+  std::vector<GemmGroup> fwd_groups, bwd_groups, act_groups;
+  cudaGraphExec_t graph_exec = nullptr;
+  bool use_graph = true;
+  void* nccl_comm = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  float last_ms = 0.f;
+  int launches = 0;
+  std::vector<std::string> prof_names;
+  b2g_sac_metrics* h_metrics_pinned = nullptr;
+  float* h_met = nullptr;        // pinned MET_COUNT floats
+  long long* h_cnt = nullptr;    // pinned counters
+
+  float* p(const std::string& n) { return P + tensors[tindex.at(n)].off; }
+  float* g(const std::string& n) { return G + tensors[tindex.at(n)].off; }
+};
+
+namespace {
+
+template <class T>
+int dalloc(b2g_sac* h, T** ptr, size_t count, bool zero = true) {
+  void* q = nullptr;
+  CK(cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T)));
+  if (zero) CK(cudaMemsetAsync(q, 0, std::max<size_t>(count, 1) * sizeof(T), h->stream));
+  h->allocs.push_back(q);
+  *ptr = (T*)q;
+  return 0;
+}
+
+int upload_table(b2g_sac* h, const std::vector<int>& v, const int** out) {
+  int* d = nullptr;
+  if (int rc = dalloc(h, &d, v.size(), false)) return rc;
+  CK(cudaMemcpyAsync(d, v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));   // v may be a temporary
+  *out = d;
+  return 0;
+}
+
+std::vector<int> iota_tab(int n, int stride = 1, int base = 0) {
+  std::vector<int> v(n);
+  for (int i = 0; i < n; ++i) v[i] = base + i * stride;
+  return v;
+}
+
+void add_tensor(b2g_sac* h, const std::string& name, std::vector<int64_t> shape, int group) {
+  Tensor t;
+  t.name = name;
+  t.ndim = (int)shape.size();
+  t.numel = 1;
+  for (int i = 0; i < 4; ++i) t.shape[i] = i < t.ndim ? shape[i] : 1;
+  for (auto s : shape) t.numel *= s;
+  t.group = group;
+  t.off = 0;
+  h->tindex[name] = (int)h->tensors.size();
+  h->tensors.push_back(t);
+}
+
+void add_cnn(b2g_sac* h, const std::string& pre, int group) {
+  add_tensor(h, pre + "/cnn1/w", {8, 8, h->Cimg, 32}, group);
+  add_tensor(h, pre + "/cnn1/b", {1, 32, 1, 1}, group);
+  add_tensor(h, pre + "/cnn2/w", {4, 4, 32, 64}, group);
+  add_tensor(h, pre + "/cnn2/b", {1, 64, 1, 1}, group);
+  add_tensor(h, pre + "/cnn3/w", {3, 3, 64, 64}, group);
+  add_tensor(h, pre + "/cnn3/b", {1, 64, 1, 1}, group);
+  add_tensor(h, pre + "/cnn_fc1/w", {1024, 512}, group);
+  add_tensor(h, pre + "/cnn_fc1/b", {512}, group);
+}
+void add_mlp(b2g_sac* h, const std::string& pre, int in_dim, int group) {
+  add_tensor(h, pre + "/fc0/kernel", {in_dim, h->H}, group);
+  add_tensor(h, pre + "/fc0/bias", {h->H}, group);
+  add_tensor(h, pre + "/fc1/kernel", {h->H, h->H}, group);
+  add_tensor(h, pre + "/fc1/bias", {h->H}, group);
+}
+
+// Parameter inventory in SB-zip order (oracle/sac_ref.py param_specs)
+void build_params(b2g_sac* h) {
+  const int A = h->A, H = h->H, fd = h->feat_dim;
+  if (h->cnn) add_cnn(h, "model/pi", 0);
+  add_mlp(h, "model/pi", fd, 0);
+  add_tensor(h, "model/pi/dense/kernel", {H, A}, 0);
+  add_tensor(h, "model/pi/dense/bias", {A}, 0);
+  add_tensor(h, "model/pi/dense_1/kernel", {H, A}, 0);
+  add_tensor(h, "model/pi/dense_1/bias", {A}, 0);
+  for (int tgt = 0; tgt < 2; ++tgt) {
+    const std::string sc = tgt ? "target/values_fn" : "model/values_fn";
+    const int grp = tgt ? 3 : 1;
+    if (h->cnn) add_cnn(h, sc, grp);
+    add_mlp(h, sc + "/vf", fd, grp);
+    add_tensor(h, sc + "/vf/vf/kernel", {H, 1}, grp);
+    add_tensor(h, sc + "/vf/vf/bias", {1}, grp);
+    if (!tgt) {
+      for (const char* q : {"qf1", "qf2"}) {
+        add_mlp(h, sc + "/" + q, fd + A, grp);
+        add_tensor(h, sc + "/" + q + "/" + q + "/kernel", {H, 1}, grp);
+        add_tensor(h, sc + "/" + q + "/" + q + "/bias", {1}, grp);
+      }
+      add_tensor(h, "model/log_ent_coef", {}, 2);
+    }
+  }
+  int64_t off = 0;
+  int64_t gstart[5] = {0, 0, 0, 0, 0};
+  int cur = 0;
+  for (auto& t : h->tensors) {
+    while (cur < t.group) gstart[++cur] = off;
+    t.off = off;
+    off += pad32(t.numel);
+  }
+  while (cur < 4) gstart[++cur] = off;
+  h->n_pi = gstart[1] - gstart[0];
+  h->n_values = gstart[2] - gstart[1];
+  h->n_ent = gstart[3] - gstart[2];
+  h->n_target = gstart[4] - gstart[3];
+  h->n_train = gstart[3];
+  h->n_all = off;
+}
+
+GemmDesc mk(const float* A, const int* aM, const int* aR, const float* B, const int* bR, const int* bN, float* C,
+            const int* cM, const int* cN, int M, int N, int R, int flags, int splitR = 1) {
+  GemmDesc d{};
+  d.A = A; d.B = B; d.C = C; d.aM = aM; d.aR = aR; d.bR = bR; d.bN = bN; d.cM = cM; d.cN = cN;
+  d.M = M; d.N = N; d.R = R; d.flags = flags; d.splitR = splitR;
+  return d;
+}
+
+int finalize_group(b2g_sac* h, GemmGroup& g) {
+  int start = 0;
+  g.flops = 0;
+  for (auto& d : g.host) {
+    d.tiles_m = (d.M + GG_SIMT_BM - 1) / GG_SIMT_BM;
+    d.tiles_n = (d.N + GG_SIMT_BN - 1) / GG_SIMT_BN;
+    d.tile_start = start;
+    d.tile_count = d.tiles_m * d.tiles_n * d.splitR;
+    start += d.tile_count;
+    g.flops += 2.0 * d.M * d.N * d.R;
+  }
+  g.total_tiles = start;
+  if (int rc = dalloc(h, &g.dev, g.host.size(), false)) return rc;
+  CK(cudaMemcpyAsync(g.dev, g.host.data(), g.host.size() * sizeof(GemmDesc), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int split_for(int tiles, int R, int target_ctas = 148) {
+  int s = std::max(1, target_ctas / std::max(1, tiles));
+  const int max_s = std::max(1, R / (4 * GG_SIMT_BK));
+  return std::min(s, max_s);
+}
+
+#define TAB(var, vec)                                         \
+  const int* var = nullptr;                                   \
+  if (int rc_ = upload_table(h, (vec), &var)) return rc_;
+
+int build_groups(b2g_sac* h) {
+  const int B = h->B, A = h->A, H = h->H, FS = h->FS, fd = h->feat_dim;
+  const char* nets[3] = {"model/pi", "model/values_fn", "target/values_fn"};
+  TAB(i64, iota_tab(64));           // generic small iotas
+  TAB(i512, iota_tab(512));
+  TAB(i1024, iota_tab(1024));
+  TAB(rowH, iota_tab(B, H));        // b*H
+  TAB(rowFS, iota_tab(B, FS));
+  TAB(row3H, iota_tab(B, 3 * H));
+  TAB(iFS, iota_tab(FS));
+  TAB(kH, iota_tab(FS, H));         // j*H  (fc0 kernel rows)
+
+  auto nn = [&](int net, const char* s) { return std::string(nets[net]) + s; };
+
+  if (h->cnn) {
+    const int Ci = h->Cimg, Hi = h->Hi, Wi = h->Wi, H1 = h->H1, W1 = h->W1, H2 = h->H2, W2 = h->W2, H3 = h->H3, W3 = h->W3;
+    const int P2h = H2 + 3, P2w = W2 + 3, P3h = H3 + 4, P3w = W3 + 4;
+    // ---- forward / wgrad tables per conv layer
+    struct Conv { int Hi, Wi, Ci, k, s, Ho, Wo, Co; };
+    const Conv cv[3] = {{Hi, Wi, Ci, 8, 4, H1, W1, 32}, {H1, W1, 32, 4, 2, H2, W2, 64}, {H2, W2, 64, 3, 1, H3, W3, 64}};
+    const int* rowoff[3]; const int* koff[3]; const int* wrow[3]; const int* crow[3];
+    for (int l = 0; l < 3; ++l) {
+      const Conv& c = cv[l];
+      std::vector<int> ro(B * c.Ho * c.Wo), ko(c.k * c.k * c.Ci);
+      for (int b = 0; b < B; ++b)
+        for (int oy = 0; oy < c.Ho; ++oy)
+          for (int ox = 0; ox < c.Wo; ++ox)
+            ro[(b * c.Ho + oy) * c.Wo + ox] = ((b * c.Hi + oy * c.s) * c.Wi + ox * c.s) * c.Ci;
+      for (int ky = 0; ky < c.k; ++ky)
+        for (int kx = 0; kx < c.k; ++kx)
+          for (int ci = 0; ci < c.Ci; ++ci) ko[(ky * c.k + kx) * c.Ci + ci] = (ky * c.Wi + kx) * c.Ci + ci;
+      if (int rc = upload_table(h, ro, &rowoff[l])) return rc;
+      if (int rc = upload_table(h, ko, &koff[l])) return rc;
+      if (int rc = upload_table(h, iota_tab(c.k * c.k * c.Ci, c.Co), &wrow[l])) return rc;
+      if (int rc = upload_table(h, iota_tab(B * c.Ho * c.Wo, c.Co), &crow[l])) return rc;
+    }
+    TAB(fcA, iota_tab(B, 1024));
+    TAB(fcW, iota_tab(1024, 512));
+    // dZ row tables in the zero-bordered layouts
+    std::vector<int> z2row(B * H2 * W2), z3row(B * H3 * W3);
+    for (int b = 0; b < B; ++b) {
+      for (int y = 0; y < H2; ++y)
+        for (int x = 0; x < W2; ++x) z2row[(b * H2 + y) * W2 + x] = ((b * P2h + y + 1) * P2w + x + 1) * 64;
+      for (int y = 0; y < H3; ++y)
+        for (int x = 0; x < W3; ++x) z3row[(b * H3 + y) * W3 + x] = ((b * P3h + y + 2) * P3w + x + 2) * 64;
+    }
+    TAB(dz2row, z2row);
+    TAB(dz3row, z3row);
+
+    // ================= forward groups
+    const char* cname[3] = {"/cnn1", "/cnn2", "/cnn3"};
+    for (int l = 0; l < 3; ++l) {
+      const Conv& c = cv[l];
+      GemmGroup g;
+      g.name = std::string("conv") + char('1' + l) + "_fwd";
+      for (int n = 0; n < 3; ++n) {
+        const float* in = l == 0 ? (n == 2 ? h->x_next : h->x_obs) : (l == 1 ? h->h1[n] : h->h2[n]);
+        float* out = l == 0 ? h->h1[n] : (l == 1 ? h->h2[n] : h->h3[n]);
+        GemmDesc d = mk(in, rowoff[l], koff[l], h->p(nn(n, cname[l]) + "/w"), wrow[l], i64, out, crow[l], i64,
+                        B * c.Ho * c.Wo, c.Co, c.k * c.k * c.Ci, GG_A_RVEC | GG_EPI_BIAS_RELU);
+        d.bias = h->p(nn(n, cname[l]) + "/b");
+        g.host.push_back(d);
+      }
+      h->fwd_groups.push_back(g);
+    }
+    {
+      GemmGroup g;
+      g.name = "fc1_fwd";
+      for (int n = 0; n < 3; ++n) {
+        GemmDesc d = mk(h->h3[n], fcA, i1024, h->p(nn(n, "/cnn_fc1/w")), fcW, i512, h->F[n], rowFS, i512, B, 512, 1024,
+                        GG_A_RVEC | GG_EPI_BIAS_RELU);
+        d.bias = h->p(nn(n, "/cnn_fc1/b"));
+        g.host.push_back(d);
+      }
+      h->fwd_groups.push_back(g);
+    }
+    // policy-inference groups (pi network only)
+    for (int l = 0; l < 4; ++l) {
+      GemmGroup g = h->fwd_groups[l];
+      g.name = "act_" + g.name;
+      g.host.resize(1);
+      g.dev = nullptr;
+      h->act_groups.push_back(g);
+    }
+
+    // ================= backward groups (pi, values)
+    // head dgrad -> dZ4 (masked by relu of cnn_fc1 output)
+    {
+      GemmGroup g;
+      g.name = "heads_dgrad";
+      TAB(row512, iota_tab(B, 512));
+      // pi
+      GemmDesc d = mk(h->dz0_pi, rowH, i64, h->p("model/pi/fc0/kernel"), i64, kH, h->dZ4[0], row512, i512, B, 512, H,
+                      GG_A_RVEC | GG_B_RVEC | GG_EPI_MASK);
+      d.mask = h->F[0]; d.kM = rowFS; d.kN = i512;
+      g.host.push_back(d);
+      // values: [dz0_vf | dz0_q1 | dz0_q2] x [K0_vf ; K0_q1 ; K0_q2]^T
+      std::vector<int> br(3 * H);
+      const char* hn[3] = {"/vf/fc0/kernel", "/qf1/fc0/kernel", "/qf2/fc0/kernel"};
+      for (int q = 0; q < 3; ++q)
+        for (int r = 0; r < H; ++r) br[q * H + r] = (int)(h->tensors[h->tindex.at(nn(1, hn[q]))].off) + r;
+      TAB(brv, br);
+      TAB(i3H, iota_tab(3 * H));
+      GemmDesc e = mk(h->dz0_v3, row3H, i3H, h->P, brv, kH, h->dZ4[1], row512, i512, B, 512, 3 * H,
+                      GG_A_RVEC | GG_B_RVEC | GG_EPI_MASK);
+      e.mask = h->F[1]; e.kM = rowFS; e.kN = i512;
+      g.host.push_back(e);
+      h->bwd_groups.push_back(g);
+      // fc1 wgrad + dgrad
+      GemmGroup f;
+      f.name = "fc1_bwd";
+      std::vector<int> cn(1024), fcT(1024);
+      for (int y = 0; y < H3; ++y)
+        for (int x = 0; x < W3; ++x)
+          for (int c = 0; c < 64; ++c) cn[(y * W3 + x) * 64 + c] = ((y + 2) * P3w + (x + 2)) * 64 + c;
+      TAB(cN3p, cn);
+      TAB(rowP3, iota_tab(B, P3h * P3w * 64));
+      TAB(wfT, iota_tab(1024, 512));
+      for (int n = 0; n < 2; ++n) {
+        GemmDesc w = mk(h->h3[n], i1024, fcA, h->dZ4[n], row512, i512, h->g(nn(n, "/cnn_fc1/w")), fcW, i512, 1024, 512, B,
+                        GG_COLSUM);
+        w.colsum = h->g(nn(n, "/cnn_fc1/b"));
+        f.host.push_back(w);
+        GemmDesc dg = mk(h->dZ4[n], row512, i512, h->p(nn(n, "/cnn_fc1/w")), i512, wfT, h->dZ3p[n], rowP3, cN3p, B, 1024, 512,
+                         GG_A_RVEC | GG_B_RVEC | GG_EPI_MASK);
+        dg.mask = h->h3[n]; dg.kM = fcA; dg.kN = i1024;
+        f.host.push_back(dg);
+      }
+      h->bwd_groups.push_back(f);
+    }
+    // conv3 wgrad + dgrad
+    {
+      GemmGroup g;
+      g.name = "conv3_bwd";
+      std::vector<int> am(B * H2 * W2), ar(9 * 64), br(9 * 64), cm(B * H2 * W2);
+      for (int b = 0; b < B; ++b)
+        for (int y = 0; y < H2; ++y)
+          for (int x = 0; x < W2; ++x) {
+            am[(b * H2 + y) * W2 + x] = ((b * P3h + y + 2) * P3w + x + 2) * 64;
+            cm[(b * H2 + y) * W2 + x] = ((b * P2h + y + 1) * P2w + x + 1) * 64;
+          }
+      for (int ky = 0; ky < 3; ++ky)
+        for (int kx = 0; kx < 3; ++kx)
+          for (int n = 0; n < 64; ++n) {
+            ar[(ky * 3 + kx) * 64 + n] = -(ky * P3w + kx) * 64 + n;
+            br[(ky * 3 + kx) * 64 + n] = (ky * 3 + kx) * 64 * 64 + n;
+          }
+      TAB(t_am, am); TAB(t_ar, ar); TAB(t_br, br); TAB(t_cm, cm);
+      TAB(c64, iota_tab(64, 64));
+      const int R = B * H3 * W3;
+      for (int n = 0; n < 2; ++n) {
+        GemmDesc w = mk(h->h2[n], koff[2], rowoff[2], h->dZ3p[n], dz3row, i64, h->g(nn(n, "/cnn3/w")), wrow[2], i64, 576, 64, R,
+                        GG_COLSUM | GG_EPI_ATOMIC, split_for(9, R));
+        w.colsum = h->g(nn(n, "/cnn3/b"));
+        g.host.push_back(w);
+        GemmDesc dg = mk(h->dZ3p[n], t_am, t_ar, h->p(nn(n, "/cnn3/w")), t_br, c64, h->dZ2p[n], t_cm, i64, B * H2 * W2, 64, 576,
+                         GG_A_RVEC | GG_B_RVEC | GG_EPI_MASK);
+        dg.mask = h->h2[n]; dg.kM = crow[1]; dg.kN = i64;
+        g.host.push_back(dg);
+      }
+      h->bwd_groups.push_back(g);
+    }
+    // conv2 wgrad + 4 parity-class dgrads
+    {
+      GemmGroup g;
+      g.name = "conv2_bwd";
+      const int R = B * H2 * W2;
+      TAB(c64, iota_tab(32, 64));
+      for (int n = 0; n < 2; ++n) {
+        GemmDesc w = mk(h->h1[n], koff[1], rowoff[1], h->dZ2p[n], dz2row, i64, h->g(nn(n, "/cnn2/w")), wrow[1], i64, 512, 64, R,
+                        GG_COLSUM | GG_EPI_ATOMIC, split_for(8, R));
+        w.colsum = h->g(nn(n, "/cnn2/b"));
+        g.host.push_back(w);
+      }
+      for (int py = 0; py < 2; ++py)
+        for (int px = 0; px < 2; ++px) {
+          const int ny = (H1 - py + 1) / 2, nx = (W1 - px + 1) / 2;
+          std::vector<int> am(B * ny * nx), cm(B * ny * nx), ar(4 * 64), br(4 * 64);
+          for (int b = 0; b < B; ++b)
+            for (int yy = 0; yy < ny; ++yy)
+              for (int xx = 0; xx < nx; ++xx) {
+                am[(b * ny + yy) * nx + xx] = ((b * P2h + yy + 1) * P2w + xx + 1) * 64;
+                cm[(b * ny + yy) * nx + xx] = ((b * H1 + 2 * yy + py) * W1 + 2 * xx + px) * 32;
+              }
+          for (int jy = 0; jy < 2; ++jy)
+            for (int jx = 0; jx < 2; ++jx)
+              for (int q = 0; q < 64; ++q) {
+                ar[(jy * 2 + jx) * 64 + q] = -(jy * P2w + jx) * 64 + q;
+                br[(jy * 2 + jx) * 64 + q] = (((py + 2 * jy) * 4 + (px + 2 * jx)) * 32) * 64 + q;
+              }
+          TAB(t_am, am); TAB(t_ar, ar); TAB(t_br, br); TAB(t_cm, cm);
+          for (int n = 0; n < 2; ++n) {
+            GemmDesc dg = mk(h->dZ2p[n], t_am, t_ar, h->p(nn(n, "/cnn2/w")), t_br, c64, h->dZ1[n], t_cm, i64, B * ny * nx, 32, 256,
+                             GG_A_RVEC | GG_B_RVEC | GG_EPI_MASK);
+            dg.mask = h->h1[n];
+            g.host.push_back(dg);
+          }
+        }
+      h->bwd_groups.push_back(g);
+    }
+    // conv1 wgrad
+    {
+      GemmGroup g;
+      g.name = "conv1_wgrad";
+      const int R = B * H1 * W1, M = 64 * Ci;
+      for (int n = 0; n < 2; ++n) {
+        GemmDesc w = mk(h->x_obs, koff[0], rowoff[0], h->dZ1[n], crow[0], i64, h->g(nn(n, "/cnn1/w")), wrow[0], i64, M, 32, R,
+                        GG_COLSUM | GG_EPI_ATOMIC, split_for((M + 63) / 64, R, 74));
+        w.colsum = h->g(nn(n, "/cnn1/b"));
+        g.host.push_back(w);
+      }
+      h->bwd_groups.push_back(g);
+    }
+  }
+
+  // ================= heads fc0 forward (all policies)
+  {
+    GemmGroup g;
+    g.name = "heads_fc0";
+    const char* hk[5] = {"model/pi/fc0/kernel", "model/values_fn/vf/fc0/kernel", "model/values_fn/qf1/fc0/kernel",
+                         "model/values_fn/qf2/fc0/kernel", "target/values_fn/vf/fc0/kernel"};
+    const int fnet[5] = {0, 1, 1, 1, 2};
+    for (int q = 0; q < 5; ++q) {
+      const int R = (q == 2 || q == 3) ? fd + A : fd;
+      g.host.push_back(mk(h->F[fnet[q]], rowFS, iFS, h->p(hk[q]), kH, i64, h->z0[q], rowH, i64, B, H, R, GG_A_RVEC));
+    }
+    h->fwd_groups.push_back(g);
+    GemmGroup a = g;
+    a.name = "act_heads_fc0";
+    a.host.resize(1);
+    h->act_groups.push_back(a);
+  }
+  // ================= heads wgrad (fc0 and fc1 kernels + their biases through COLSUM)
+  {
+    GemmGroup g;
+    g.name = "heads_wgrad";
+    const char* hp[4] = {"model/pi", "model/values_fn/vf", "model/values_fn/qf1", "model/values_fn/qf2"};
+    TAB(i3Hs0, iota_tab(B, 3 * H, 0));
+    TAB(i3Hs1, iota_tab(B, 3 * H, H));
+    TAB(i3Hs2, iota_tab(B, 3 * H, 2 * H));
+    const int* dzrow[4] = {rowH, i3Hs0, i3Hs1, i3Hs2};
+    for (int q = 0; q < 4; ++q) {
+      const int M = (q >= 2) ? fd + A : fd;
+      const float* dz0 = q == 0 ? h->dz0_pi : h->dz0_v3;
+      GemmDesc w0 = mk(h->F[q == 0 ? 0 : 1], iFS, rowFS, dz0, dzrow[q], i64, h->g(std::string(hp[q]) + "/fc0/kernel"), kH, i64, M, H, B,
+                       GG_COLSUM);
+      w0.colsum = h->g(std::string(hp[q]) + "/fc0/bias");
+      g.host.push_back(w0);
+      GemmDesc w1 = mk(h->a0[q], i64, rowH, h->dz1[q], rowH, i64, h->g(std::string(hp[q]) + "/fc1/kernel"), kH, i64, H, H, B, GG_COLSUM);
+      w1.colsum = h->g(std::string(hp[q]) + "/fc1/bias");
+      g.host.push_back(w1);
+    }
+    // heads_wgrad must run before heads_dgrad? no dependency; keep it first in the backward list
+    h->bwd_groups.insert(h->bwd_groups.begin(), g);
+  }
+  for (auto& g : h->fwd_groups) if (int rc = finalize_group(h, g)) return rc;
+  for (auto& g : h->bwd_groups) if (int rc = finalize_group(h, g)) return rc;
+  for (auto& g : h->act_groups) if (int rc = finalize_group(h, g)) return rc;
+  return 0;
+}
+
+HeadW head_w(b2g_sac* h, const std::string& pre, const std::string& out) {
+  HeadW w;
+  w.k0 = h->p(pre + "/fc0/kernel");
+  w.b0 = h->p(pre + "/fc0/bias");
+  w.k1 = h->p(pre + "/fc1/kernel");
+  w.b1 = h->p(pre + "/fc1/bias");
+  w.ko = h->p(pre + "/" + out + "/kernel");
+  w.bo = h->p(pre + "/" + out + "/bias");
+  return w;
+}
+HeadG head_g(b2g_sac* h, const std::string& pre, const std::string& out) {
+  HeadG g;
+  g.b1 = h->g(pre + "/fc1/bias");
+  g.ko = h->g(pre + "/" + out + "/kernel");
+  g.bo = h->g(pre + "/" + out + "/bias");
+  return g;
+}
+
+TailArgs make_tail(b2g_sac* h, bool want_per_sample) {
+  TailArgs t{};
+  t.B = h->B; t.H = h->H; t.A = h->A; t.feat_dim = h->feat_dim;
+  t.gamma = h->cfg.gamma; t.target_entropy = h->cfg.target_entropy;
+  t.grad_scale_B = h->B;
+  t.z0_pi = h->z0[0]; t.z0_vf = h->z0[1]; t.z0_q1 = h->z0[2]; t.z0_q2 = h->z0[3]; t.z0_vt = h->z0[4];
+  t.pi = head_w(h, "model/pi", "dense");
+  t.vf = head_w(h, "model/values_fn/vf", "vf");
+  t.q1 = head_w(h, "model/values_fn/qf1", "qf1");
+  t.q2 = head_w(h, "model/values_fn/qf2", "qf2");
+  t.vt = head_w(h, "target/values_fn/vf", "vf");
+  t.ksig = h->p("model/pi/dense_1/kernel"); t.bsig = h->p("model/pi/dense_1/bias");
+  t.g_pi = head_g(h, "model/pi", "dense");
+  t.g_vf = head_g(h, "model/values_fn/vf", "vf");
+  t.g_q1 = head_g(h, "model/values_fn/qf1", "qf1");
+  t.g_q2 = head_g(h, "model/values_fn/qf2", "qf2");
+  t.g_ksig = h->g("model/pi/dense_1/kernel"); t.g_bsig = h->g("model/pi/dense_1/bias");
+  t.log_alpha = h->p("model/log_ent_coef"); t.g_log_alpha = h->g("model/log_ent_coef");
+  t.act = h->F[1] + h->feat_dim; t.act_stride = h->FS;
+  t.eps = h->eps; t.rew = h->rew_n; t.done = h->done_n;
+  t.a0_pi = h->a0[0]; t.a0_vf = h->a0[1]; t.a0_q1 = h->a0[2]; t.a0_q2 = h->a0[3];
+  t.dz1_pi = h->dz1[0]; t.dz1_vf = h->dz1[1]; t.dz1_q1 = h->dz1[2]; t.dz1_q2 = h->dz1[3];
+  t.dz0_pi = h->dz0_pi; t.dz0_v3 = h->dz0_v3;
+  t.per_sample = want_per_sample ? h->per_sample : nullptr;
+  t.pi_out = want_per_sample ? h->pi_out : nullptr;
+  t.metrics = h->metrics;
+  return t;
+}
+
+GatherArgs make_gather(b2g_sac* h, bool from_replay, bool with_next) {
+  GatherArgs g{};
+  g.obs = from_replay ? h->r_obs : h->s_obs;
+  g.next_obs = with_next ? (from_replay ? h->r_next : h->s_next) : nullptr;
+  g.act = with_next ? (from_replay ? h->r_act : h->s_act) : nullptr;
+  g.rew = from_replay ? h->r_rew : h->s_rew;
+  g.done = from_replay ? h->r_done : h->s_done;
+  g.indices = from_replay ? h->indices : nullptr;
+  g.mean = h->d_mean; g.var = h->d_istd;
+  g.normc = h->d_normc;
+  g.B = h->B;
+  g.H = h->cnn ? h->Hi : 0; g.W = h->cnn ? h->Wi : h->cfg.obs_dim; g.Cfull = h->cnn ? h->Cimg + 1 : 1;
+  g.scale = h->cnn ? 255.f : 1.f;
+  g.x_obs = h->x_obs; g.x_next = h->x_next;
+  g.F_pi = h->F[0]; g.F_v = h->F[1]; g.F_t = h->F[2]; g.FS = h->FS; g.feat_col = 512;
+  g.rew_out = h->rew_n; g.done_out = h->done_n; g.n_act = h->A;
+  return g;
+}
+
+struct Prof {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;
+  std::vector<std::string> names;
+};
+
+// Issues every launch of one gradient step on h->stream.  Returns the number of launches.
+int issue_step(b2g_sac* h, bool sampled, bool apply, bool want_per_sample, Prof* prof, int* n_launch) {
+  cudaStream_t s = h->stream;
+  int n = 0;
+  auto mark = [&](const char* name) {
+    if (prof && prof->on) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      cudaEventRecord(e, s);
+      prof->ev.push_back(e);
+      prof->names.push_back(name);
+    }
+  };
+  mark("begin");
+  PrepArgs pa{};
+  pa.counters = h->counters; pa.step_consts = h->step_consts; pa.lr = h->d_lr; pa.metrics = h->metrics;
+  pa.indices = h->indices; pa.eps = h->eps; pa.B = h->B; pa.A = h->A; pa.replay_size = nullptr;  /* device counter [5] */
+  pa.seed = h->cfg.seed + 0x9E3779B97F4A7C15ull * (unsigned long long)h->cfg.rank; pa.gen = sampled ? 1 : 0; pa.apply = apply ? 1 : 0;
+  prep_launch(pa, s); ++n; mark("prep");
+  gather_launch(make_gather(h, sampled, true), s); ++n; mark("gather_normalize");
+  CK(cudaMemsetAsync(h->G, 0, (size_t)(h->n_train + MET_COUNT) * sizeof(float), s)); ++n; mark("zero_grads");
+  for (auto& g : h->fwd_groups) { gg_simt_launch(g.dev, (int)g.host.size(), g.total_tiles, s); ++n; mark(g.name.c_str()); }
+  tail_launch(make_tail(h, want_per_sample), s); ++n; mark("heads_tail");
+  for (auto& g : h->bwd_groups) { gg_simt_launch(g.dev, (int)g.host.size(), g.total_tiles, s); ++n; mark(g.name.c_str()); }
+  if (h->cfg.nranks > 1) {
+    // losses/means ride behind the gradients in the same buffer
+    CK(cudaMemcpyAsync(h->G + h->n_train, h->metrics, MET_GN_PI * sizeof(float), cudaMemcpyDeviceToDevice, s)); ++n;
+    int rc = g_nccl.AllReduce(h->G, h->G, (size_t)(h->n_train + MET_COUNT), /*ncclFloat32*/ 7, /*ncclSum*/ 0, h->nccl_comm, s);
+    if (rc != 0) return fail(B2G_ENCCL, std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
+    ++n;
+    CK(cudaMemcpyAsync(h->metrics, h->G + h->n_train, MET_GN_PI * sizeof(float), cudaMemcpyDeviceToDevice, s)); ++n;
+    mark("allreduce");
+  }
+  OptimArgs oa{};
+  oa.P = h->P; oa.Mo = h->Mo; oa.Vo = h->Vo; oa.G = h->G; oa.T = h->P + h->n_train;
+  oa.n_pi = (int)h->n_pi; oa.n_values = (int)h->n_values; oa.n_ent = (int)h->n_ent; oa.n_target = (int)h->n_target;
+  oa.step_consts = h->step_consts; oa.tau = h->cfg.tau; oa.grad_scale = 1.0f / (float)h->cfg.nranks;
+  oa.metrics = h->metrics; oa.apply = apply ? 1 : 0;
+  optim_launch(oa, s); ++n; mark("adam_polyak");
+  CK(cudaGetLastError());
+  if (n_launch) *n_launch = n;
+  return 0;
+}
+
+int set_lr(b2g_sac* h, float lr) {
+  if (lr != h->cur_lr) {
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(h->d_lr, &lr, sizeof(float), cudaMemcpyHostToDevice));
+    h->cur_lr = lr;
+  }
+  return 0;
+}
+
+int fetch_metrics(b2g_sac* h, b2g_sac_metrics* out) {
+  CK(cudaMemcpyAsync(h->h_met, h->metrics, MET_COUNT * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(h->h_cnt, h->counters, 8 * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+  float la = 0.f, gla = 0.f;
+  CK(cudaMemcpyAsync(&la, h->p("model/log_ent_coef"), sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(&gla, h->g("model/log_ent_coef"), sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (!out) return 0;
+  const float inv = 1.0f / (float)h->cfg.nranks;
+  const float* m = h->h_met;
+  out->policy_loss = m[MET_POLICY_LOSS] * inv; out->qf1_loss = m[MET_QF1_LOSS] * inv; out->qf2_loss = m[MET_QF2_LOSS] * inv;
+  out->value_loss = m[MET_VALUE_LOSS] * inv; out->ent_coef_loss = m[MET_ENT_COEF_LOSS] * inv; out->entropy = m[MET_ENTROPY] * inv;
+  out->mean_q1 = m[MET_MEAN_Q1] * inv; out->mean_q2 = m[MET_MEAN_Q2] * inv; out->mean_v = m[MET_MEAN_V] * inv;
+  out->mean_logp = m[MET_MEAN_LOGP] * inv;
+  out->grad_norm_pi = sqrtf(m[MET_GN_PI]); out->grad_norm_values = sqrtf(m[MET_GN_VALUES]);
+  out->grad_ent = gla * inv;
+  out->ent_coef = expf(la);     // value AFTER the update when apply_update != 0 (SB logs the pre-update value)
+  out->n_updates = h->h_cnt[3];
+  return 0;
+}
+
+int find_tensor(const b2g_sac* h, const char* name) {
+  if (!name) return -1;
+  std::string n(name);
+  if (n.size() > 2 && n.compare(n.size() - 2, 2, ":0") == 0) n.resize(n.size() - 2);
+  auto it = h->tindex.find(n);
+  return it == h->tindex.end() ? -1 : it->second;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+const char* b2g_last_error(void) { return g_err.c_str(); }
+int b2g_version(void) { return 100; }
+
+int b2g_nccl_unique_id(void* out128, const char* nccl_lib) {
+  if (!out128) return fail(B2G_EINVAL, "out128 is NULL");
+  if (int rc = load_nccl(nccl_lib)) return rc;
+  int rc = g_nccl.GetUniqueId(out128);
+  if (rc != 0) return fail(B2G_ENCCL, "ncclGetUniqueId failed");
+  return 0;
+}
+
+int b2g_sac_destroy(b2g_sac* h) {
+  if (!h) return 0;
+  cudaSetDevice(h->cfg.device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+  if (h->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->nccl_comm);
+  for (void* q : h->allocs) cudaFree(q);
+  if (h->h_met) cudaFreeHost(h->h_met);
+  if (h->h_cnt) cudaFreeHost(h->h_cnt);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return 0;
+}
+
+int b2g_sac_create(const b2g_sac_cfg* cfg, b2g_sac** out) {
+  if (!cfg || !out) return fail(B2G_EINVAL, "cfg/out is NULL");
+  *out = nullptr;
+  if (cfg->hidden != 64) return fail(B2G_EINVAL, "hidden must be 64 (SAC.layers [64,64], config/gripper_grasp.yaml:81)");
+  if (cfg->n_act < 1 || cfg->n_act > 8) return fail(B2G_EINVAL, "n_act must be in [1,8]");
+  if (cfg->batch < 1 || cfg->buffer_capacity < 1) return fail(B2G_EINVAL, "batch and buffer_capacity must be positive");
+  if (cfg->nranks < 1 || cfg->rank < 0 || cfg->rank >= cfg->nranks) return fail(B2G_EINVAL, "bad rank/nranks");
+  if (cfg->precision != B2G_PREC_FP32_SIMT)
+    return fail(B2G_EINVAL, "precision mode not built in this revision (only B2G_PREC_FP32_SIMT)");
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(B2G_ECUDA, "no such CUDA device");
+  CK(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop{};
+  CK(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10) return fail(B2G_ECUDA, std::string("libb200grasp is built for sm_100a only; found ") + prop.name);
+
+  b2g_sac* h = new b2g_sac();
+  h->cfg = *cfg;
+  h->cfg.nccl_id = nullptr; h->cfg.nccl_lib = nullptr;
+  h->cnn = cfg->obs_h > 0;
+  h->B = cfg->batch; h->A = cfg->n_act; h->H = cfg->hidden;
+  if (h->cnn) {
+    if (cfg->obs_c < 2) { delete h; return fail(B2G_EINVAL, "CNN policy needs obs_c >= 2 (image planes + feature plane)"); }
+    h->Cimg = cfg->obs_c - 1; h->Hi = cfg->obs_h; h->Wi = cfg->obs_w;
+    h->H1 = (h->Hi - 8) / 4 + 1; h->W1 = (h->Wi - 8) / 4 + 1;
+    h->H2 = (h->H1 - 4) / 2 + 1; h->W2 = (h->W1 - 4) / 2 + 1;
+    h->H3 = h->H2 - 2; h->W3 = h->W2 - 2;
+    if (h->H3 * h->W3 * 64 != 1024 || (h->Wi * h->Cimg) % 4 != 0) {
+      delete h;
+      return fail(B2G_EINVAL, "observation size must give a 4x4x64 conv3 output (64x64 input; cnn_fc1/w is (1024,512))");
+    }
+    h->E = h->Hi * h->Wi * cfg->obs_c;
+    h->feat_dim = 513;
+  } else {
+    if (cfg->obs_dim < 1) { delete h; return fail(B2G_EINVAL, "obs_dim must be positive for the MLP policy"); }
+    h->E = cfg->obs_dim;
+    h->feat_dim = cfg->obs_dim;
+  }
+  h->FS = (h->feat_dim + h->A + 7) / 8 * 8;
+  auto bail = [&](int rc) { std::string keep = g_err; b2g_sac_destroy(h); g_err = keep; return rc; };
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(B2G_ECUDA, "cudaStreamCreate failed"));
+  cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1);
+  build_params(h);
+  int rc = 0;
+  const int B = h->B;
+#define DA(ptr, count) if ((rc = dalloc(h, &(ptr), (size_t)(count)))) return bail(rc)
+  DA(h->P, h->n_all); DA(h->Mo, h->n_train); DA(h->Vo, h->n_train); DA(h->G, h->n_train + MET_COUNT);
+  DA(h->metrics, MET_COUNT); DA(h->counters, 8); DA(h->step_consts, 4); DA(h->d_lr, 1);
+  const int64_t cap = cfg->buffer_capacity;
+  DA(h->r_obs, cap * h->E); DA(h->r_next, cap * h->E); DA(h->r_act, cap * h->A); DA(h->r_rew, cap); DA(h->r_done, cap);
+  DA(h->d_mean, h->E); DA(h->d_istd, h->E); DA(h->d_normc, 8);
+  DA(h->s_obs, (size_t)B * h->E); DA(h->s_next, (size_t)B * h->E); DA(h->s_act, B * h->A); DA(h->s_rew, B); DA(h->s_done, B);
+  if (h->cnn) {
+    DA(h->x_obs, (size_t)B * h->Hi * h->Wi * h->Cimg); DA(h->x_next, (size_t)B * h->Hi * h->Wi * h->Cimg);
+    for (int n = 0; n < 3; ++n) {
+      DA(h->h1[n], (size_t)B * h->H1 * h->W1 * 32); DA(h->h2[n], (size_t)B * h->H2 * h->W2 * 64); DA(h->h3[n], (size_t)B * 1024);
+    }
+    for (int n = 0; n < 2; ++n) {
+      DA(h->dZ4[n], (size_t)B * 512); DA(h->dZ3p[n], (size_t)B * (h->H3 + 4) * (h->W3 + 4) * 64);
+      DA(h->dZ2p[n], (size_t)B * (h->H2 + 3) * (h->W2 + 3) * 64); DA(h->dZ1[n], (size_t)B * h->H1 * h->W1 * 32);
+    }
+  }
+  for (int n = 0; n < 3; ++n) DA(h->F[n], (size_t)B * h->FS);
+  for (int q = 0; q < 5; ++q) DA(h->z0[q], B * h->H);
+  for (int q = 0; q < 4; ++q) { DA(h->a0[q], B * h->H); DA(h->dz1[q], B * h->H); }
+  DA(h->dz0_pi, B * h->H); DA(h->dz0_v3, B * 3 * h->H);
+  DA(h->per_sample, 7 * B); DA(h->pi_out, B * h->A); DA(h->eps, B * h->A + 4); DA(h->rew_n, B); DA(h->done_n, B);
+  DA(h->indices, B + 4);
+#undef DA
+  if (cudaMallocHost((void**)&h->h_met, MET_COUNT * sizeof(float)) != cudaSuccess ||
+      cudaMallocHost((void**)&h->h_cnt, 8 * sizeof(long long)) != cudaSuccess)
+    return bail(fail(B2G_ECUDA, "cudaMallocHost failed"));
+  // identity normalisation until b2g_set_norm_stats is called
+  {
+    std::vector<double> ones(h->E, 1.0);
+    if (cudaMemcpyAsync(h->d_istd, ones.data(), h->E * sizeof(double), cudaMemcpyHostToDevice, h->stream) != cudaSuccess ||
+        cudaStreamSynchronize(h->stream) != cudaSuccess)
+      return bail(fail(B2G_ECUDA, "init copy failed"));
+  }
+  if ((rc = build_groups(h))) return bail(rc);
+  if (cfg->nranks > 1) {
+    if (!cfg->nccl_id) return bail(fail(B2G_EINVAL, "nranks > 1 needs nccl_id"));
+    if ((rc = load_nccl(cfg->nccl_lib))) return bail(rc);
+    UId id;
+    memcpy(id.b, cfg->nccl_id, 128);
+    int nrc = g_nccl.CommInitRank(&h->nccl_comm, cfg->nranks, id, cfg->rank);
+    if (nrc != 0) return bail(fail(B2G_ENCCL, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "?")));
+  }
+  const char* ng = getenv("B2G_NO_GRAPH");
+  h->use_graph = !(ng && ng[0] == '1');
+  if (cudaStreamSynchronize(h->stream) != cudaSuccess) return bail(fail(B2G_ECUDA, "create: sync failed"));
+  *out = h;
+  return 0;
+}
+
+int b2g_sync(b2g_sac* h) {
+  if (!h) return fail(B2G_EINVAL, "NULL handle");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int b2g_param_count(const b2g_sac* h) { return h ? (int)h->tensors.size() : 0; }
+
+int b2g_param_info(const b2g_sac* h, int idx, const char** name, int64_t* numel, int32_t* ndim, int64_t shape[4]) {
+  if (!h || idx < 0 || idx >= (int)h->tensors.size()) return fail(B2G_EINVAL, "bad tensor index");
+  const Tensor& t = h->tensors[idx];
+  if (name) *name = t.name.c_str();
+  if (numel) *numel = t.numel;
+  if (ndim) *ndim = t.ndim;
+  if (shape) for (int i = 0; i < 4; ++i) shape[i] = t.shape[i];
+  return 0;
+}
+
+static int copy_tensor(b2g_sac* h, const char* name, float* arena, float* host, size_t numel, bool to_host, bool trainable_only) {
+  if (!h || !host) return fail(B2G_EINVAL, "NULL argument");
+  const int i = find_tensor(h, name);
+  if (i < 0) return fail(B2G_EINVAL, std::string("unknown variable: ") + (name ? name : "(null)"));
+  const Tensor& t = h->tensors[i];
+  if ((int64_t)numel != t.numel) return fail(B2G_EINVAL, std::string("size mismatch for ") + t.name);
+  if (trainable_only && t.group == 3) return fail(B2G_EINVAL, std::string("not a trainable variable: ") + t.name);
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaStreamSynchronize(h->stream));
+  if (to_host) CK(cudaMemcpy(host, arena + t.off, numel * sizeof(float), cudaMemcpyDeviceToHost));
+  else CK(cudaMemcpy(arena + t.off, host, numel * sizeof(float), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int b2g_get_param(b2g_sac* h, const char* name, float* dst, size_t numel) { return copy_tensor(h, name, h ? h->P : nullptr, dst, numel, true, false); }
+int b2g_set_param(b2g_sac* h, const char* name, const float* src, size_t numel) {
+  return copy_tensor(h, name, h ? h->P : nullptr, const_cast<float*>(src), numel, false, false);
+}
+int b2g_get_grad(b2g_sac* h, const char* name, float* dst, size_t numel) {
+  int rc = copy_tensor(h, name, h ? h->G : nullptr, dst, numel, true, true);
+  if (rc == 0 && h->cfg.nranks > 1) for (size_t i = 0; i < numel; ++i) dst[i] /= (float)h->cfg.nranks;
+  return rc;
+}
+int b2g_get_adam(b2g_sac* h, const char* name, float* m, float* v, size_t numel) {
+  if (int rc = copy_tensor(h, name, h ? h->Mo : nullptr, m, numel, true, true)) return rc;
+  return copy_tensor(h, name, h->Vo, v, numel, true, true);
+}
+int b2g_reset_optimizer(b2g_sac* h) {
+  if (!h) return fail(B2G_EINVAL, "NULL handle");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaMemsetAsync(h->Mo, 0, h->n_train * sizeof(float), h->stream));
+  CK(cudaMemsetAsync(h->Vo, 0, h->n_train * sizeof(float), h->stream));
+  CK(cudaMemsetAsync(h->counters, 0, 4 * sizeof(long long), h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int b2g_replay_add(b2g_sac* h, const float* obs, const float* act, const float* rew, const float* next_obs, const float* done,
+                   int64_t n) {
+  if (!h || !obs || !act || !rew || !next_obs || !done || n < 0) return fail(B2G_EINVAL, "NULL argument");
+  CK(cudaSetDevice(h->cfg.device));
+  const int64_t cap = h->cfg.buffer_capacity;
+  int64_t done_n = 0;
+  while (done_n < n) {
+    const int64_t chunk = std::min(n - done_n, cap - h->r_pos);
+    const size_t E = h->E, A = h->A;
+    CK(cudaMemcpyAsync(h->r_obs + h->r_pos * E, obs + done_n * E, chunk * E * sizeof(float), cudaMemcpyDefault, h->stream));
+    CK(cudaMemcpyAsync(h->r_next + h->r_pos * E, next_obs + done_n * E, chunk * E * sizeof(float), cudaMemcpyDefault, h->stream));
+    CK(cudaMemcpyAsync(h->r_act + h->r_pos * A, act + done_n * A, chunk * A * sizeof(float), cudaMemcpyDefault, h->stream));
+    CK(cudaMemcpyAsync(h->r_rew + h->r_pos, rew + done_n, chunk * sizeof(float), cudaMemcpyDefault, h->stream));
+    CK(cudaMemcpyAsync(h->r_done + h->r_pos, done + done_n, chunk * sizeof(float), cudaMemcpyDefault, h->stream));
+    h->r_pos = (h->r_pos + chunk) % cap;
+    h->r_size = std::min(cap, h->r_size + chunk);
+    done_n += chunk;
+  }
+  h->h_cnt[7] = h->r_size;
+  CK(cudaMemcpyAsync(h->counters + 5, h->h_cnt + 7, sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));     // host arrays are caller-owned: copied before return
+  return 0;
+}
+
+int64_t b2g_replay_size(const b2g_sac* h) { return h ? h->r_size : 0; }
+
+int b2g_set_norm_stats(b2g_sac* h, const double* obs_mean, const double* obs_var, double ret_var, double clip_obs, double clip_rew,
+                       double eps, int norm_obs, int norm_reward) {
+  if (!h) return fail(B2G_EINVAL, "NULL handle");
+  if (norm_obs && (!obs_mean || !obs_var)) return fail(B2G_EINVAL, "norm_obs needs obs_mean/obs_var");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaStreamSynchronize(h->stream));
+  if (norm_obs) {
+    std::vector<double> istd(h->E);
+    for (int i = 0; i < h->E; ++i) istd[i] = 1.0 / sqrt(obs_var[i] + eps);
+    CK(cudaMemcpy(h->d_mean, obs_mean, h->E * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->d_istd, istd.data(), h->E * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  h->ret_istd = 1.0 / sqrt(ret_var + eps);
+  h->clip_obs = clip_obs; h->clip_rew = clip_rew; h->norm_obs = norm_obs; h->norm_rew = norm_reward;
+  const double nc[8] = {h->ret_istd, clip_obs, clip_rew, (double)norm_obs, (double)norm_reward, 0, 0, 0};
+  CK(cudaMemcpy(h->d_normc, nc, sizeof(nc), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+static int ensure_graph(b2g_sac* h) {
+  if (h->graph_exec) return 0;
+  cudaGraph_t graph = nullptr;
+  CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+  int n = 0;
+  int rc = issue_step(h, true, true, false, nullptr, &n);
+  cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+  if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+  if (e != cudaSuccess) return fail(B2G_ECUDA, std::string("graph capture failed: ") + cudaGetErrorString(e));
+  e = cudaGraphInstantiate(&h->graph_exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) return fail(B2G_ECUDA, std::string("graph instantiate failed: ") + cudaGetErrorString(e));
+  h->launches = n;
+  return 0;
+}
+
+int b2g_sac_step_async(b2g_sac* h, int n_steps, float lr) {
+  if (!h || n_steps < 0) return fail(B2G_EINVAL, "bad argument");
+  if (h->r_size < 1) return fail(B2G_ESTATE, "replay buffer is empty");
+  CK(cudaSetDevice(h->cfg.device));
+  if (int rc = set_lr(h, lr)) return rc;
+  if (h->use_graph) if (int rc = ensure_graph(h)) return rc;
+  CK(cudaEventRecord(h->ev0, h->stream));
+  for (int i = 0; i < n_steps; ++i) {
+    if (h->use_graph) CK(cudaGraphLaunch(h->graph_exec, h->stream));
+    else if (int rc = issue_step(h, true, true, false, nullptr, &h->launches)) return rc;
+  }
+  CK(cudaEventRecord(h->ev1, h->stream));
+  return 0;
+}
+
+int b2g_sac_step(b2g_sac* h, int n_steps, float lr, b2g_sac_metrics* out) {
+  if (int rc = b2g_sac_step_async(h, n_steps, lr)) return rc;
+  if (int rc = fetch_metrics(h, out)) return rc;
+  cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1);
+  return 0;
+}
+
+int b2g_sac_step_explicit(b2g_sac* h, const float* obs, const float* act, const float* rew, const float* next_obs, const float* done,
+                          const float* eps, float lr, int apply_update, b2g_sac_metrics* out, float* per_sample, float* pi_out) {
+  if (!h || !obs || !act || !rew || !next_obs || !done || !eps) return fail(B2G_EINVAL, "NULL argument");
+  CK(cudaSetDevice(h->cfg.device));
+  if (int rc = set_lr(h, lr)) return rc;
+  const size_t B = h->B, E = h->E, A = h->A;
+  CK(cudaEventRecord(h->ev0, h->stream));
+  CK(cudaMemcpyAsync(h->s_obs, obs, B * E * sizeof(float), cudaMemcpyDefault, h->stream));
+  CK(cudaMemcpyAsync(h->s_next, next_obs, B * E * sizeof(float), cudaMemcpyDefault, h->stream));
+  CK(cudaMemcpyAsync(h->s_act, act, B * A * sizeof(float), cudaMemcpyDefault, h->stream));
+  CK(cudaMemcpyAsync(h->s_rew, rew, B * sizeof(float), cudaMemcpyDefault, h->stream));
+  CK(cudaMemcpyAsync(h->s_done, done, B * sizeof(float), cudaMemcpyDefault, h->stream));
+  CK(cudaMemcpyAsync(h->eps, eps, B * A * sizeof(float), cudaMemcpyDefault, h->stream));
+  int n = 0;
+  if (int rc = issue_step(h, false, apply_update != 0, true, nullptr, &n)) return rc;
+  CK(cudaEventRecord(h->ev1, h->stream));
+  if (per_sample) CK(cudaMemcpyAsync(per_sample, h->per_sample, 7 * B * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  if (pi_out) CK(cudaMemcpyAsync(pi_out, h->pi_out, B * A * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  if (int rc = fetch_metrics(h, out)) return rc;
+  cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1);
+  return 0;
+}
+
+int b2g_sac_act(b2g_sac* h, const float* obs, int n, int deterministic, float* act_out) {
+  if (!h || !obs || !act_out || n < 0) return fail(B2G_EINVAL, "bad argument");
+  CK(cudaSetDevice(h->cfg.device));
+  const size_t E = h->E, A = h->A;
+  for (int done_n = 0; done_n < n; done_n += h->B) {
+    const int chunk = std::min(h->B, n - done_n);
+    CK(cudaMemcpyAsync(h->s_obs, obs + (size_t)done_n * E, chunk * E * sizeof(float), cudaMemcpyDefault, h->stream));
+    PrepArgs pa{};
+    pa.counters = h->counters; pa.step_consts = h->step_consts; pa.lr = h->d_lr; pa.metrics = h->metrics;
+    pa.indices = h->indices; pa.eps = h->eps; pa.B = h->B; pa.A = h->A; pa.replay_size = nullptr;
+    pa.seed = h->cfg.seed ^ 0xA5A5A5A5DEADBEEFull; pa.gen = deterministic ? 0 : 1; pa.apply = 0;
+    prep_launch(pa, h->stream);
+    GatherArgs g = make_gather(h, false, false);
+    g.indices = nullptr;
+    gather_launch(g, h->stream);
+    for (auto& gr : h->act_groups) gg_simt_launch(gr.dev, (int)gr.host.size(), gr.total_tiles, h->stream);
+    b2g::act_launch(make_tail(h, false), chunk, deterministic, h->pi_out, h->stream);
+    CK(cudaMemcpyAsync(act_out + (size_t)done_n * A, h->pi_out, chunk * A * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int b2g_launches_per_step(const b2g_sac* h) {
+  if (!h) return 0;
+  if (h->launches) return h->launches;
+  // prep + gather + memset + groups + tail + optim (+3 with a collective)
+  return 3 + (int)h->fwd_groups.size() + 1 + (int)h->bwd_groups.size() + 1 + (h->cfg.nranks > 1 ? 3 : 0);
+}
+
+float b2g_last_step_ms(const b2g_sac* h) { return h ? h->last_ms : 0.f; }
+
+int b2g_profile_step(b2g_sac* h, float lr, const char** names, float* ms, int cap) {
+  if (!h || !names || !ms) return fail(B2G_EINVAL, "NULL argument");
+  if (h->r_size < 1) return fail(B2G_ESTATE, "replay buffer is empty");
+  CK(cudaSetDevice(h->cfg.device));
+  if (int rc = set_lr(h, lr)) return rc;
+  Prof prof;
+  prof.on = true;
+  int n = 0;
+  if (int rc = issue_step(h, true, true, false, &prof, &n)) return rc;
+  CK(cudaStreamSynchronize(h->stream));
+  h->prof_names = prof.names;
+  int k = 0;
+  for (size_t i = 1; i < prof.ev.size() && k < cap; ++i, ++k) {
+    cudaEventElapsedTime(&ms[k], prof.ev[i - 1], prof.ev[i]);
+    names[k] = h->prof_names[i].c_str();
+  }
+  for (auto e : prof.ev) cudaEventDestroy(e);
+  return k;
+}
+
+}  // extern "C"

@@ -1,0 +1,315 @@
+// Fused head "tail": everything between the fc0 contractions and their gradients, one warp per
+// sample (coalesced HBM/L2 reads, warp-shuffle reductions, no tensor cores: these are 64-wide
+// latency-bound layers).
+//
+// Restates [SB2] sac/policies.py make_actor / make_critics after the first dense layer, and
+// [SB2] sac/sac.py setup_model's loss block:
+//   actor  : a0=relu(z0+b0) -> fc1 -> mu, log_std(clip) -> u=mu+eps*std -> pi=tanh(u), logp
+//   critics: vf, qf1, qf2 at the replay action; qf1, qf2 at pi (fc0 reused: z0(pi)=z0(a)+(pi-a)K0[act rows])
+//   target : vf_target(next)
+//   losses : qf1/qf2/value/policy/ent_coef + their backward seeds, back-propagated to dz0 per head
+// Outputs feed the gather-GEMM engine (fc0 wgrad/dgrad); the tiny output-layer gradients are
+// reduced in shared memory and added to the gradient arena here.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace b2g {
+namespace {
+constexpr int H = 64, LD = 65, WARPS = 8, AMAX = 8;
+constexpr float EPSF = 1e-6f, LS_MAX = 2.0f, LS_MIN = -20.0f;
+
+struct V2 { float lo, hi; };
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ V2 relu2(V2 a) { return V2{fmaxf(a.lo, 0.f), fmaxf(a.hi, 0.f)}; }
+
+// out[j] = bias[j] + sum_i a[i] * W[i][j]
+__device__ __forceinline__ V2 fwd64(const float* __restrict__ Ws, const float* __restrict__ bias, V2 a, int lane) {
+  V2 o{bias[lane], bias[lane + 32]};
+#pragma unroll 8
+  for (int i = 0; i < 32; ++i) {
+    const float ai = __shfl_sync(0xffffffffu, a.lo, i);
+    o.lo = fmaf(ai, Ws[i * LD + lane], o.lo);
+    o.hi = fmaf(ai, Ws[i * LD + lane + 32], o.hi);
+  }
+#pragma unroll 8
+  for (int i = 0; i < 32; ++i) {
+    const float ai = __shfl_sync(0xffffffffu, a.hi, i);
+    o.lo = fmaf(ai, Ws[(i + 32) * LD + lane], o.lo);
+    o.hi = fmaf(ai, Ws[(i + 32) * LD + lane + 32], o.hi);
+  }
+  return o;
+}
+// out[i] = sum_j dz[j] * W[i][j]
+__device__ __forceinline__ V2 bwd64(const float* __restrict__ Ws, V2 dz, int lane) {
+  V2 o{0.f, 0.f};
+#pragma unroll 8
+  for (int j = 0; j < 32; ++j) {
+    const float dj = __shfl_sync(0xffffffffu, dz.lo, j);
+    o.lo = fmaf(dj, Ws[lane * LD + j], o.lo);
+    o.hi = fmaf(dj, Ws[(lane + 32) * LD + j], o.hi);
+  }
+#pragma unroll 8
+  for (int j = 0; j < 32; ++j) {
+    const float dj = __shfl_sync(0xffffffffu, dz.hi, j);
+    o.lo = fmaf(dj, Ws[lane * LD + j + 32], o.lo);
+    o.hi = fmaf(dj, Ws[(lane + 32) * LD + j + 32], o.hi);
+  }
+  return o;
+}
+__device__ __forceinline__ V2 ld2(const float* p, int lane) { return V2{p[lane], p[lane + 32]}; }
+__device__ __forceinline__ void st2(float* p, int lane, V2 v) { p[lane] = v.lo; p[lane + 32] = v.hi; }
+// scalar head output: sum_i a[i]*ko[i] + bo
+__device__ __forceinline__ float out1(const float* __restrict__ ko, const float* __restrict__ bo, V2 a, int lane) {
+  return warp_sum(a.lo * ko[lane] + a.hi * ko[lane + 32]) + bo[0];
+}
+
+enum { S_PI = 0, S_VF, S_Q1, S_Q2, S_VT, S_NW };
+
+__global__ void __launch_bounds__(WARPS * 32) tail_kernel(TailArgs t) {
+  extern __shared__ float smem[];
+  float* Wk1 = smem;                              // S_NW x [64][65]
+  float* acc = Wk1 + S_NW * H * LD;               // output-layer gradient accumulators
+  // acc layout: kmu[64*A] ksig[64*A] bmu[A] bsig[A] | vf ko[64] bo | q1 ko[64] bo | q2 ko[64] bo
+  const int A = t.A;
+  const int n_acc = 2 * H * A + 2 * A + 3 * (H + 1);
+  float* red = acc + n_acc;                       // MET_COUNT + 1 (g_log_alpha)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  const float* k1s[S_NW] = {t.pi.k1, t.vf.k1, t.q1.k1, t.q2.k1, t.vt.k1};
+  for (int w = 0; w < S_NW; ++w)
+    for (int i = tid; i < H * H; i += blockDim.x) Wk1[w * H * LD + (i >> 6) * LD + (i & 63)] = k1s[w][i];
+  for (int i = tid; i < n_acc + MET_COUNT + 1; i += blockDim.x) acc[i] = 0.f;
+  __syncthreads();
+
+  float* a_kmu = acc;
+  float* a_ksig = a_kmu + H * A;
+  float* a_bmu = a_ksig + H * A;
+  float* a_bsig = a_bmu + A;
+  float* a_vf = a_bsig + A;
+  float* a_q1 = a_vf + H + 1;
+  float* a_q2 = a_q1 + H + 1;
+
+  const float invB = 1.0f / (float)t.grad_scale_B;
+  const float log_alpha = t.log_alpha[0];
+  const float alpha = expf(log_alpha);
+
+  for (int b = blockIdx.x * WARPS + warp; b < t.B; b += gridDim.x * WARPS) {
+    // ------------------------------------------------------------------ actor forward
+    const V2 a0_pi = relu2(V2{t.z0_pi[b * H + lane] + t.pi.b0[lane], t.z0_pi[b * H + lane + 32] + t.pi.b0[lane + 32]});
+    st2(t.a0_pi + b * H, lane, a0_pi);
+    const V2 g = relu2(fwd64(Wk1 + S_PI * H * LD, t.pi.b1, a0_pi, lane));
+    float mu[AMAX], ls_raw[AMAX], ls[AMAX], sd[AMAX], pi[AMAX], tt[AMAX], epsn[AMAX], actv[AMAX];
+    float logp = 0.f, ent = 0.f;
+#pragma unroll
+    for (int a = 0; a < AMAX; ++a) {
+      if (a < A) {
+        mu[a] = warp_sum(g.lo * t.pi.ko[lane * A + a] + g.hi * t.pi.ko[(lane + 32) * A + a]) + t.pi.bo[a];
+        ls_raw[a] = warp_sum(g.lo * t.ksig[lane * A + a] + g.hi * t.ksig[(lane + 32) * A + a]) + t.bsig[a];
+        ls[a] = fminf(fmaxf(ls_raw[a], LS_MIN), LS_MAX);
+        sd[a] = expf(ls[a]);
+        epsn[a] = t.eps[b * A + a];
+        actv[a] = t.act[(size_t)b * t.act_stride + a];
+        const float u = mu[a] + epsn[a] * sd[a];
+        tt[a] = (u - mu[a]) / (sd[a] + EPSF);
+        pi[a] = tanhf(u);
+        logp += -0.5f * (tt[a] * tt[a] + 2.f * ls[a] + 1.8378770664093453f) - logf(1.f - pi[a] * pi[a] + EPSF);
+        ent += ls[a] + 1.4189385332046727f;
+      }
+    }
+    // ------------------------------------------------------------------ critics forward
+    const V2 a0_vf = relu2(V2{t.z0_vf[b * H + lane] + t.vf.b0[lane], t.z0_vf[b * H + lane + 32] + t.vf.b0[lane + 32]});
+    const V2 a1_vf = relu2(fwd64(Wk1 + S_VF * H * LD, t.vf.b1, a0_vf, lane));
+    const float v = out1(t.vf.ko, t.vf.bo, a1_vf, lane);
+    const V2 a0_vt = relu2(V2{t.z0_vt[b * H + lane] + t.vt.b0[lane], t.z0_vt[b * H + lane + 32] + t.vt.b0[lane + 32]});
+    const V2 a1_vt = relu2(fwd64(Wk1 + S_VT * H * LD, t.vt.b1, a0_vt, lane));
+    const float v_targ = out1(t.vt.ko, t.vt.bo, a1_vt, lane);
+
+    V2 z0q1 = ld2(t.z0_q1 + b * H, lane), z0q2 = ld2(t.z0_q2 + b * H, lane);
+    V2 z0q1p = z0q1, z0q2p = z0q2;   // fc0 pre-activation at pi: linear in the action columns
+#pragma unroll
+    for (int a = 0; a < AMAX; ++a) {
+      if (a < A) {
+        const float dlt = pi[a] - actv[a];
+        const float* r1 = t.q1.k0 + (size_t)(t.feat_dim + a) * H;
+        const float* r2 = t.q2.k0 + (size_t)(t.feat_dim + a) * H;
+        z0q1p.lo = fmaf(dlt, r1[lane], z0q1p.lo); z0q1p.hi = fmaf(dlt, r1[lane + 32], z0q1p.hi);
+        z0q2p.lo = fmaf(dlt, r2[lane], z0q2p.lo); z0q2p.hi = fmaf(dlt, r2[lane + 32], z0q2p.hi);
+      }
+    }
+    const V2 b0q1 = ld2(t.q1.b0, lane), b0q2 = ld2(t.q2.b0, lane);
+    const V2 a0_q1 = relu2(V2{z0q1.lo + b0q1.lo, z0q1.hi + b0q1.hi});
+    const V2 a0_q2 = relu2(V2{z0q2.lo + b0q2.lo, z0q2.hi + b0q2.hi});
+    const V2 a0_q1p = relu2(V2{z0q1p.lo + b0q1.lo, z0q1p.hi + b0q1.hi});
+    const V2 a0_q2p = relu2(V2{z0q2p.lo + b0q2.lo, z0q2p.hi + b0q2.hi});
+    const V2 a1_q1 = relu2(fwd64(Wk1 + S_Q1 * H * LD, t.q1.b1, a0_q1, lane));
+    const V2 a1_q2 = relu2(fwd64(Wk1 + S_Q2 * H * LD, t.q2.b1, a0_q2, lane));
+    const V2 a1_q1p = relu2(fwd64(Wk1 + S_Q1 * H * LD, t.q1.b1, a0_q1p, lane));
+    const V2 a1_q2p = relu2(fwd64(Wk1 + S_Q2 * H * LD, t.q2.b1, a0_q2p, lane));
+    const float q1 = out1(t.q1.ko, t.q1.bo, a1_q1, lane), q2 = out1(t.q2.ko, t.q2.bo, a1_q2, lane);
+    const float q1p = out1(t.q1.ko, t.q1.bo, a1_q1p, lane), q2p = out1(t.q2.ko, t.q2.bo, a1_q2p, lane);
+
+    // ------------------------------------------------------------------ losses + seeds
+    const float q_backup = t.rew[b] + (1.f - t.done[b]) * t.gamma * v_targ;
+    const float v_backup = fminf(q1p, q2p) - alpha * logp;
+    const float e1 = q1 - q_backup, e2 = q2 - q_backup, ev = v - v_backup;
+    if (lane == 0) {
+      atomicAdd(&red[MET_POLICY_LOSS], (alpha * logp - q1p) * invB);
+      atomicAdd(&red[MET_QF1_LOSS], 0.5f * e1 * e1 * invB);
+      atomicAdd(&red[MET_QF2_LOSS], 0.5f * e2 * e2 * invB);
+      atomicAdd(&red[MET_VALUE_LOSS], 0.5f * ev * ev * invB);
+      atomicAdd(&red[MET_ENT_COEF_LOSS], -log_alpha * (logp + t.target_entropy) * invB);
+      atomicAdd(&red[MET_ENTROPY], ent * invB);
+      atomicAdd(&red[MET_MEAN_Q1], q1 * invB);
+      atomicAdd(&red[MET_MEAN_Q2], q2 * invB);
+      atomicAdd(&red[MET_MEAN_V], v * invB);
+      atomicAdd(&red[MET_MEAN_LOGP], logp * invB);
+      atomicAdd(&red[MET_COUNT], -(logp + t.target_entropy) * invB);   // d ent_coef_loss / d log_alpha
+      if (t.per_sample) {
+        float* ps = t.per_sample;
+        ps[0 * t.B + b] = q1; ps[1 * t.B + b] = q2; ps[2 * t.B + b] = v; ps[3 * t.B + b] = logp;
+        ps[4 * t.B + b] = v_targ; ps[5 * t.B + b] = q1p; ps[6 * t.B + b] = q2p;
+      }
+    }
+    if (t.pi_out && lane < A) {
+      float pv = 0.f;
+#pragma unroll
+      for (int a = 0; a < AMAX; ++a) if (a == lane) pv = pi[a];
+      t.pi_out[b * A + lane] = pv;
+    }
+
+    // ------------------------------------------------------------------ value heads backward
+    auto value_head_bwd = [&](float dout, const HeadW& w, const float* Ws, V2 a0, V2 a1, float* accv, float* dz1_out,
+                              float* dz0_out) {
+      // output layer grads
+      atomicAdd(&accv[lane], a1.lo * dout);
+      atomicAdd(&accv[lane + 32], a1.hi * dout);
+      if (lane == 0) atomicAdd(&accv[H], dout);
+      V2 dz1{a1.lo > 0.f ? dout * w.ko[lane] : 0.f, a1.hi > 0.f ? dout * w.ko[lane + 32] : 0.f};
+      st2(dz1_out, lane, dz1);
+      V2 da0 = bwd64(Ws, dz1, lane);
+      V2 dz0{a0.lo > 0.f ? da0.lo : 0.f, a0.hi > 0.f ? da0.hi : 0.f};
+      st2(dz0_out, lane, dz0);
+    };
+    st2(t.a0_vf + b * H, lane, a0_vf);
+    st2(t.a0_q1 + b * H, lane, a0_q1);
+    st2(t.a0_q2 + b * H, lane, a0_q2);
+    value_head_bwd(ev * invB, t.vf, Wk1 + S_VF * H * LD, a0_vf, a1_vf, a_vf, t.dz1_vf + b * H, t.dz0_v3 + (size_t)b * 3 * H);
+    value_head_bwd(e1 * invB, t.q1, Wk1 + S_Q1 * H * LD, a0_q1, a1_q1, a_q1, t.dz1_q1 + b * H, t.dz0_v3 + (size_t)b * 3 * H + H);
+    value_head_bwd(e2 * invB, t.q2, Wk1 + S_Q2 * H * LD, a0_q2, a1_q2, a_q2, t.dz1_q2 + b * H, t.dz0_v3 + (size_t)b * 3 * H + 2 * H);
+
+    // ------------------------------------------------------------------ policy backward
+    // d(-Q1(s,pi))/d pi through qf1 with its weights held constant
+    float dpi[AMAX];
+    {
+      const float dout = -invB;
+      V2 dz1{a1_q1p.lo > 0.f ? dout * t.q1.ko[lane] : 0.f, a1_q1p.hi > 0.f ? dout * t.q1.ko[lane + 32] : 0.f};
+      V2 da0 = bwd64(Wk1 + S_Q1 * H * LD, dz1, lane);
+      V2 dz0{a0_q1p.lo > 0.f ? da0.lo : 0.f, a0_q1p.hi > 0.f ? da0.hi : 0.f};
+#pragma unroll
+      for (int a = 0; a < AMAX; ++a) {
+        if (a < A) {
+          const float* r1 = t.q1.k0 + (size_t)(t.feat_dim + a) * H;
+          dpi[a] = warp_sum(dz0.lo * r1[lane] + dz0.hi * r1[lane + 32]);
+        }
+      }
+    }
+    float dmu[AMAX], dls[AMAX];
+    V2 dg{0.f, 0.f};
+#pragma unroll
+    for (int a = 0; a < AMAX; ++a) {
+      if (a < A) {
+        const float one_m = 1.f - pi[a] * pi[a];
+        const float du = (alpha * invB) * 2.f * pi[a] * one_m / (one_m + EPSF) + dpi[a] * one_m;
+        dmu[a] = du;
+        const float sp = sd[a] + EPSF;
+        float d = du * epsn[a] * sd[a] + (alpha * invB) * (-tt[a] * epsn[a] * sd[a] * EPSF / (sp * sp) - 1.f);
+        dls[a] = (ls_raw[a] >= LS_MIN && ls_raw[a] <= LS_MAX) ? d : 0.f;
+        atomicAdd(&a_kmu[lane * A + a], g.lo * dmu[a]);
+        atomicAdd(&a_kmu[(lane + 32) * A + a], g.hi * dmu[a]);
+        atomicAdd(&a_ksig[lane * A + a], g.lo * dls[a]);
+        atomicAdd(&a_ksig[(lane + 32) * A + a], g.hi * dls[a]);
+        if (lane == 0) { atomicAdd(&a_bmu[a], dmu[a]); atomicAdd(&a_bsig[a], dls[a]); }
+        dg.lo += dmu[a] * t.pi.ko[lane * A + a] + dls[a] * t.ksig[lane * A + a];
+        dg.hi += dmu[a] * t.pi.ko[(lane + 32) * A + a] + dls[a] * t.ksig[(lane + 32) * A + a];
+      }
+    }
+    {
+      V2 dz1{g.lo > 0.f ? dg.lo : 0.f, g.hi > 0.f ? dg.hi : 0.f};
+      st2(t.dz1_pi + b * H, lane, dz1);
+      V2 da0 = bwd64(Wk1 + S_PI * H * LD, dz1, lane);
+      V2 dz0{a0_pi.lo > 0.f ? da0.lo : 0.f, a0_pi.hi > 0.f ? da0.hi : 0.f};
+      st2(t.dz0_pi + b * H, lane, dz0);
+    }
+    // a1 (= g etc.) needed by the fc1 wgrad contractions: store over a0? no -- fc1 wgrad uses a0 (its input)
+  }
+  __syncthreads();
+  // ---- CTA -> global
+  for (int i = tid; i < H * A; i += blockDim.x) {
+    atomicAdd(t.g_pi.ko + i, a_kmu[i]);
+    atomicAdd(t.g_ksig + i, a_ksig[i]);
+  }
+  if (tid < A) { atomicAdd(t.g_pi.bo + tid, a_bmu[tid]); atomicAdd(t.g_bsig + tid, a_bsig[tid]); }
+  if (tid < H) {
+    atomicAdd(t.g_vf.ko + tid, a_vf[tid]); atomicAdd(t.g_q1.ko + tid, a_q1[tid]); atomicAdd(t.g_q2.ko + tid, a_q2[tid]);
+  }
+  if (tid == 0) {
+    atomicAdd(t.g_vf.bo, a_vf[H]); atomicAdd(t.g_q1.bo, a_q1[H]); atomicAdd(t.g_q2.bo, a_q2[H]);
+    atomicAdd(t.g_log_alpha, red[MET_COUNT]);
+  }
+  if (tid < MET_GN_PI) atomicAdd(t.metrics + tid, red[tid]);
+}
+
+// ---- policy inference ([SB2] SACPolicy.step: deterministic_policy = tanh(mu), policy = tanh(mu + eps*std))
+__global__ void __launch_bounds__(WARPS * 32) act_kernel(TailArgs t, int n, int deterministic, float* act_out) {
+  __shared__ float Wk1[H * LD];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < H * H; i += blockDim.x) Wk1[(i >> 6) * LD + (i & 63)] = t.pi.k1[i];
+  __syncthreads();
+  const int A = t.A;
+  for (int b = blockIdx.x * WARPS + warp; b < n; b += gridDim.x * WARPS) {
+    const V2 a0 = relu2(V2{t.z0_pi[b * H + lane] + t.pi.b0[lane], t.z0_pi[b * H + lane + 32] + t.pi.b0[lane + 32]});
+    const V2 g = relu2(fwd64(Wk1, t.pi.b1, a0, lane));
+    for (int a = 0; a < A; ++a) {
+      const float mu = warp_sum(g.lo * t.pi.ko[lane * A + a] + g.hi * t.pi.ko[(lane + 32) * A + a]) + t.pi.bo[a];
+      float u = mu;
+      if (!deterministic) {
+        float ls = warp_sum(g.lo * t.ksig[lane * A + a] + g.hi * t.ksig[(lane + 32) * A + a]) + t.bsig[a];
+        ls = fminf(fmaxf(ls, LS_MIN), LS_MAX);
+        u = mu + t.eps[b * A + a] * expf(ls);
+      }
+      if (lane == 0) act_out[b * A + a] = tanhf(u);
+    }
+  }
+}
+}  // namespace
+
+void act_launch(const TailArgs& t, int n, int deterministic, float* act_out, cudaStream_t s) {
+  if (n <= 0) return;
+  act_kernel<<<(n + WARPS - 1) / WARPS, WARPS * 32, 0, s>>>(t, n, deterministic, act_out);
+}
+
+namespace {
+}  // namespace
+
+static size_t tail_smem(int A) {
+  return sizeof(float) * (S_NW * H * LD + 2 * H * A + 2 * A + 3 * (H + 1) + MET_COUNT + 1 + 8);
+}
+
+void tail_launch(const TailArgs& a, cudaStream_t s) {
+  static bool attr_set = false;
+  const size_t smem = tail_smem(a.A);
+  if (!attr_set) {
+    cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem(AMAX));
+    attr_set = true;
+  }
+  const int grid = (a.B + WARPS - 1) / WARPS;
+  tail_kernel<<<grid, WARPS * 32, smem, s>>>(a);
+}
+
+}  // namespace b2g

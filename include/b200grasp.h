@@ -1,0 +1,130 @@
+/*
+ * b200grasp.h -- C ABI of the B200-native SAC learner (libb200grasp.so).
+ *
+ * Drop-in boundary for the ONE hot path of BarisYazici/deep-rl-grasping: the replay-buffer
+ * minibatch gradient step that the reference delegates to stable_baselines.SAC (TF1) --
+ *   constructed at  manipulation_main/training/sb_helper.py:104-128
+ *   driven from     manipulation_main/training/sb_helper.py:175   (model.learn -> SAC._train_step)
+ *   queried from    manipulation_main/utils.py:71                 (agent.predict)
+ *   (de)serialised  manipulation_main/training/sb_helper.py:228-247, train_stable_baselines.py:95-104
+ *
+ * Conventions: every function returns 0 on success or a negative B2G_E* code and never throws
+ * across the ABI; b2g_last_error() gives the message for the calling thread's last failure.  A
+ * handle is single-owner and not thread-safe; it owns one CUDA stream and all of its device
+ * memory.  Host arrays passed in are caller-owned and copied before the call returns (or, for the
+ * *_async calls, before the next b2g_sync).  All floating point data is IEEE fp32 unless noted.
+ * Parameter tensors use the TF variable names and layouts of the shipped SB zips (conv filters
+ * HWIO, conv bias (1,n,1,1), dense kernels [in,out]) so get/set round-trips with them.
+ */
+#ifndef B200GRASP_H_
+#define B200GRASP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2G_OK 0
+#define B2G_EINVAL (-1)   /* bad argument / unknown variable name / size mismatch            */
+#define B2G_ECUDA (-2)    /* CUDA runtime error (no device, launch failure, out of memory)   */
+#define B2G_ESTATE (-3)   /* call not valid in this state (e.g. sampling from an empty buffer) */
+#define B2G_ENCCL (-4)    /* NCCL unavailable or failed                                      */
+
+/* precision modes of the dense contractions (convs, cnn_fc1, fc0 layers) */
+#define B2G_PREC_FP32_SIMT 0   /* fp32 FFMA on CUDA cores: bit-faithful fp32 arithmetic            */
+#define B2G_PREC_BF16X3 1      /* tcgen05 BF16 hi/lo split, 3 MMAs, fp32 TMEM accumulate (~2^-16)  */
+#define B2G_PREC_BF16 2        /* tcgen05 single-pass BF16 (fast mode; tolerance reported)         */
+
+typedef struct b2g_sac b2g_sac;
+
+/* Replaces the keyword arguments of sb.SAC(policy, env, policy_kwargs, gamma, buffer_size,
+ * batch_size, learning_rate, ...) -- sb_helper.py:120-128 -- plus the shapes the policy class
+ * would read from env.observation_space / action_space (robot.py:207-228). */
+typedef struct b2g_sac_cfg {
+  int32_t obs_h, obs_w, obs_c; /* CNN policy: NHWC obs, obs_c = image channels + 1 feature plane
+                                  (custom_obs_policy.py:28-32).  obs_h == 0 selects the MLP policy */
+  int32_t obs_dim;             /* MLP policy: flat observation size (101 for the encoder config)   */
+  int32_t n_act;               /* 5 (actuator.py:72-73); <= 8                                      */
+  int32_t hidden;              /* SAC.layers = [hidden, hidden] (config/gripper_grasp.yaml:81); 64 */
+  int32_t batch;               /* per-rank minibatch size                                          */
+  int64_t buffer_capacity;     /* replay slots on this rank (config/gripper_grasp.yaml:82)         */
+  float gamma, tau, target_entropy;
+  uint64_t seed;               /* replay-index and policy-noise streams                            */
+  int32_t precision;           /* B2G_PREC_*                                                       */
+  int32_t device;              /* CUDA ordinal                                                     */
+  int32_t rank, nranks;        /* data-parallel group; nranks == 1 -> no collective                */
+  const void* nccl_id;         /* 128-byte ncclUniqueId shared by all ranks (nranks > 1)           */
+  const char* nccl_lib;        /* optional path of libnccl.so.2 to dlopen; NULL = default search   */
+} b2g_sac_cfg;
+
+/* What SAC._train_step returns / logs (logs.csv columns policy_loss, qf1_loss, qf2_loss,
+ * value_loss, entropy, ent_coef, ent_coef_loss) plus the parity scalars north_star names. */
+typedef struct b2g_sac_metrics {
+  float policy_loss, qf1_loss, qf2_loss, value_loss, ent_coef_loss, entropy, ent_coef;
+  float grad_norm_pi, grad_norm_values, grad_ent;
+  float mean_q1, mean_q2, mean_v, mean_logp;
+  int64_t n_updates;
+} b2g_sac_metrics;
+
+const char* b2g_last_error(void);
+int b2g_version(void);
+/* writes a fresh 128-byte ncclUniqueId (rank 0 calls this, then shares it out of band) */
+int b2g_nccl_unique_id(void* out128, const char* nccl_lib);
+
+int b2g_sac_create(const b2g_sac_cfg* cfg, b2g_sac** out);
+int b2g_sac_destroy(b2g_sac* h);
+int b2g_sync(b2g_sac* h);
+
+/* ---- parameters: SB-zip variable names without the ":0" suffix (get_parameters / load_parameters,
+ *      sb_helper.py:114-115) */
+int b2g_param_count(const b2g_sac* h);
+int b2g_param_info(const b2g_sac* h, int idx, const char** name, int64_t* numel, int32_t* ndim, int64_t shape[4]);
+int b2g_get_param(b2g_sac* h, const char* name, float* dst, size_t numel);
+int b2g_set_param(b2g_sac* h, const char* name, const float* src, size_t numel);
+int b2g_get_grad(b2g_sac* h, const char* name, float* dst, size_t numel); /* gradient of the last step */
+int b2g_get_adam(b2g_sac* h, const char* name, float* m, float* v, size_t numel);
+int b2g_reset_optimizer(b2g_sac* h);   /* zero Adam moments and step counters (fresh tf.Session) */
+
+/* ---- replay buffer (ReplayBuffer.add; stores UN-normalised obs/reward as SB does when a
+ *      VecNormalize wraps the env) and VecNormalize statistics used at sample time
+ *      (sb_helper.py:118-119; float64 like numpy) */
+int b2g_replay_add(b2g_sac* h, const float* obs, const float* act, const float* rew, const float* next_obs,
+                   const float* done, int64_t n);
+int64_t b2g_replay_size(const b2g_sac* h);
+int b2g_set_norm_stats(b2g_sac* h, const double* obs_mean, const double* obs_var, double ret_var, double clip_obs,
+                       double clip_rew, double eps, int norm_obs, int norm_reward);
+
+/* ---- the hot path.  One call = n_steps x { sample -> normalise -> fwd -> bwd -> [allreduce] ->
+ *      3x Adam -> Polyak }  (SAC._train_step + target_update_op).  Indices and policy noise come
+ *      from the handle's counter-based generators.  metrics (may be NULL) = last step. */
+int b2g_sac_step(b2g_sac* h, int n_steps, float lr, b2g_sac_metrics* out);
+/* Same, but metrics stay on the device until b2g_sync/next blocking call (no host round trip). */
+int b2g_sac_step_async(b2g_sac* h, int n_steps, float lr);
+
+/* Parity entry point: the caller supplies the RAW batch (host pointers; normalised on the device
+ * with the current statistics) and the N(0,1) noise eps[batch, n_act], so results are comparable
+ * with the oracle.  per_sample (may be NULL) receives q1,q2,v,logp,v_targ,q1_pi,q2_pi as 7 rows of
+ * [batch]; pi_out (may be NULL) receives tanh-squashed actions [batch, n_act].
+ * apply_update == 0 computes losses and gradients only. */
+int b2g_sac_step_explicit(b2g_sac* h, const float* obs, const float* act, const float* rew, const float* next_obs,
+                          const float* done, const float* eps, float lr, int apply_update, b2g_sac_metrics* out,
+                          float* per_sample, float* pi_out);
+
+/* policy_tf.step (SAC.predict, utils.py:71): obs are RAW, normalised with the current stats.
+ * deterministic -> tanh(mu); else tanh(mu + eps*std) with eps from the handle's generator. */
+int b2g_sac_act(b2g_sac* h, const float* obs, int n, int deterministic, float* act_out);
+
+/* number of kernel launches one gradient step issues (bench.py's gpu_launches) */
+int b2g_launches_per_step(const b2g_sac* h);
+/* device-time of the last b2g_sac_step call measured with CUDA events on the handle's stream (ms) */
+float b2g_last_step_ms(const b2g_sac* h);
+/* per-kernel-group device time of ONE extra profiled step (events around each launch);
+ * names/ms arrays of capacity cap; returns the number of groups */
+int b2g_profile_step(b2g_sac* h, float lr, const char** names, float* ms, int cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200GRASP_H_ */
