@@ -19,7 +19,8 @@ def _fp(a: np.ndarray):
 
 
 def _f32(a) -> np.ndarray:
-    return np.ascontiguousarray(a, dtype=np.float32)
+    a = np.asarray(a, dtype=np.float32)          # (ascontiguousarray would promote 0-d to 1-d)
+    return a if a.flags.c_contiguous else a.copy()
 
 
 class Learner:
@@ -90,7 +91,7 @@ class Learner:
         out = OrderedDict()
         for n, shp in self._info.items():
             a = np.empty(shp, np.float32)
-            _lib.check(self.lib.b2g_get_param(self.h, n.encode(), _fp(a.reshape(-1)) if a.ndim else _fp(a.reshape(1)), a.size))
+            _lib.check(self.lib.b2g_get_param(self.h, n.encode(), _fp(a.reshape(-1)), a.size))
             out[n] = a
         return out
 
