@@ -49,11 +49,17 @@ struct GemmGroup {          // one grouped launch
   GemmDesc* dev = nullptr;
   int total_tiles = 0;
   double flops = 0;
+  bool tc = false;          // run on the tcgen05 engine
+  bool tc_eligible = false; // large dense contraction (convs, cnn_fc1)
 };
 
 // engines (gg_simt.cu / gg_tc.cu)
 void gg_simt_launch(const GemmDesc* dev_descs, int ndesc, int total_tiles, cudaStream_t s);
 constexpr int GG_SIMT_BM = 64, GG_SIMT_BN = 64, GG_SIMT_BK = 16;
+// tcgen05 engine: 128 x 64 output tile, 64-wide r-chunks; x3 != 0 -> BF16 hi/lo split (3 MMAs)
+cudaError_t gg_tc_launch(const GemmDesc* dev_descs, int ndesc, int total_tiles, int mode_flags, int x3, cudaStream_t s);
+int gg_tc_smem_bytes();
+constexpr int GG_TC_BM = 128, GG_TC_BN = 64, GG_TC_BK = 64;
 
 // ---------------------------------------------------------------------------------------------
 // head "tail" kernel (tail.cu): everything after the fc0 contractions, per sample

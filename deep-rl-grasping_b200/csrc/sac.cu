@@ -241,9 +241,16 @@ GemmDesc mk(const float* A, const int* aM, const int* aR, const float* B, const 
 int finalize_group(b2g_sac* h, GemmGroup& g) {
   int start = 0;
   g.flops = 0;
+  const int bm = g.tc ? GG_TC_BM : GG_SIMT_BM, bn = g.tc ? GG_TC_BN : GG_SIMT_BN, bk = g.tc ? GG_TC_BK : GG_SIMT_BK;
   for (auto& d : g.host) {
-    d.tiles_m = (d.M + GG_SIMT_BM - 1) / GG_SIMT_BM;
-    d.tiles_n = (d.N + GG_SIMT_BN - 1) / GG_SIMT_BN;
+    d.tiles_m = (d.M + bm - 1) / bm;
+    d.tiles_n = (d.N + bn - 1) / bn;
+    if (d.flags & GG_EPI_ATOMIC) {     // split-R sized for this engine's tile grid
+      const int tiles = d.tiles_m * d.tiles_n;
+      int sp = std::max(1, (g.tc ? 148 : 148) / std::max(1, tiles));
+      sp = std::min(sp, std::max(1, d.R / (2 * bk)));
+      d.splitR = sp;
+    }
     d.tile_start = start;
     d.tile_count = d.tiles_m * d.tiles_n * d.splitR;
     start += d.tile_count;
@@ -521,9 +528,34 @@ int build_groups(b2g_sac* h) {
     // heads_wgrad must run before heads_dgrad? no dependency; keep it first in the backward list
     h->bwd_groups.insert(h->bwd_groups.begin(), g);
   }
-  for (auto& g : h->fwd_groups) if (int rc = finalize_group(h, g)) return rc;
-  for (auto& g : h->bwd_groups) if (int rc = finalize_group(h, g)) return rc;
-  for (auto& g : h->act_groups) if (int rc = finalize_group(h, g)) return rc;
+  // one operand-contiguity mode per launch (the tcgen05 kernel is specialised on it): split mixed groups
+  {
+    std::vector<GemmGroup> split;
+    for (auto& g : h->bwd_groups) {
+      std::vector<GemmDesc> wg, dg;
+      for (auto& d : g.host) ((d.flags & GG_A_RVEC) ? dg : wg).push_back(d);
+      if (wg.empty() || dg.empty()) { split.push_back(g); continue; }
+      GemmGroup a = g, b = g;
+      const std::string base = g.name.substr(0, g.name.find('_'));
+      a.name = base + "_wgrad"; a.host = wg;
+      b.name = base + "_dgrad"; b.host = dg;
+      split.push_back(a); split.push_back(b);
+    }
+    h->bwd_groups.swap(split);
+  }
+  // engine selection: the large dense contractions go to the tcgen05 engine unless fp32 SIMT is asked for
+  const char* sel = getenv("B2G_TC_GROUPS");   // debugging: comma-separated group names, "all" or "none"
+  auto pick = [&](GemmGroup& g) {
+    g.tc_eligible = g.name.find("conv") != std::string::npos || g.name.find("fc1_") != std::string::npos;
+    g.tc = g.tc_eligible && h->cfg.precision != B2G_PREC_FP32_SIMT;
+    if (sel && g.tc_eligible && h->cfg.precision != B2G_PREC_FP32_SIMT) {
+      const std::string s(sel);
+      g.tc = s == "all" || (s != "none" && ("," + s + ",").find("," + g.name + ",") != std::string::npos);
+    }
+  };
+  for (auto& g : h->fwd_groups) { pick(g); if (int rc = finalize_group(h, g)) return rc; }
+  for (auto& g : h->bwd_groups) { pick(g); if (int rc = finalize_group(h, g)) return rc; }
+  for (auto& g : h->act_groups) { pick(g); if (int rc = finalize_group(h, g)) return rc; }
   return 0;
 }
 
@@ -620,9 +652,16 @@ int issue_step(b2g_sac* h, bool sampled, bool apply, bool want_per_sample, Prof*
   prep_launch(pa, s); ++n; mark("prep");
   gather_launch(make_gather(h, sampled, true), s); ++n; mark("gather_normalize");
   CK(cudaMemsetAsync(h->G, 0, (size_t)(h->n_train + MET_COUNT) * sizeof(float), s)); ++n; mark("zero_grads");
-  for (auto& g : h->fwd_groups) { gg_simt_launch(g.dev, (int)g.host.size(), g.total_tiles, s); ++n; mark(g.name.c_str()); }
+  const int x3 = h->cfg.precision == B2G_PREC_BF16X3 ? 1 : 0;
+  auto run_group = [&](GemmGroup& g) -> int {
+    if (g.tc) CK(gg_tc_launch(g.dev, (int)g.host.size(), g.total_tiles, g.host[0].flags, x3, s));
+    else gg_simt_launch(g.dev, (int)g.host.size(), g.total_tiles, s);
+    ++n; mark(g.name.c_str());
+    return 0;
+  };
+  for (auto& g : h->fwd_groups) if (int rc = run_group(g)) return rc;
   tail_launch(make_tail(h, want_per_sample), s); ++n; mark("heads_tail");
-  for (auto& g : h->bwd_groups) { gg_simt_launch(g.dev, (int)g.host.size(), g.total_tiles, s); ++n; mark(g.name.c_str()); }
+  for (auto& g : h->bwd_groups) if (int rc = run_group(g)) return rc;
   if (h->cfg.nranks > 1) {
     // losses/means ride behind the gradients in the same buffer
     CK(cudaMemcpyAsync(h->G + h->n_train, h->metrics, MET_GN_PI * sizeof(float), cudaMemcpyDeviceToDevice, s)); ++n;
@@ -722,8 +761,8 @@ int b2g_sac_create(const b2g_sac_cfg* cfg, b2g_sac** out) {
   if (cfg->n_act < 1 || cfg->n_act > 8) return fail(B2G_EINVAL, "n_act must be in [1,8]");
   if (cfg->batch < 1 || cfg->buffer_capacity < 1) return fail(B2G_EINVAL, "batch and buffer_capacity must be positive");
   if (cfg->nranks < 1 || cfg->rank < 0 || cfg->rank >= cfg->nranks) return fail(B2G_EINVAL, "bad rank/nranks");
-  if (cfg->precision != B2G_PREC_FP32_SIMT)
-    return fail(B2G_EINVAL, "precision mode not built in this revision (only B2G_PREC_FP32_SIMT)");
+  if (cfg->precision < B2G_PREC_FP32_SIMT || cfg->precision > B2G_PREC_BF16)
+    return fail(B2G_EINVAL, "unknown precision mode");
   int ndev = 0;
   CK(cudaGetDeviceCount(&ndev));
   if (cfg->device < 0 || cfg->device >= ndev) return fail(B2G_ECUDA, "no such CUDA device");
@@ -988,7 +1027,10 @@ int b2g_sac_act(b2g_sac* h, const float* obs, int n, int deterministic, float* a
     GatherArgs g = make_gather(h, false, false);
     g.indices = nullptr;
     gather_launch(g, h->stream);
-    for (auto& gr : h->act_groups) gg_simt_launch(gr.dev, (int)gr.host.size(), gr.total_tiles, h->stream);
+    for (auto& gr : h->act_groups) {
+      if (gr.tc) CK(gg_tc_launch(gr.dev, (int)gr.host.size(), gr.total_tiles, gr.host[0].flags, h->cfg.precision == B2G_PREC_BF16X3 ? 1 : 0, h->stream));
+      else gg_simt_launch(gr.dev, (int)gr.host.size(), gr.total_tiles, h->stream);
+    }
     b2g::act_launch(make_tail(h, false), chunk, deterministic, h->pi_out, h->stream);
     CK(cudaMemcpyAsync(act_out + (size_t)done_n * A, h->pi_out, chunk * A * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));

@@ -27,9 +27,9 @@ def make_batch(vn, B, seed=synth.DATA_SEED):
     return raw, norm, synth.make_eps(B, seed=seed + 1)
 
 
-def make_learner(cfg, vn, B, params=None, buffer_size=1024, **kw):
+def make_learner(cfg, vn, B, params=None, buffer_size=1024, precision=0, **kw):
     L = b200grasp.Learner(cfg.obs_shape, n_act=cfg.n_act, batch_size=B, buffer_size=buffer_size, gamma=cfg.gamma,
-                          tau=cfg.tau, target_entropy=cfg.target_entropy, **kw)
+                          tau=cfg.tau, target_entropy=cfg.target_entropy, precision=precision, **kw)
     L.set_norm_stats(vn["obs_mean"], vn["obs_var"], float(vn["ret_var"]), float(vn["clip_obs"]), float(vn["clip_reward"]),
                      float(vn["epsilon"]))
     if params is not None:
