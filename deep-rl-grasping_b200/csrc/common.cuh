@@ -57,7 +57,8 @@ struct GemmGroup {          // one grouped launch
 void gg_simt_launch(const GemmDesc* dev_descs, int ndesc, int total_tiles, cudaStream_t s);
 constexpr int GG_SIMT_BM = 64, GG_SIMT_BN = 64, GG_SIMT_BK = 16;
 // tcgen05 engine: 128 x 64 output tile, 64-wide r-chunks; x3 != 0 -> BF16 hi/lo split (3 MMAs)
-cudaError_t gg_tc_launch(const GemmDesc* dev_descs, int ndesc, int total_tiles, int mode_flags, int x3, cudaStream_t s);
+cudaError_t gg_tc_launch(const GemmDesc* host_descs, int ndesc, int total_tiles, int mode_flags, int x3, int num_sms, cudaStream_t s);
+constexpr int GG_TC_MAX_DESCS = 16;
 int gg_tc_smem_bytes();
 constexpr int GG_TC_BM = 128, GG_TC_BN = 64, GG_TC_BK = 64;
 

@@ -3,17 +3,20 @@
 //
 //   C[cM[m] + cN[n]] (=|+=) epi( sum_r A[aM[m] + aR[r]] * B[bR[r] + bN[n]] )       (common.cuh)
 //
-// One CTA computes one 128(m) x <=64(n) output tile over its r-range:
+// Persistent, warp-specialised kernel: grid = min(#tiles, #SMs); every CTA walks the flattened tile
+// list of a grouped launch (tile = 128(m) x <=64(n) x its r-range) with three concurrent roles:
 //   * 16 producer warps gather fp32 operands through the offset tables (implicit im2col / wgrad /
-//     dgrad views), split every value into BF16 hi + BF16 lo (x = hi + lo to ~2^-17) and write
-//     both as K-major, 128B-swizzled UMMA tiles into a 3-stage shared-memory ring
-//     (generic-proxy stores -> fence.proxy.async -> mbarrier arrive);
-//   * 1 MMA warp (one elected thread) issues tcgen05.mma.cta_group::1.kind::f16 over the ring:
-//     mode BF16X3: hi*hi + hi*lo + lo*hi (fp32-faithful to ~1e-5 relative, parity mode),
-//     mode BF16  : hi*hi only (fast mode); tcgen05.commit frees ring slots and signals the epilogue;
-//   * the producer warps then become the epilogue: tcgen05.ld the accumulator rows from TMEM,
-//     apply bias+ReLU / ReLU-mask / split-R atomics and store.
-// Accumulator: 128 lanes x 64 fp32 columns of TMEM.  Ring: 3 x 48 KiB = 144 KiB of shared memory.
+//     dgrad views), split every value into BF16 hi + BF16 lo (x = hi + lo to ~2^-17) and write both
+//     as K-major, 128B-swizzled UMMA tiles into a 4-stage shared-memory ring that runs continuously
+//     across tiles (generic-proxy stores -> fence.proxy.async -> mbarrier arrive);
+//   * 1 MMA warp (one thread) issues tcgen05.mma.cta_group::1.kind::f16 over the ring into one of
+//     two TMEM accumulators: mode BF16X3 = hi*hi + hi*lo + lo*hi (fp32-faithful to ~1e-5, the parity
+//     mode), mode BF16 = hi*hi only (fast mode); tcgen05.commit frees ring slots and publishes the
+//     accumulator;
+//   * 4 epilogue warps tcgen05.ld the finished accumulator (one row per thread), release it to the
+//     MMA warp at once, then apply bias+ReLU / ReLU-mask / split-R atomics and store, overlapping the
+//     next tile's mainloop.
+// TMEM: 2 x (128 lanes x 64 fp32 columns).  Shared memory: 4 x 48 KiB ring.
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -21,15 +24,23 @@
 namespace b2g {
 namespace {
 
-constexpr int TM = GG_TC_BM, TN = GG_TC_BN, TK = 64;   // tile: 128 x 64 x 64
-constexpr int STAGES = 3;
-constexpr int NPROD = 512;                              // producer / epilogue threads (16 warps)
-constexpr int NTHREADS = NPROD + 32;                    // + MMA warp
+constexpr int TM = GG_TC_BM, TN = GG_TC_BN, TK = GG_TC_BK;   // tile: 128 x 64 x 64
+constexpr int STAGES = 4;
+constexpr int NPROD = 512;                              // producer threads (16 warps)
+constexpr int MMA_WARP = NPROD / 32;                    // warp 16
+constexpr int NEPI = 128;                               // epilogue threads (warps 17..20)
+constexpr int NTHREADS = NPROD + 32 + NEPI;             // 672
 constexpr int A_BYTES = TM * TK * 2;                    // 16 KiB per (hi | lo)
 constexpr int B_BYTES = TN * TK * 2;                    // 8 KiB
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;  // 48 KiB
-constexpr int RTAB = 1024;                              // r-offset table entries staged in smem per operand
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
+constexpr int TMEM_COLS = 2 * TN;
+
+struct DescPack {
+  GemmDesc d[GG_TC_MAX_DESCS];
+  int n;
+  int total_tiles;
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -103,327 +114,413 @@ __device__ __forceinline__ void st_shared16(uint32_t addr, const uint4& v) {
 }
 __device__ __forceinline__ float4 ldg4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
+struct TileInfo {
+  int p, m0, n0, tm, r_begin, r_end, nchunks, un;
+};
+__device__ __forceinline__ TileInfo tile_info(const DescPack& pk, int tile) {
+  int p = 0;
+  while (p + 1 < pk.n && tile >= pk.d[p + 1].tile_start) ++p;
+  const GemmDesc& d = pk.d[p];
+  int t = tile - d.tile_start;
+  const int per = d.tiles_m * d.tiles_n;
+  const int split = t / per;
+  t -= split * per;
+  TileInfo ti;
+  ti.p = p;
+  ti.tm = t / d.tiles_n;
+  const int tn = t - ti.tm * d.tiles_n;
+  ti.m0 = ti.tm * TM;
+  ti.n0 = tn * TN;
+  const int chunk_r = (((d.R + d.splitR - 1) / d.splitR) + TK - 1) / TK * TK;
+  ti.r_begin = split * chunk_r;
+  ti.r_end = min(d.R, ti.r_begin + chunk_r);
+  ti.nchunks = ti.r_end > ti.r_begin ? (ti.r_end - ti.r_begin + TK - 1) / TK : 0;
+  ti.un = min(TN, ((d.N - ti.n0) + 15) / 16 * 16);   // UMMA N for this tile (multiple of 16)
+  return ti;
+}
+
 template <bool a_rvec, bool b_rvec>
-__global__ void __launch_bounds__(NTHREADS, 1) gg_tc_kernel(const GemmDesc* __restrict__ descs, int ndesc, int x3) {
+__global__ void __launch_bounds__(NTHREADS, 1) gg_tc_kernel(const __grid_constant__ DescPack pk, int x3_in) {
+  int x3 = x3_in;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ GemmDesc sd;
-  __shared__ __align__(8) uint64_t bar_full[STAGES], bar_empty[STAGES], bar_accum;
+  __shared__ __align__(8) uint64_t bar_full[STAGES], bar_empty[STAGES], bar_acc_full[2], bar_acc_empty[2];
   __shared__ uint32_t tmem_slot;
-  __shared__ float cs[TN];
-  __shared__ int s_aR[RTAB], s_bR[RTAB];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool dbg_noload = x3 & 0x100, dbg_nomma = x3 & 0x200, dbg_nostore = x3 & 0x400, dbg_nosplit = x3 & 0x800;
+  x3 &= 1;
   if (tid == 0) {
-    int p = 0;
-    const int t = blockIdx.x;
-    while (p + 1 < ndesc && t >= descs[p + 1].tile_start) ++p;
-    sd = descs[p];
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(smem_u32(&bar_full[s]), NPROD);
       mbar_init(smem_u32(&bar_empty[s]), 1);
     }
-    mbar_init(smem_u32(&bar_accum), 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&bar_acc_full[b]), 1);
+      mbar_init(smem_u32(&bar_acc_empty[b]), NEPI);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (tid < TN) cs[tid] = 0.f;
-  if (warp == NPROD / 32) {   // MMA warp owns the TMEM allocation
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(TN));
+  if (warp == MMA_WARP) {   // MMA warp owns the TMEM allocation
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  const GemmDesc& d = sd;
-
-  int t = blockIdx.x - d.tile_start;
-  const int per = d.tiles_m * d.tiles_n;
-  const int split = t / per;
-  t -= split * per;
-  const int tm = t / d.tiles_n, tn = t - tm * d.tiles_n;
-  const int m0 = tm * TM, n0 = tn * TN;
-  const int chunk_r = (((d.R + d.splitR - 1) / d.splitR) + TK - 1) / TK * TK;
-  const int r_begin = split * chunk_r;
-  const int r_end = min(d.R, r_begin + chunk_r);
-  const int nchunks = r_end > r_begin ? (r_end - r_begin + TK - 1) / TK : 0;
-  const int un = min(TN, ((d.N - n0) + 15) / 16 * 16);   // UMMA N for this tile (multiple of 16)
-
   const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
 
-  // r-offset tables of this CTA's r-range -> shared memory (falls back to global reads if too long)
-  const bool tab_smem = (r_end - r_begin) <= RTAB;
-  if (tab_smem) {
-    for (int i = tid; i < r_end - r_begin; i += NTHREADS) { s_aR[i] = d.aR[r_begin + i]; s_bR[i] = d.bR[r_begin + i]; }
-  }
-  __syncthreads();
-
-  if (warp < NPROD / 32) {
+  if (warp < MMA_WARP) {
     // =========================================================================== producers
-    const bool do_colsum = (d.flags & GG_COLSUM) && tm == 0 && !b_rvec;
-    const float* __restrict__ A = d.A;
-    const float* __restrict__ Bp = d.B;
     const int c8 = tid & 7;             // 16-byte chunk (8 r values) inside the 64-wide r-chunk
     const int q = tid >> 3;             // 0..63
     // A, r-contiguous: all threads, rows q + 64 i (i < 2).  A, m-contiguous: threads < 256, rows 4 q .. 4 q + 3.
     const bool a_thread = a_rvec ? true : (q < 32);
-    int a_off[4];
-    bool a_ok[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int m = m0 + (a_rvec ? q + 64 * i : 4 * q + i);
-      a_ok[i] = a_thread && m < d.M && (a_rvec ? i < 2 : true);
-      a_off[i] = a_ok[i] ? d.aM[m] : 0;
-    }
-    // B, n-contiguous: threads 256..383 (q - 32 in 0..15), n = 4 (q-32) .. +3.  B, r-contiguous: all threads, n = q.
+    // B, n-contiguous: threads 256..383 (qb in 0..15), n = 4 qb .. +3.  B, r-contiguous: all threads, n = q.
     const int qb = b_rvec ? q : q - 32;
     const bool b_thread = b_rvec ? true : (qb >= 0 && qb < TN / 4);
-    int b_off[4];
-    bool b_ok[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int n = n0 + (b_rvec ? qb : 4 * qb + i);
-      b_ok[i] = b_thread && n < d.N && (b_rvec ? i < 1 : true);
-      b_off[i] = b_ok[i] ? d.bN[n] : 0;
-    }
-    float4 csum = make_float4(0, 0, 0, 0);
+    uint32_t gc = 0;                    // ring chunk counter, continuous across tiles
 
-    for (int ch = 0; ch < nchunks; ++ch) {
-      const int s = ch % STAGES;
-      const uint32_t sA_hi = ring + s * STAGE_BYTES, sA_lo = sA_hi + A_BYTES;
-      const uint32_t sB_hi = sA_lo + A_BYTES, sB_lo = sB_hi + B_BYTES;
-      const int rl = ch * TK + c8 * 8;                 // r relative to r_begin
-      const int r0 = r_begin + rl;
-      const int nr = min(8, r_end - r0);               // valid r values (<= 0: none)
-      int ar[8], br[8];
+    for (int tile = blockIdx.x; tile < pk.total_tiles; tile += gridDim.x) {
+      const TileInfo ti = tile_info(pk, tile);
+      if (ti.nchunks == 0) continue;
+      const GemmDesc& d = pk.d[ti.p];
+      const float* __restrict__ A = d.A;
+      const float* __restrict__ Bp = d.B;
+      const bool do_colsum = (d.flags & GG_COLSUM) && ti.tm == 0 && !b_rvec;
+      int a_off[4], b_off[4];
+      bool a_ok[4], b_ok[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        ar[j] = br[j] = 0;
-        if (j < nr) {
-          ar[j] = tab_smem ? s_aR[rl + j] : d.aR[r0 + j];
-          br[j] = tab_smem ? s_bR[rl + j] : d.bR[r0 + j];
-        }
+      for (int i = 0; i < 4; ++i) {
+        const int m = ti.m0 + (a_rvec ? q + 64 * i : 4 * q + i);
+        a_ok[i] = a_thread && m < d.M && (a_rvec ? i < 2 : true);
+        a_off[i] = a_ok[i] ? d.aM[m] : 0;
+        const int n = ti.n0 + (b_rvec ? qb : 4 * qb + i);
+        b_ok[i] = b_thread && n < d.N && (b_rvec ? i < 1 : true);
+        b_off[i] = b_ok[i] ? d.bN[n] : 0;
       }
-      // ---------------------------------------------------------------- issue every global load first
-      float xa[4][8];     // rvec: [unit i][r j] (i < 2);  mvec: [m i][r j]
-      float xb[4][8];     // rvec: [0][r j];                nvec: [n i][r j]
+      float4 csum = make_float4(0, 0, 0, 0);
+
+      // r-offset table entries of the thread's 8 r values: loaded one chunk ahead so that the operand
+      // loads of a chunk are a single batch of independent LDG.128 (one round trip).
+      // r-contiguous operands need entries 0 and 4 only; block (m-/n-contiguous) operands need all 8.
+      const int* __restrict__ tabA = d.aR;
+      const int* __restrict__ tabB = d.bR;
+      const bool blk_is_B = !a_rvec && !a_thread;           // wgrad: this thread gathers the B operand
+      const int* __restrict__ tabBlk = a_rvec ? tabB : (blk_is_B ? tabB : tabA);
+      int t2a[2] = {0, 0}, t2b[2] = {0, 0};                 // r-contiguous A / B
+      int t8[8] = {0, 0, 0, 0, 0, 0, 0, 0};                 // block operand (A m-contig, or B n-contig)
+      const bool need_blk = a_rvec ? (!b_rvec && b_thread) : (a_thread || b_thread);
+      auto load_tabs = [&](int r, int n_valid, int (&o2a)[2], int (&o2b)[2], int (&o8)[8]) {
+        if (n_valid == 8) {
+          if (a_rvec) { o2a[0] = tabA[r]; o2a[1] = tabA[r + 4]; }
+          if (b_rvec) { o2b[0] = tabB[r]; o2b[1] = tabB[r + 4]; }
+          if (need_blk) {
+            const int4 u = *reinterpret_cast<const int4*>(tabBlk + r), w = *reinterpret_cast<const int4*>(tabBlk + r + 4);
+            o8[0] = u.x; o8[1] = u.y; o8[2] = u.z; o8[3] = u.w; o8[4] = w.x; o8[5] = w.y; o8[6] = w.z; o8[7] = w.w;
+          }
+        }
+      };
+      {
+        const int r00 = ti.r_begin + c8 * 8;
+        load_tabs(r00, min(8, ti.r_end - r00), t2a, t2b, t8);
+      }
+
+      for (int ch = 0; ch < ti.nchunks; ++ch, ++gc) {
+        const int s = gc % STAGES;
+        const uint32_t sA_hi = ring + s * STAGE_BYTES, sA_lo = sA_hi + A_BYTES;
+        const uint32_t sB_hi = sA_lo + A_BYTES, sB_lo = sB_hi + B_BYTES;
+        const int r0 = ti.r_begin + ch * TK + c8 * 8;
+        const int nr = min(8, ti.r_end - r0);            // valid r values (<= 0: none)
+        // ---------------------------------------------------------------- issue every global load first
+        float xa[4][8];     // rvec: [unit i][r j] (i < 2);  mvec: [m i][r j]  (wgrad: B-threads reuse it)
+        float xb[4][8];     // rvec: [0][r j];                nvec: [n i][r j]
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) xa[i][j] = xb[i][j] = 0.f;
-      if (a_rvec) {
+          for (int j = 0; j < 8; ++j) xa[i][j] = xb[i][j] = 0.f;
+        if (dbg_noload) {
+        } else if (nr == 8) {
+          // ---- fast path: full 8-wide r group, straight-line independent loads
+          if (a_rvec) {
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          if (a_ok[i] && nr > 0) {
-            if (nr == 8) {
-              const float4 v = ldg4(A + a_off[i] + ar[0]), w = ldg4(A + a_off[i] + ar[4]);
-              xa[i][0] = v.x; xa[i][1] = v.y; xa[i][2] = v.z; xa[i][3] = v.w;
-              xa[i][4] = w.x; xa[i][5] = w.y; xa[i][6] = w.z; xa[i][7] = w.w;
+            for (int i = 0; i < 2; ++i) {
+              if (a_ok[i]) {
+                const float4 v = ldg4(A + a_off[i] + t2a[0]), w = ldg4(A + a_off[i] + t2a[1]);
+                xa[i][0] = v.x; xa[i][1] = v.y; xa[i][2] = v.z; xa[i][3] = v.w;
+                xa[i][4] = w.x; xa[i][5] = w.y; xa[i][6] = w.z; xa[i][7] = w.w;
+              }
+            }
+          }
+          if (b_rvec) {
+            if (b_ok[0]) {
+              const float4 v = ldg4(Bp + b_off[0] + t2b[0]), w = ldg4(Bp + b_off[0] + t2b[1]);
+              xb[0][0] = v.x; xb[0][1] = v.y; xb[0][2] = v.z; xb[0][3] = v.w;
+              xb[0][4] = w.x; xb[0][5] = w.y; xb[0][6] = w.z; xb[0][7] = w.w;
+            }
+          }
+          if (need_blk) {
+            float (&xq)[4][8] = a_rvec ? xb : xa;
+            const float* __restrict__ base = (a_rvec || blk_is_B) ? Bp : A;
+            const int (&off)[4] = (a_rvec || blk_is_B) ? b_off : a_off;
+            const bool (&ok)[4] = (a_rvec || blk_is_B) ? b_ok : a_ok;
+            if (ok[3]) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 v = ldg4(base + off[0] + t8[j]);
+                xq[0][j] = v.x; xq[1][j] = v.y; xq[2][j] = v.z; xq[3][j] = v.w;
+              }
             } else {
 #pragma unroll
               for (int j = 0; j < 8; ++j)
-                if (j < nr) xa[i][j] = A[a_off[i] + ar[j]];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  if (ok[i]) xq[i][j] = base[off[i] + t8[j]];
             }
           }
-        }
-      } else if (a_thread) {
+        } else if (nr > 0) {
+          // ---- slow path: ragged tail of the r range
+          if (a_rvec) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (j < nr) {
-            if (a_ok[3]) {
-              const float4 v = ldg4(A + a_off[0] + ar[j]);
-              xa[0][j] = v.x; xa[1][j] = v.y; xa[2][j] = v.z; xa[3][j] = v.w;
-            } else {
+            for (int i = 0; i < 2; ++i)
 #pragma unroll
-              for (int i = 0; i < 4; ++i)
-                if (a_ok[i]) xa[i][j] = A[a_off[i] + ar[j]];
-            }
-          }
-        }
-      }
-      if (b_rvec) {
-        if (b_ok[0] && nr > 0) {
-          if (nr == 8) {
-            const float4 v = ldg4(Bp + b_off[0] + br[0]), w = ldg4(Bp + b_off[0] + br[4]);
-            xb[0][0] = v.x; xb[0][1] = v.y; xb[0][2] = v.z; xb[0][3] = v.w;
-            xb[0][4] = w.x; xb[0][5] = w.y; xb[0][6] = w.z; xb[0][7] = w.w;
-          } else {
+              for (int j = 0; j < 8; ++j)
+                if (a_ok[i] && j < nr) xa[i][j] = A[a_off[i] + tabA[r0 + j]];
+          } else if (a_thread) {
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              if (j < nr) xb[0][j] = Bp[b_off[0] + br[j]];
-          }
-        }
-      } else if (b_thread) {
-        // wgrad mode (A m-contiguous): A-threads and B-threads are disjoint, so B reuses the xa registers
-        float (&xq)[4][8] = a_rvec ? xb : xa;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (j < nr) {
-            if (b_ok[3]) {
-              const float4 v = ldg4(Bp + b_off[0] + br[j]);
-              xq[0][j] = v.x; xq[1][j] = v.y; xq[2][j] = v.z; xq[3][j] = v.w;
-            } else {
 #pragma unroll
               for (int i = 0; i < 4; ++i)
-                if (b_ok[i]) xq[i][j] = Bp[b_off[i] + br[j]];
-            }
+                if (a_ok[i] && j < nr) xa[i][j] = A[a_off[i] + tabA[r0 + j]];
+          }
+          if (b_rvec) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (b_ok[0] && j < nr) xb[0][j] = Bp[b_off[0] + tabB[r0 + j]];
+          } else if (b_thread) {
+            float (&xq)[4][8] = a_rvec ? xb : xa;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                if (b_ok[i] && j < nr) xq[i][j] = Bp[b_off[i] + tabB[r0 + j]];
           }
         }
-        if (do_colsum) {
+        if (do_colsum && b_thread) {
+          float (&xq)[4][8] = a_rvec ? xb : xa;
 #pragma unroll
           for (int j = 0; j < 8; ++j) { csum.x += xq[0][j]; csum.y += xq[1][j]; csum.z += xq[2][j]; csum.w += xq[3][j]; }
         }
-      }
-      // ---------------------------------------------------------------- ring slot free?  then split + store
-      if (ch >= STAGES) mbar_wait(smem_u32(&bar_empty[s]), ((ch / STAGES) - 1) & 1);
-      if (a_thread) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          if (a_rvec && i >= 2) break;
-          uint4 hi, lo;
-          split8(xa[i], hi, lo);
-          const uint32_t o = sw128(a_rvec ? q + 64 * i : 4 * q + i, c8);
-          st_shared16(sA_hi + o, hi);
-          if (x3) st_shared16(sA_lo + o, lo);
+        // table entries of the next chunk (in flight during the wait + split + store below)
+        if (ch + 1 < ti.nchunks) {
+          const int r1 = r0 + TK;
+          load_tabs(r1, min(8, ti.r_end - r1), t2a, t2b, t8);
         }
-      }
-      if (b_thread) {
+        // ---------------------------------------------------------------- ring slot free?  then split + store
+        if (gc >= STAGES) mbar_wait(smem_u32(&bar_empty[s]), ((gc / STAGES) - 1) & 1);
+        if (a_thread && !dbg_nosplit) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          if (b_rvec && i >= 1) break;
-          uint4 hi, lo;
-          split8((a_rvec || b_rvec) ? xb[i] : xa[i], hi, lo);
-          const uint32_t o = sw128(b_rvec ? qb : 4 * qb + i, c8);
-          st_shared16(sB_hi + o, hi);
-          if (x3) st_shared16(sB_lo + o, lo);
-        }
-      }
-      fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor-core (async) proxy
-      mbar_arrive(smem_u32(&bar_full[s]));
-    }
-
-    // =========================================================================== epilogue
-    if (nchunks > 0) {
-      mbar_wait(smem_u32(&bar_accum), 0);
-      tc_fence_after();
-    }
-    const int lq = warp & 3;                     // TMEM lane quarter this warp may access
-    const int ch0 = (warp >> 2) * (TN / 4);      // column quarter
-    const int m = m0 + lq * 32 + lane;
-    const bool m_ok = m < d.M;
-    const int cm = m_ok ? d.cM[m] : 0;
-    const int km = (m_ok && (d.flags & GG_EPI_MASK)) ? (d.kM ? d.kM[m] : cm) : 0;
-#pragma unroll
-    for (int cb = 0; cb < TN / 4; cb += 8) {
-      uint32_t v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      if (nchunks > 0 && ch0 + cb < un) {       // warp-uniform
-        const uint32_t taddr = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(ch0 + cb);
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-                     : "r"(taddr));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      }
-      if (!m_ok) continue;
-      float o[8];
-      int co[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int n = n0 + ch0 + cb + j;
-        o[j] = __uint_as_float(v[j]);
-        co[j] = -1;
-        if (n < d.N) {
-          const int cn = d.cN[n];
-          co[j] = cm + cn;
-          if (d.flags & GG_EPI_BIAS_RELU) o[j] = fmaxf(o[j] + d.bias[n], 0.f);
-          if (d.flags & GG_EPI_MASK) {
-            const int kn = d.kN ? d.kN[n] : cn;
-            o[j] = d.mask[km + kn] > 0.f ? o[j] : 0.f;
+          for (int i = 0; i < 4; ++i) {
+            if (a_rvec && i >= 2) break;
+            uint4 hi, lo;
+            split8(xa[i], hi, lo);
+            const uint32_t o = sw128(a_rvec ? q + 64 * i : 4 * q + i, c8);
+            st_shared16(sA_hi + o, hi);
+            if (x3) st_shared16(sA_lo + o, lo);
           }
         }
-      }
-      if (d.flags & GG_EPI_ATOMIC) {
+        if (b_thread && !dbg_nosplit) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (co[j] >= 0) atomicAdd(d.C + co[j], o[j]);
-      } else {
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          const int b = 4 * g;
-          if (co[b + 3] >= 0 && co[b + 1] == co[b] + 1 && co[b + 2] == co[b] + 2 && co[b + 3] == co[b] + 3 && (co[b] & 3) == 0) {
-            *reinterpret_cast<float4*>(d.C + co[b]) = make_float4(o[b], o[b + 1], o[b + 2], o[b + 3]);
-          } else {
-#pragma unroll
-            for (int j = b; j < b + 4; ++j)
-              if (co[j] >= 0) d.C[co[j]] = o[j];
+          for (int i = 0; i < 4; ++i) {
+            if (b_rvec && i >= 1) break;
+            uint4 hi, lo;
+            split8((a_rvec || b_rvec) ? xb[i] : xa[i], hi, lo);
+            const uint32_t o = sw128(b_rvec ? qb : 4 * qb + i, c8);
+            st_shared16(sB_hi + o, hi);
+            if (x3) st_shared16(sB_lo + o, lo);
           }
         }
+        fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+        mbar_arrive(smem_u32(&bar_full[s]));
+      }
+      if (do_colsum && b_thread) {           // bias gradients: column sums of the B operand rows of this r-range
+        const int nb = ti.n0 + 4 * qb;
+        if (nb + 0 < d.N) atomicAdd(d.colsum + nb + 0, csum.x);
+        if (nb + 1 < d.N) atomicAdd(d.colsum + nb + 1, csum.y);
+        if (nb + 2 < d.N) atomicAdd(d.colsum + nb + 2, csum.z);
+        if (nb + 3 < d.N) atomicAdd(d.colsum + nb + 3, csum.w);
       }
     }
-    if (do_colsum) {
-      if (b_thread) {
-        atomicAdd(&cs[4 * qb + 0], csum.x); atomicAdd(&cs[4 * qb + 1], csum.y);
-        atomicAdd(&cs[4 * qb + 2], csum.z); atomicAdd(&cs[4 * qb + 3], csum.w);
-      }
-    }
-    tc_fence_before();
-    asm volatile("bar.sync 1, %0;" ::"n"(NPROD));           // producers only
-    if ((d.flags & GG_COLSUM) && tm == 0 && !b_rvec && tid < TN && n0 + tid < d.N) atomicAdd(d.colsum + n0 + tid, cs[tid]);
-  } else {
+  } else if (warp == MMA_WARP) {
     // =========================================================================== MMA issuer
-    if (lane == 0 && nchunks > 0) {
-      const uint32_t idesc = umma_idesc(TM, un);
-      for (int ch = 0; ch < nchunks; ++ch) {
-        const int s = ch % STAGES;
-        mbar_wait(smem_u32(&bar_full[s]), (ch / STAGES) & 1);
+    if (lane == 0) {
+      uint32_t gc = 0, it = 0;
+      for (int tile = blockIdx.x; tile < pk.total_tiles; tile += gridDim.x) {
+        const TileInfo ti = tile_info(pk, tile);
+        if (ti.nchunks == 0) continue;
+        const uint32_t buf = it & 1;
+        if (it >= 2) mbar_wait(smem_u32(&bar_acc_empty[buf]), ((it >> 1) - 1) & 1);
         tc_fence_after();
-        const uint32_t sA_hi = ring + s * STAGE_BYTES, sA_lo = sA_hi + A_BYTES;
-        const uint32_t sB_hi = sA_lo + A_BYTES, sB_lo = sB_hi + B_BYTES;
+        const uint32_t idesc = umma_idesc(TM, ti.un);
+        const uint32_t acc = tmem + buf * TN;
+        for (int ch = 0; ch < ti.nchunks; ++ch, ++gc) {
+          const int s = gc % STAGES;
+          mbar_wait(smem_u32(&bar_full[s]), (gc / STAGES) & 1);
+          tc_fence_after();
+          const uint32_t sA_hi = ring + s * STAGE_BYTES, sA_lo = sA_hi + A_BYTES;
+          const uint32_t sB_hi = sA_lo + A_BYTES, sB_lo = sB_hi + B_BYTES;
 #pragma unroll
-        for (int k = 0; k < TK / 16; ++k) {
-          const uint64_t ah = umma_desc(sA_hi + k * 32), bh = umma_desc(sB_hi + k * 32);
-          umma_bf16(tmem, ah, bh, idesc, (ch | k) ? 1u : 0u);
-          if (x3) {
-            const uint64_t al = umma_desc(sA_lo + k * 32), bl = umma_desc(sB_lo + k * 32);
-            umma_bf16(tmem, ah, bl, idesc, 1u);
-            umma_bf16(tmem, al, bh, idesc, 1u);
+          for (int k = 0; k < TK / 16; ++k) {
+            if (dbg_nomma) break;
+            const uint64_t ah = umma_desc(sA_hi + k * 32), bh = umma_desc(sB_hi + k * 32);
+            umma_bf16(acc, ah, bh, idesc, (ch | k) ? 1u : 0u);
+            if (x3) {
+              const uint64_t al = umma_desc(sA_lo + k * 32), bl = umma_desc(sB_lo + k * 32);
+              umma_bf16(acc, ah, bl, idesc, 1u);
+              umma_bf16(acc, al, bh, idesc, 1u);
+            }
           }
+          umma_commit(smem_u32(&bar_empty[s]));        // frees the ring slot when these MMAs retire
         }
-        umma_commit(smem_u32(&bar_empty[s]));      // frees the ring slot when these MMAs retire
+        umma_commit(smem_u32(&bar_acc_full[buf]));     // accumulator complete -> epilogue
+        ++it;
       }
-      umma_commit(smem_u32(&bar_accum));           // accumulator complete -> epilogue
     }
     __syncwarp();
+  } else {
+    // =========================================================================== epilogue (4 warps)
+    const int lq = warp & 3;                       // TMEM lane quarter this warp may access
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < pk.total_tiles; tile += gridDim.x) {
+      const TileInfo ti = tile_info(pk, tile);
+      if (ti.nchunks == 0) continue;
+      const GemmDesc& d = pk.d[ti.p];
+      const uint32_t buf = it & 1;
+      const int m = ti.m0 + lq * 32 + lane;
+      const bool m_ok = m < d.M;
+      const int cm = m_ok ? d.cM[m] : 0;           // issued before the wait: overlaps the mainloop
+      const int km = (m_ok && (d.flags & GG_EPI_MASK)) ? (d.kM ? d.kM[m] : cm) : 0;
+      mbar_wait(smem_u32(&bar_acc_full[buf]), (it >> 1) & 1);
+      tc_fence_after();
+      // 16 accumulator columns per round: TMEM load, then one batch of table / bias / mask loads, then stores
+#pragma unroll 1
+      for (int cb = 0; cb < TN; cb += 16) {
+        if (cb >= ti.un) break;                     // warp-uniform
+        uint32_t v[16];
+        const uint32_t taddr = tmem + buf * TN + ((uint32_t)(lq * 32) << 16) + (uint32_t)cb;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (cb + 16 >= ti.un) {                     // last TMEM read of this tile: hand the accumulator back
+          tc_fence_before();
+          mbar_arrive(smem_u32(&bar_acc_empty[buf]));
+        }
+        if (!m_ok || dbg_nostore) continue;
+        const int nb0 = ti.n0 + cb;
+        // fast path: 4 aligned, contiguous groups of 4 columns (every tensor-core problem of the SAC step)
+        int cn[4];
+        bool fast = nb0 + 16 <= d.N;
+        if (fast) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) cn[g] = d.cN[nb0 + 4 * g];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) fast = fast && (((cm + cn[g]) & 3) == 0) && (d.cN[nb0 + 4 * g + 3] == cn[g] + 3);
+        }
+        if (fast) {
+          float4 o[4];
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            o[g] = make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2]),
+                               __uint_as_float(v[4 * g + 3]));
+          if (d.flags & GG_EPI_BIAS_RELU) {
+            float4 bb[4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) bb[g] = ldg4(d.bias + nb0 + 4 * g);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              o[g].x = fmaxf(o[g].x + bb[g].x, 0.f); o[g].y = fmaxf(o[g].y + bb[g].y, 0.f);
+              o[g].z = fmaxf(o[g].z + bb[g].z, 0.f); o[g].w = fmaxf(o[g].w + bb[g].w, 0.f);
+            }
+          }
+          if (d.flags & GG_EPI_MASK) {
+            float4 mk[4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) mk[g] = ldg4(d.mask + km + (d.kN ? d.kN[nb0 + 4 * g] : cn[g]));
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              o[g].x = mk[g].x > 0.f ? o[g].x : 0.f; o[g].y = mk[g].y > 0.f ? o[g].y : 0.f;
+              o[g].z = mk[g].z > 0.f ? o[g].z : 0.f; o[g].w = mk[g].w > 0.f ? o[g].w : 0.f;
+            }
+          }
+          if (d.flags & GG_EPI_ATOMIC) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              float* c = d.C + cm + cn[g];
+              atomicAdd(c + 0, o[g].x); atomicAdd(c + 1, o[g].y); atomicAdd(c + 2, o[g].z); atomicAdd(c + 3, o[g].w);
+            }
+          } else {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) *reinterpret_cast<float4*>(d.C + cm + cn[g]) = o[g];
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int n = nb0 + j;
+            if (n >= d.N) break;
+            float o = __uint_as_float(v[j]);
+            const int cnj = d.cN[n];
+            if (d.flags & GG_EPI_BIAS_RELU) o = fmaxf(o + d.bias[n], 0.f);
+            if (d.flags & GG_EPI_MASK) o = d.mask[km + (d.kN ? d.kN[n] : cnj)] > 0.f ? o : 0.f;
+            if (d.flags & GG_EPI_ATOMIC) atomicAdd(d.C + cm + cnj, o);
+            else d.C[cm + cnj] = o;
+          }
+        }
+      }
+      ++it;
+    }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == NPROD / 32) {
+  if (warp == MMA_WARP) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TN));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS));
   }
 }
-}  // namespace
-
-int gg_tc_smem_bytes() { return SMEM_BYTES; }
 
 template <bool AR, bool BR>
-static cudaError_t launch_mode(const GemmDesc* dev_descs, int ndesc, int total_tiles, int x3, cudaStream_t s) {
+cudaError_t launch_mode(const DescPack& pk, int x3, int num_sms, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gg_tc_kernel<AR, BR>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  gg_tc_kernel<AR, BR><<<total_tiles, NTHREADS, SMEM_BYTES, s>>>(dev_descs, ndesc, x3);
+  const int grid = pk.total_tiles < num_sms ? pk.total_tiles : num_sms;
+  gg_tc_kernel<AR, BR><<<grid, NTHREADS, SMEM_BYTES, s>>>(pk, x3);
   return cudaSuccess;
 }
+}  // namespace
+
+int gg_tc_smem_bytes() { return SMEM_BYTES; }
 
 // All problems of one launch share the operand-contiguity mode (flags & (GG_A_RVEC | GG_B_RVEC)).
-cudaError_t gg_tc_launch(const GemmDesc* dev_descs, int ndesc, int total_tiles, int mode_flags, int x3, cudaStream_t s) {
+// host_descs: the group's descriptors (at most GG_TC_MAX_DESCS), passed as a __grid_constant__ pack.
+cudaError_t gg_tc_launch(const GemmDesc* host_descs, int ndesc, int total_tiles, int mode_flags, int x3, int num_sms,
+                         cudaStream_t s) {
   if (total_tiles <= 0) return cudaSuccess;
+  if (ndesc > GG_TC_MAX_DESCS) return cudaErrorInvalidValue;
+  DescPack pk;
+  for (int i = 0; i < ndesc; ++i) pk.d[i] = host_descs[i];
+  pk.n = ndesc;
+  pk.total_tiles = total_tiles;
   const bool ar = mode_flags & GG_A_RVEC, br = mode_flags & GG_B_RVEC;
-  if (ar && br) return launch_mode<true, true>(dev_descs, ndesc, total_tiles, x3, s);
-  if (ar) return launch_mode<true, false>(dev_descs, ndesc, total_tiles, x3, s);
-  if (br) return launch_mode<false, true>(dev_descs, ndesc, total_tiles, x3, s);
-  return launch_mode<false, false>(dev_descs, ndesc, total_tiles, x3, s);
+  if (ar && br) return launch_mode<true, true>(pk, x3, num_sms, s);
+  if (ar) return launch_mode<true, false>(pk, x3, num_sms, s);
+  if (br) return launch_mode<false, true>(pk, x3, num_sms, s);
+  return launch_mode<false, false>(pk, x3, num_sms, s);
 }
 
 }  // namespace b2g

@@ -86,6 +86,7 @@ int64_t pad32(int64_t n) { return (n + 31) / 32 * 32; }
 struct b2g_sac {
   b2g_sac_cfg cfg{};
   bool cnn = false;
+  int num_sms = 148;
   int B = 0, A = 0, H = 0, E = 0, Cimg = 0, feat_dim = 0, FS = 0;
   int Hi = 0, Wi = 0, H1 = 0, W1 = 0, H2 = 0, W2 = 0, H3 = 0, W3 = 0;
   std::vector<Tensor> tensors;
@@ -652,9 +653,10 @@ int issue_step(b2g_sac* h, bool sampled, bool apply, bool want_per_sample, Prof*
   prep_launch(pa, s); ++n; mark("prep");
   gather_launch(make_gather(h, sampled, true), s); ++n; mark("gather_normalize");
   CK(cudaMemsetAsync(h->G, 0, (size_t)(h->n_train + MET_COUNT) * sizeof(float), s)); ++n; mark("zero_grads");
-  const int x3 = h->cfg.precision == B2G_PREC_BF16X3 ? 1 : 0;
+  int x3 = h->cfg.precision == B2G_PREC_BF16X3 ? 1 : 0;
+  if (const char* dbg = getenv("B2G_TC_DEBUG")) x3 |= atoi(dbg) << 8;   // kernel bring-up toggles (gg_tc.cu)
   auto run_group = [&](GemmGroup& g) -> int {
-    if (g.tc) CK(gg_tc_launch(g.dev, (int)g.host.size(), g.total_tiles, g.host[0].flags, x3, s));
+    if (g.tc) CK(gg_tc_launch(g.host.data(), (int)g.host.size(), g.total_tiles, g.host[0].flags, x3, h->num_sms, s));
     else gg_simt_launch(g.dev, (int)g.host.size(), g.total_tiles, s);
     ++n; mark(g.name.c_str());
     return 0;
@@ -773,6 +775,7 @@ int b2g_sac_create(const b2g_sac_cfg* cfg, b2g_sac** out) {
 
   b2g_sac* h = new b2g_sac();
   h->cfg = *cfg;
+  h->num_sms = prop.multiProcessorCount;
   h->cfg.nccl_id = nullptr; h->cfg.nccl_lib = nullptr;
   h->cnn = cfg->obs_h > 0;
   h->B = cfg->batch; h->A = cfg->n_act; h->H = cfg->hidden;
@@ -1028,7 +1031,7 @@ int b2g_sac_act(b2g_sac* h, const float* obs, int n, int deterministic, float* a
     g.indices = nullptr;
     gather_launch(g, h->stream);
     for (auto& gr : h->act_groups) {
-      if (gr.tc) CK(gg_tc_launch(gr.dev, (int)gr.host.size(), gr.total_tiles, gr.host[0].flags, h->cfg.precision == B2G_PREC_BF16X3 ? 1 : 0, h->stream));
+      if (gr.tc) CK(gg_tc_launch(gr.host.data(), (int)gr.host.size(), gr.total_tiles, gr.host[0].flags, h->cfg.precision == B2G_PREC_BF16X3 ? 1 : 0, h->num_sms, h->stream));
       else gg_simt_launch(gr.dev, (int)gr.host.size(), gr.total_tiles, h->stream);
     }
     b2g::act_launch(make_tail(h, false), chunk, deterministic, h->pi_out, h->stream);
