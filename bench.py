@@ -251,10 +251,10 @@ def main():
     # ---- dominant-kernel roofline: per-launch device time of every group of ONE step (CUDA events on
     # the learner's stream between launches), on rank 0
     line = None
+    prof = None
+    for _ in range(3):              # every rank: the step contains the all-reduce
+        prof = L.profile_step(lr=LR)
     if rank == 0:
-        prof = None
-        for _ in range(3):
-            prof = L.profile_step(lr=LR)
         gemm_groups = {k: v for k, v in prof.items() if k.startswith("conv") or k.startswith("fc1_") or k.startswith("heads_fc0")
                        or k in ("heads_wgrad", "heads_dgrad")}
         gemm_ms = sum(gemm_groups.values())

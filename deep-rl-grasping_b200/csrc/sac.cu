@@ -845,6 +845,9 @@ int b2g_sac_create(const b2g_sac_cfg* cfg, b2g_sac** out) {
     memcpy(id.b, cfg->nccl_id, 128);
     int nrc = g_nccl.CommInitRank(&h->nccl_comm, cfg->nranks, id, cfg->rank);
     if (nrc != 0) return bail(fail(B2G_ENCCL, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "?")));
+    // warm the communicator up outside any stream capture (NCCL allocates its channels lazily)
+    nrc = g_nccl.AllReduce(h->G, h->G, (size_t)(h->n_train + MET_COUNT), 7, 0, h->nccl_comm, h->stream);
+    if (nrc != 0 || cudaStreamSynchronize(h->stream) != cudaSuccess) return bail(fail(B2G_ENCCL, "NCCL warm-up all-reduce failed"));
   }
   const char* ng = getenv("B2G_NO_GRAPH");
   h->use_graph = !(ng && ng[0] == '1');
