@@ -9,6 +9,27 @@
 namespace b2g {
 
 // ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch: a kernel launched through launch_pdl() may start (smem carve-up,
+// barrier init, TMEM allocation) while its predecessor on the stream is still running; it must call
+// pdl_wait() before touching global memory, and pdl_trigger() lets ITS successor start early.
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
+bool pdl_enabled();   // sac.cu: B2G_PDL != 0
+
+// ---------------------------------------------------------------------------------------------
 // Gather-GEMM problem descriptor.  One engine serves every dense contraction on the path:
 //   C[cM[m] + cN[n]]  (=|+=)  epi( sum_r  A[aM[m] + aR[r]] * B[bR[r] + bN[n]] )
 // The offset tables (built once on the host, resident in HBM/L2) encode im2col for the forward
@@ -22,6 +43,9 @@ enum GemmFlags : int {
   GG_EPI_MASK = 1 << 3,   // C = acc * (mask[kM[m] + kN[n]] > 0)
   GG_EPI_ATOMIC = 1 << 4, // split-R accumulate into pre-zeroed C
   GG_COLSUM = 1 << 5,     // colsum[n] += sum_r B(r, n)   (bias gradients; tile_m == 0 only)
+  GG_PLANES = 1 << 6,     // operands come pre-split as BF16 hi/lo planes (A_hi.., B_hi..), copied by cp.async
+  GG_A_ALIGN4 = 1 << 7,   // plane A rows are only 8-byte aligned (conv1 with one image channel)
+  GG_CN_AFFINE4 = 1 << 8, // host-verified: cN / kN contiguous inside aligned 4-column groups, outputs 16-byte aligned
 };
 
 struct GemmDesc {
@@ -35,6 +59,11 @@ struct GemmDesc {
   const float* bias;
   const float* mask;
   float* colsum;
+  // BF16 hi/lo planes (same element offsets as the fp32 tensors; B planes may use their own tables)
+  const uint16_t* A_hi; const uint16_t* A_lo;
+  const uint16_t* B_hi; const uint16_t* B_lo;
+  const int* bR_p; const int* bN_p;
+  uint16_t* C_hi; uint16_t* C_lo;      // optional plane copy of the output (feeds the next contraction)
   int M, N, R;
   int flags;
   int splitR;
@@ -60,6 +89,7 @@ constexpr int GG_SIMT_BM = 64, GG_SIMT_BN = 64, GG_SIMT_BK = 16;
 cudaError_t gg_tc_launch(const GemmDesc* host_descs, int ndesc, int total_tiles, int mode_flags, int x3, int num_sms, cudaStream_t s);
 constexpr int GG_TC_MAX_DESCS = 16;
 int gg_tc_smem_bytes();
+extern long long* g_tc_trace;   // bring-up hook (gg_tc.cu)
 constexpr int GG_TC_BM = 128, GG_TC_BN = 64, GG_TC_BK = 64;
 
 // ---------------------------------------------------------------------------------------------
@@ -125,6 +155,16 @@ struct OptimArgs {
 };
 void optim_launch(const OptimArgs& a, cudaStream_t s);
 
+// weights -> BF16 hi/lo planes, original [R,N] layout and transposed [N,R] (optim.cu)
+struct PlaneJob {
+  const float* src;            // [R, N] row-major fp32 (TF layout: HWIO filters flattened, dense [in,out])
+  uint16_t* hi; uint16_t* lo;  // [R, N] planes (may be null)
+  uint16_t* hiT; uint16_t* loT;// [N, R] planes (may be null)
+  int R, N;
+  int tile_start;              // first 32x32 tile of this job in the flattened launch
+};
+void planes_launch(const PlaneJob* dev_jobs, int njobs, int total_tiles, cudaStream_t s);
+
 struct PrepArgs {          // 1-CTA kernel at the head of every step
   long long* counters;     // [0..2] Adam t per optimiser, [3] n_updates, [4] rng step counter
   double* step_consts;     // lr_t x3
@@ -147,6 +187,7 @@ struct GatherArgs {
   int B, H, W, Cfull;        // CNN: obs [H,W,Cfull]; MLP: H = 0, W = obs_dim
   float scale;               // 255 for CNN, 1 for MLP
   float* x_obs; float* x_next;   // CNN: [B,H,W,Cfull-1] image planes (scaled)
+  uint16_t* x_obs_hi; uint16_t* x_obs_lo; uint16_t* x_next_hi; uint16_t* x_next_lo;   // optional BF16 planes of x
   float* F_pi; float* F_v; float* F_t; int FS; int feat_col; // feature rows: direct feature -> col feat_col; MLP: whole obs -> cols 0..
   float* rew_out; float* done_out; int n_act;
 };

@@ -4,6 +4,8 @@
 // on-device numerical reference the tcgen05 engine (gg_tc.cu) is validated against, and the
 // engine used for the small head-side contractions in every mode.
 // Tile: 64(m) x 64(n) x 16(r), 256 threads, 4x4 outputs per thread, register-prefetched smem.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace b2g {
@@ -25,6 +27,8 @@ __global__ void __launch_bounds__(256) gg_simt_kernel(const GemmDesc* __restrict
     sd = descs[p];
   }
   if (tid < BN) cs[tid] = 0.f;
+  pdl_trigger();
+  pdl_wait();
   __syncthreads();
   const GemmDesc& d = sd;
   int t = blockIdx.x - d.tile_start;
@@ -206,6 +210,15 @@ __global__ void __launch_bounds__(256) gg_simt_kernel(const GemmDesc* __restrict
         }
       }
     }
+    if (d.C_hi) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (co[j] >= 0) {
+          const __nv_bfloat16 hh = __float2bfloat16_rn(v[j]);
+          d.C_hi[co[j]] = __bfloat16_as_ushort(hh);
+          d.C_lo[co[j]] = __bfloat16_as_ushort(__float2bfloat16_rn(v[j] - __bfloat162float(hh)));
+        }
+    }
     if (d.flags & GG_EPI_ATOMIC) {
 #pragma unroll
       for (int j = 0; j < 4; ++j)
@@ -229,7 +242,7 @@ __global__ void __launch_bounds__(256) gg_simt_kernel(const GemmDesc* __restrict
 
 void gg_simt_launch(const GemmDesc* dev_descs, int ndesc, int total_tiles, cudaStream_t s) {
   if (total_tiles <= 0) return;
-  gg_simt_kernel<<<total_tiles, 256, 0, s>>>(dev_descs, ndesc);
+  launch_pdl(gg_simt_kernel, dim3(total_tiles), dim3(256), 0, s, pdl_enabled(), dev_descs, ndesc);
 }
 
 }  // namespace b2g

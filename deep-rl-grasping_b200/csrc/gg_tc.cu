@@ -40,6 +40,7 @@ struct DescPack {
   GemmDesc d[GG_TC_MAX_DESCS];
   int n;
   int total_tiles;
+  long long* trace;   // bring-up: per-tile clock64 stamps of CTA 0 (nullptr in production)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -112,6 +113,17 @@ __device__ __forceinline__ uint32_t sw128(int row, int c) { return (uint32_t)(ro
 __device__ __forceinline__ void st_shared16(uint32_t addr, const uint4& v) {
   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+// 16-byte (or 8-byte) asynchronous global->shared copy with zero fill beyond src_bytes
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+// the mbarrier receives one arrival when all cp.async issued so far by this thread have landed
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ float4 ldg4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
 struct TileInfo {
@@ -139,12 +151,14 @@ __device__ __forceinline__ TileInfo tile_info(const DescPack& pk, int tile) {
   return ti;
 }
 
-template <bool a_rvec, bool b_rvec>
+template <bool a_rvec, bool b_rvec, bool planes>
 __global__ void __launch_bounds__(NTHREADS, 1) gg_tc_kernel(const __grid_constant__ DescPack pk, int x3_in) {
   int x3 = x3_in;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[STAGES], bar_empty[STAGES], bar_acc_full[2], bar_acc_empty[2];
   __shared__ uint32_t tmem_slot;
+  __shared__ int s_cn[TN], s_kn[TN];
+  __shared__ __align__(16) float s_bias[TN];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool dbg_noload = x3 & 0x100, dbg_nomma = x3 & 0x200, dbg_nostore = x3 & 0x400, dbg_nosplit = x3 & 0x800;
@@ -169,8 +183,93 @@ __global__ void __launch_bounds__(NTHREADS, 1) gg_tc_kernel(const __grid_constan
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
   const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  pdl_trigger();      // the next kernel on the stream may begin its own prologue now
+  pdl_wait();         // everything above overlapped the predecessor; its results are visible from here on
 
-  if (warp < MMA_WARP) {
+  if (planes && warp < MMA_WARP) {
+    // =========================================================================== producers (BF16 planes, cp.async)
+    // Operands are already split into BF16 hi/lo planes in HBM: every 16-byte chunk of a UMMA tile is one
+    // cp.async straight into its swizzled slot -- no registers, no conversion; the ring depth is the prefetch
+    // depth, and the slot's mbarrier is signalled by the copies themselves (cp.async.mbarrier.arrive.noinc).
+    const int c8 = tid & 7, q = tid >> 3;      // chunk, row (A rows q and q + 64; B row q)
+    uint32_t gc = 0;
+    // per-tile gather state, fetched ONE TILE AHEAD so that the row-offset / table round trips of tile i+1
+    // overlap the copies of tile i (the ring keeps running across tile boundaries)
+    struct TState { TileInfo ti; int a_off[2]; bool a_ok[2]; int b_off; bool b_ok; int ta, tb; bool valid; };
+    auto fetch = [&](int tile) {
+      TState t;
+      t.valid = tile < pk.total_tiles;
+      if (!t.valid) return t;
+      t.ti = tile_info(pk, tile);
+      const GemmDesc& d = pk.d[t.ti.p];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int m = t.ti.m0 + q + 64 * i;
+        t.a_ok[i] = m < d.M;
+        t.a_off[i] = t.a_ok[i] ? d.aM[m] : 0;
+      }
+      const int nB = t.ti.n0 + q;
+      t.b_ok = nB < d.N;
+      t.b_off = t.b_ok ? (d.bN_p ? d.bN_p : d.bN)[nB] : 0;
+      t.ta = t.tb = 0;
+      if (t.ti.nchunks > 0) {
+        t.ta = d.aR[t.ti.r_begin + c8 * 8];
+        t.tb = (d.bR_p ? d.bR_p : d.bR)[t.ti.r_begin + c8 * 8];
+      }
+      return t;
+    };
+    TState cur = fetch(blockIdx.x);
+    int tcount = 0;
+    for (int tile = blockIdx.x; tile < pk.total_tiles; tile += gridDim.x, ++tcount) {
+      if (pk.trace && blockIdx.x == 0 && tid == 0 && tcount < 64) pk.trace[tcount * 8 + 0] = clock64();
+      const TState nxt = fetch(tile + gridDim.x);
+      const TileInfo ti = cur.ti;
+      if (ti.nchunks > 0) {
+        const GemmDesc& d = pk.d[ti.p];
+        const bool align4 = d.flags & GG_A_ALIGN4;
+        const int* __restrict__ tabA = d.aR;
+        const int* __restrict__ tabB = d.bR_p ? d.bR_p : d.bR;
+        int ta = cur.ta, tb = cur.tb;
+        for (int ch = 0; ch < ti.nchunks; ++ch, ++gc) {
+          const int s = gc % STAGES;
+          const uint32_t sA_hi = ring + s * STAGE_BYTES, sA_lo = sA_hi + A_BYTES;
+          const uint32_t sB_hi = sA_lo + A_BYTES, sB_lo = sB_hi + B_BYTES;
+          const int r0 = ti.r_begin + ch * TK + c8 * 8;
+          const int nbytes = max(0, min(8, ti.r_end - r0)) * 2;
+          if (gc >= STAGES) mbar_wait(smem_u32(&bar_empty[s]), ((gc / STAGES) - 1) & 1);
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const uint32_t o = sw128(q + 64 * i, c8);
+            const int nb = cur.a_ok[i] ? nbytes : 0;
+            const size_t e = (size_t)(cur.a_off[i] + ta);
+            if (!align4) {
+              cp_async16(sA_hi + o, d.A_hi + e, nb);
+              if (x3) cp_async16(sA_lo + o, d.A_lo + e, nb);
+            } else {
+              cp_async8(sA_hi + o, d.A_hi + e, min(nb, 8));
+              cp_async8(sA_hi + o + 8, d.A_hi + e + 4, max(nb - 8, 0));
+              if (x3) {
+                cp_async8(sA_lo + o, d.A_lo + e, min(nb, 8));
+                cp_async8(sA_lo + o + 8, d.A_lo + e + 4, max(nb - 8, 0));
+              }
+            }
+          }
+          {
+            const uint32_t o = sw128(q, c8);
+            const int nb = cur.b_ok ? nbytes : 0;
+            const size_t e = (size_t)(cur.b_off + tb);
+            cp_async16(sB_hi + o, d.B_hi + e, nb);
+            if (x3) cp_async16(sB_lo + o, d.B_lo + e, nb);
+          }
+          cp_async_arrive_noinc(smem_u32(&bar_full[s]));
+          if (ch + 1 < ti.nchunks) { ta = tabA[r0 + TK]; tb = tabB[r0 + TK]; }
+        }
+      }
+      if (pk.trace && blockIdx.x == 0 && tid == 0 && tcount < 64) pk.trace[tcount * 8 + 1] = clock64();
+      cur = nxt;
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+  } else if (warp < MMA_WARP) {
     // =========================================================================== producers
     const int c8 = tid & 7;             // 16-byte chunk (8 r values) inside the 64-wide r-chunk
     const int q = tid >> 3;             // 0..63
@@ -366,6 +465,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gg_tc_kernel(const __grid_constan
         for (int ch = 0; ch < ti.nchunks; ++ch, ++gc) {
           const int s = gc % STAGES;
           mbar_wait(smem_u32(&bar_full[s]), (gc / STAGES) & 1);
+          if (pk.trace && blockIdx.x == 0 && ch == 0 && it < 64) pk.trace[it * 8 + 2] = clock64();
+          if (planes) fence_proxy_async();       // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
           tc_fence_after();
           const uint32_t sA_hi = ring + s * STAGE_BYTES, sA_lo = sA_hi + A_BYTES;
           const uint32_t sB_hi = sA_lo + A_BYTES, sB_lo = sB_hi + B_BYTES;
@@ -383,13 +484,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) gg_tc_kernel(const __grid_constan
           umma_commit(smem_u32(&bar_empty[s]));        // frees the ring slot when these MMAs retire
         }
         umma_commit(smem_u32(&bar_acc_full[buf]));     // accumulator complete -> epilogue
+        if (pk.trace && blockIdx.x == 0 && it < 64) pk.trace[it * 8 + 3] = clock64();
         ++it;
       }
     }
     __syncwarp();
   } else {
     // =========================================================================== epilogue (4 warps)
+    // Column-side tables (cN, kN, bias) of the tile are staged in shared memory BEFORE the accumulator is
+    // waited for, so the per-round work after tcgen05.ld is: (mask loads ->) math -> stores, no dependent
+    // table round trips.  Fast path contract (GG_CN_AFFINE4, verified on the host): inside every aligned
+    // group of 4 columns cN / kN are contiguous and the output offset is 16-byte aligned.
     const int lq = warp & 3;                       // TMEM lane quarter this warp may access
+    const int et = tid - (MMA_WARP + 1) * 32;      // 0..127
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < pk.total_tiles; tile += gridDim.x) {
       const TileInfo ti = tile_info(pk, tile);
@@ -400,9 +507,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) gg_tc_kernel(const __grid_constan
       const bool m_ok = m < d.M;
       const int cm = m_ok ? d.cM[m] : 0;           // issued before the wait: overlaps the mainloop
       const int km = (m_ok && (d.flags & GG_EPI_MASK)) ? (d.kM ? d.kM[m] : cm) : 0;
+      asm volatile("bar.sync 2, %0;" ::"n"(NEPI));  // previous tile's readers of the staged tables are done
+      if (et < TN) {
+        const int n = ti.n0 + et;
+        const bool ok = n < d.N;
+        const int cn = ok ? d.cN[n] : 0;
+        s_cn[et] = cn;
+        s_kn[et] = ok ? (d.kN ? d.kN[n] : cn) : 0;
+      } else if (et < 2 * TN) {
+        const int n = ti.n0 + et - TN;
+        s_bias[et - TN] = ((d.flags & GG_EPI_BIAS_RELU) && n < d.N) ? d.bias[n] : 0.f;
+      }
+      asm volatile("bar.sync 2, %0;" ::"n"(NEPI));
+      const bool tr = pk.trace && blockIdx.x == 0 && warp == MMA_WARP + 1 && lane == 0 && it < 64;
       mbar_wait(smem_u32(&bar_acc_full[buf]), (it >> 1) & 1);
       tc_fence_after();
-      // 16 accumulator columns per round: TMEM load, then one batch of table / bias / mask loads, then stores
+      if (tr) pk.trace[it * 8 + 4] = clock64();
+      const bool fastp = d.flags & GG_CN_AFFINE4;
 #pragma unroll 1
       for (int cb = 0; cb < TN; cb += 16) {
         if (cb >= ti.un) break;                     // warp-uniform
@@ -413,57 +534,63 @@ __global__ void __launch_bounds__(NTHREADS, 1) gg_tc_kernel(const __grid_constan
             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
               "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
             : "r"(taddr));
+        // mask values of this round: independent global loads, in flight while the TMEM load completes
+        const int nb0 = ti.n0 + cb;
+        const bool full16 = nb0 + 16 <= d.N;
+        float4 mk[4];
+        const bool use_mask = (d.flags & GG_EPI_MASK) && m_ok && fastp && full16 && !dbg_nostore;
+        if (use_mask) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) mk[g] = ldg4(d.mask + km + s_kn[cb + 4 * g]);
+        }
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (cb + 16 >= ti.un) {                     // last TMEM read of this tile: hand the accumulator back
           tc_fence_before();
           mbar_arrive(smem_u32(&bar_acc_empty[buf]));
+          if (tr) pk.trace[it * 8 + 5] = clock64();
         }
         if (!m_ok || dbg_nostore) continue;
-        const int nb0 = ti.n0 + cb;
-        // fast path: 4 aligned, contiguous groups of 4 columns (every tensor-core problem of the SAC step)
-        int cn[4];
-        bool fast = nb0 + 16 <= d.N;
-        if (fast) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) cn[g] = d.cN[nb0 + 4 * g];
-#pragma unroll
-          for (int g = 0; g < 4; ++g) fast = fast && (((cm + cn[g]) & 3) == 0) && (d.cN[nb0 + 4 * g + 3] == cn[g] + 3);
-        }
-        if (fast) {
+        if (fastp && full16) {
           float4 o[4];
 #pragma unroll
           for (int g = 0; g < 4; ++g)
             o[g] = make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2]),
                                __uint_as_float(v[4 * g + 3]));
           if (d.flags & GG_EPI_BIAS_RELU) {
-            float4 bb[4];
-#pragma unroll
-            for (int g = 0; g < 4; ++g) bb[g] = ldg4(d.bias + nb0 + 4 * g);
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-              o[g].x = fmaxf(o[g].x + bb[g].x, 0.f); o[g].y = fmaxf(o[g].y + bb[g].y, 0.f);
-              o[g].z = fmaxf(o[g].z + bb[g].z, 0.f); o[g].w = fmaxf(o[g].w + bb[g].w, 0.f);
+              const float4 bb = *reinterpret_cast<const float4*>(&s_bias[cb + 4 * g]);
+              o[g].x = fmaxf(o[g].x + bb.x, 0.f); o[g].y = fmaxf(o[g].y + bb.y, 0.f);
+              o[g].z = fmaxf(o[g].z + bb.z, 0.f); o[g].w = fmaxf(o[g].w + bb.w, 0.f);
             }
           }
-          if (d.flags & GG_EPI_MASK) {
-            float4 mk[4];
-#pragma unroll
-            for (int g = 0; g < 4; ++g) mk[g] = ldg4(d.mask + km + (d.kN ? d.kN[nb0 + 4 * g] : cn[g]));
+          if (use_mask) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               o[g].x = mk[g].x > 0.f ? o[g].x : 0.f; o[g].y = mk[g].y > 0.f ? o[g].y : 0.f;
               o[g].z = mk[g].z > 0.f ? o[g].z : 0.f; o[g].w = mk[g].w > 0.f ? o[g].w : 0.f;
             }
           }
+          if (d.C_hi) {      // BF16 hi/lo plane copy of the stored values (operand of the next contraction)
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const float x[8] = {o[g].x, o[g].y, o[g].z, o[g].w, 0.f, 0.f, 0.f, 0.f};
+              uint4 hi, lo;
+              split8(x, hi, lo);
+              const int c = cm + s_cn[cb + 4 * g];
+              *reinterpret_cast<uint2*>(d.C_hi + c) = make_uint2(hi.x, hi.y);
+              *reinterpret_cast<uint2*>(d.C_lo + c) = make_uint2(lo.x, lo.y);
+            }
+          }
           if (d.flags & GG_EPI_ATOMIC) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-              float* c = d.C + cm + cn[g];
+              float* c = d.C + cm + s_cn[cb + 4 * g];
               atomicAdd(c + 0, o[g].x); atomicAdd(c + 1, o[g].y); atomicAdd(c + 2, o[g].z); atomicAdd(c + 3, o[g].w);
             }
           } else {
 #pragma unroll
-            for (int g = 0; g < 4; ++g) *reinterpret_cast<float4*>(d.C + cm + cn[g]) = o[g];
+            for (int g = 0; g < 4; ++g) *reinterpret_cast<float4*>(d.C + cm + s_cn[cb + 4 * g]) = o[g];
           }
         } else {
 #pragma unroll
@@ -471,14 +598,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) gg_tc_kernel(const __grid_constan
             const int n = nb0 + j;
             if (n >= d.N) break;
             float o = __uint_as_float(v[j]);
-            const int cnj = d.cN[n];
-            if (d.flags & GG_EPI_BIAS_RELU) o = fmaxf(o + d.bias[n], 0.f);
-            if (d.flags & GG_EPI_MASK) o = d.mask[km + (d.kN ? d.kN[n] : cnj)] > 0.f ? o : 0.f;
+            const int cnj = s_cn[cb + j];
+            if (d.flags & GG_EPI_BIAS_RELU) o = fmaxf(o + s_bias[cb + j], 0.f);
+            if (d.flags & GG_EPI_MASK) o = d.mask[km + s_kn[cb + j]] > 0.f ? o : 0.f;
             if (d.flags & GG_EPI_ATOMIC) atomicAdd(d.C + cm + cnj, o);
             else d.C[cm + cnj] = o;
+            if (d.C_hi) {
+              const __nv_bfloat16 h = __float2bfloat16_rn(o);
+              d.C_hi[cm + cnj] = __bfloat16_as_ushort(h);
+              d.C_lo[cm + cnj] = __bfloat16_as_ushort(__float2bfloat16_rn(o - __bfloat162float(h)));
+            }
           }
         }
       }
+      if (tr) pk.trace[it * 8 + 6] = clock64();
       ++it;
     }
   }
@@ -490,17 +623,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) gg_tc_kernel(const __grid_constan
   }
 }
 
-template <bool AR, bool BR>
+template <bool AR, bool BR, bool PL>
 cudaError_t launch_mode(const DescPack& pk, int x3, int num_sms, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gg_tc_kernel<AR, BR>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gg_tc_kernel<AR, BR, PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   const int grid = pk.total_tiles < num_sms ? pk.total_tiles : num_sms;
-  gg_tc_kernel<AR, BR><<<grid, NTHREADS, SMEM_BYTES, s>>>(pk, x3);
-  return cudaSuccess;
+  return launch_pdl(gg_tc_kernel<AR, BR, PL>, dim3(grid), dim3(NTHREADS), SMEM_BYTES, s, pdl_enabled(), pk, x3);
 }
 }  // namespace
 
@@ -508,6 +640,8 @@ int gg_tc_smem_bytes() { return SMEM_BYTES; }
 
 // All problems of one launch share the operand-contiguity mode (flags & (GG_A_RVEC | GG_B_RVEC)).
 // host_descs: the group's descriptors (at most GG_TC_MAX_DESCS), passed as a __grid_constant__ pack.
+long long* g_tc_trace = nullptr;   // set by sac.cu for one traced launch
+
 cudaError_t gg_tc_launch(const GemmDesc* host_descs, int ndesc, int total_tiles, int mode_flags, int x3, int num_sms,
                          cudaStream_t s) {
   if (total_tiles <= 0) return cudaSuccess;
@@ -516,11 +650,13 @@ cudaError_t gg_tc_launch(const GemmDesc* host_descs, int ndesc, int total_tiles,
   for (int i = 0; i < ndesc; ++i) pk.d[i] = host_descs[i];
   pk.n = ndesc;
   pk.total_tiles = total_tiles;
+  pk.trace = g_tc_trace;
   const bool ar = mode_flags & GG_A_RVEC, br = mode_flags & GG_B_RVEC;
-  if (ar && br) return launch_mode<true, true>(pk, x3, num_sms, s);
-  if (ar) return launch_mode<true, false>(pk, x3, num_sms, s);
-  if (br) return launch_mode<false, true>(pk, x3, num_sms, s);
-  return launch_mode<false, false>(pk, x3, num_sms, s);
+  if (mode_flags & GG_PLANES) return launch_mode<true, true, true>(pk, x3, num_sms, s);
+  if (ar && br) return launch_mode<true, true, false>(pk, x3, num_sms, s);
+  if (ar) return launch_mode<true, false, false>(pk, x3, num_sms, s);
+  if (br) return launch_mode<false, true, false>(pk, x3, num_sms, s);
+  return launch_mode<false, false, false>(pk, x3, num_sms, s);
 }
 
 }  // namespace b2g

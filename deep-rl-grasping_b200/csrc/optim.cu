@@ -10,6 +10,8 @@
 //                   values_fn ([SB2] target_update_op), plus squared gradient norms per optimiser.
 #include <math.h>
 
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace b2g {
@@ -119,7 +121,48 @@ __global__ void __launch_bounds__(256) optim_kernel(OptimArgs a) {
     atomicAdd(a.metrics + MET_GN_PI + threadIdx.x, v);
   }
 }
+
+// weights -> BF16 hi/lo planes; 32x32 smem-tiled transpose for the [N,R] copy (both sides coalesced)
+__global__ void __launch_bounds__(256) planes_kernel(const PlaneJob* __restrict__ jobs, int njobs) {
+  __shared__ float tile[32][33];
+  int j = 0;
+  while (j + 1 < njobs && (int)blockIdx.x >= jobs[j + 1].tile_start) ++j;
+  const PlaneJob job = jobs[j];
+  const int t = blockIdx.x - job.tile_start;
+  const int tiles_n = (job.N + 31) / 32;
+  const int r0 = (t / tiles_n) * 32, n0 = (t % tiles_n) * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, n = n0 + tx;
+    float v = 0.f;
+    if (r < job.R && n < job.N) {
+      v = job.src[(size_t)r * job.N + n];
+      if (job.hi) {
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        job.hi[(size_t)r * job.N + n] = __bfloat16_as_ushort(h);
+        job.lo[(size_t)r * job.N + n] = __bfloat16_as_ushort(__float2bfloat16_rn(v - __bfloat162float(h)));
+      }
+    }
+    tile[i][tx] = v;
+  }
+  __syncthreads();
+  if (job.hiT) {
+    for (int i = ty; i < 32; i += 8) {
+      const int n = n0 + i, r = r0 + tx;
+      if (r < job.R && n < job.N) {
+        const float v = tile[tx][i];
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        job.hiT[(size_t)n * job.R + r] = __bfloat16_as_ushort(h);
+        job.loT[(size_t)n * job.R + r] = __bfloat16_as_ushort(__float2bfloat16_rn(v - __bfloat162float(h)));
+      }
+    }
+  }
+}
 }  // namespace
+
+void planes_launch(const PlaneJob* dev_jobs, int njobs, int total_tiles, cudaStream_t s) {
+  if (total_tiles > 0) planes_kernel<<<total_tiles, 256, 0, s>>>(dev_jobs, njobs);
+}
 
 void prep_launch(const PrepArgs& a, cudaStream_t s) { prep_kernel<<<1, 256, 0, s>>>(a); }
 

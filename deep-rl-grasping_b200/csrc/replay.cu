@@ -6,6 +6,8 @@
 // observation_input(scale=True) ((x-0)/255 for the Box(0,255) of robot.py:224-228), and the
 // channel split of custom_obs_policy.py:28-32 (last plane pixel [0,0] = direct feature).
 // HBM-bound: one coalesced pass over 2*B observations; no intermediate copies.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace b2g {
@@ -21,25 +23,70 @@ __global__ void __launch_bounds__(256) gather_kernel(GatherArgs g) {
   const int cimg = g.Cfull - 1;
   const double ret_istd = g.normc[0], clip_obs = g.normc[1], clip_rew = g.normc[2];
   const bool norm_obs = g.normc[3] != 0.0, norm_rew = g.normc[4] != 0.0;
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
-    float y = src[e];
+  const float inv_scale_denom = g.scale;
+  float* __restrict__ xdst = (which ? g.x_next : g.x_obs);
+  uint16_t* __restrict__ xhi = which ? g.x_next_hi : g.x_obs_hi;
+  uint16_t* __restrict__ xlo = which ? g.x_next_lo : g.x_obs_lo;
+  // 4 consecutive elements per thread (128-bit loads); E % 4 == 0 for every supported shape except odd MLP sizes
+  const int E4 = (E & 3) == 0 ? E >> 2 : 0;
+  for (int e4 = blockIdx.x * blockDim.x + threadIdx.x; e4 < E4; e4 += gridDim.x * blockDim.x) {
+    const float4 v = *reinterpret_cast<const float4*>(src + 4 * e4);
+    float y[4] = {v.x, v.y, v.z, v.w};
     if (norm_obs) {
-      double d = ((double)y - g.mean[e]) * g.var[e];       // var[] holds 1/sqrt(var+eps) (set_norm_stats)
-      d = fmin(fmax(d, -clip_obs), clip_obs);
-      y = (float)d;
-    }
-    y = y / g.scale;
-    if (cnn) {
-      const int c = e % g.Cfull, pix = e / g.Cfull;
-      if (c < cimg) {
-        (which ? g.x_next : g.x_obs)[((size_t)b * g.H * g.W + pix) * cimg + c] = y;
-      } else if (pix == 0) {
-        if (which) g.F_t[(size_t)b * g.FS + g.feat_col] = y;
-        else { g.F_pi[(size_t)b * g.FS + g.feat_col] = y; g.F_v[(size_t)b * g.FS + g.feat_col] = y; }
+      const double2 m0 = *reinterpret_cast<const double2*>(g.mean + 4 * e4), m1 = *reinterpret_cast<const double2*>(g.mean + 4 * e4 + 2);
+      const double2 s0 = *reinterpret_cast<const double2*>(g.var + 4 * e4), s1 = *reinterpret_cast<const double2*>(g.var + 4 * e4 + 2);
+      const double mm[4] = {m0.x, m0.y, m1.x, m1.y}, ss[4] = {s0.x, s0.y, s1.x, s1.y};   // ss = 1/sqrt(var+eps)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        double d = ((double)y[j] - mm[j]) * ss[j];
+        d = fmin(fmax(d, -clip_obs), clip_obs);
+        y[j] = (float)d;
       }
-    } else {
-      if (which) g.F_t[(size_t)b * g.FS + e] = y;
-      else { g.F_pi[(size_t)b * g.FS + e] = y; g.F_v[(size_t)b * g.FS + e] = y; }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int e = 4 * e4 + j;
+      const float yy = y[j] / inv_scale_denom;
+      if (cnn) {
+        const int c = e % g.Cfull, pix = e / g.Cfull;
+        if (c < cimg) {
+          const size_t o = ((size_t)b * g.H * g.W + pix) * cimg + c;
+          xdst[o] = yy;
+          if (xhi) {
+            const __nv_bfloat16 h = __float2bfloat16_rn(yy);
+            xhi[o] = __bfloat16_as_ushort(h);
+            xlo[o] = __bfloat16_as_ushort(__float2bfloat16_rn(yy - __bfloat162float(h)));
+          }
+        } else if (pix == 0) {
+          if (which) g.F_t[(size_t)b * g.FS + g.feat_col] = yy;
+          else { g.F_pi[(size_t)b * g.FS + g.feat_col] = yy; g.F_v[(size_t)b * g.FS + g.feat_col] = yy; }
+        }
+      } else {
+        if (which) g.F_t[(size_t)b * g.FS + e] = yy;
+        else { g.F_pi[(size_t)b * g.FS + e] = yy; g.F_v[(size_t)b * g.FS + e] = yy; }
+      }
+    }
+  }
+  if (E4 == 0) {   // generic scalar path
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
+      float y = src[e];
+      if (norm_obs) {
+        double d = ((double)y - g.mean[e]) * g.var[e];
+        d = fmin(fmax(d, -clip_obs), clip_obs);
+        y = (float)d;
+      }
+      y = y / g.scale;
+      if (cnn) {
+        const int c = e % g.Cfull, pix = e / g.Cfull;
+        if (c < cimg) xdst[((size_t)b * g.H * g.W + pix) * cimg + c] = y;
+        else if (pix == 0) {
+          if (which) g.F_t[(size_t)b * g.FS + g.feat_col] = y;
+          else { g.F_pi[(size_t)b * g.FS + g.feat_col] = y; g.F_v[(size_t)b * g.FS + g.feat_col] = y; }
+        }
+      } else {
+        if (which) g.F_t[(size_t)b * g.FS + e] = y;
+        else { g.F_pi[(size_t)b * g.FS + e] = y; g.F_v[(size_t)b * g.FS + e] = y; }
+      }
     }
   }
   if (which == 0 && blockIdx.x == 0 && g.act) {
@@ -61,8 +108,9 @@ __global__ void __launch_bounds__(256) gather_kernel(GatherArgs g) {
 
 void gather_launch(const GatherArgs& a, cudaStream_t s) {
   const int E = a.H > 0 ? a.H * a.W * a.Cfull : a.W;
-  int gx = (E + 256 * 4 - 1) / (256 * 4);
+  int gx = (E / 4 + 255) / 256;      // one 128-bit group per thread
   if (gx < 1) gx = 1;
+  if (gx > 4) gx = 4;
   dim3 grid(gx, a.B, a.next_obs ? 2 : 1);
   gather_kernel<<<grid, 256, 0, s>>>(a);
 }

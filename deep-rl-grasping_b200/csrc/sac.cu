@@ -27,6 +27,14 @@
 
 using namespace b2g;
 
+namespace b2g {
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("B2G_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
+}  // namespace b2g
+
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 #define CK(call)                                                                                  \
@@ -108,6 +116,16 @@ struct b2g_sac {
   float *h1[3]{}, *h2[3]{}, *h3[3]{}, *F[3]{};
   float *dZ4[2]{}, *dZ3p[2]{}, *dZ2p[2]{}, *dZ1[2]{};
   float *z0[5]{}, *a0[4]{}, *dz1[4]{}, *dz0_pi = nullptr, *dz0_v3 = nullptr;
+  // BF16 hi/lo planes ([..][0] = hi, [..][1] = lo) of the tensors that feed forward / dgrad contractions
+  bool use_planes = false;
+  uint16_t *xp[2][2]{}, *h1p[3][2]{}, *h2p[3][2]{}, *h3p[3][2]{};
+  uint16_t *dZ4p[2][2]{}, *dZ3pp[2][2]{}, *dZ2pp[2][2]{};
+  uint16_t* wp[3][4][4]{};          // [net][cnn1,cnn2,cnn3,fc1][hi, lo, hiT, loT]
+  PlaneJob* d_jobs = nullptr;
+  int n_jobs = 0, job_tiles = 0;
+  bool planes_dirty = true;
+  long long* dbg_trace = nullptr;
+  std::map<const int*, std::vector<int>> host_tabs;   // host copies of the offset tables (contract checks at build time)
   float *per_sample = nullptr, *pi_out = nullptr, *eps = nullptr, *rew_n = nullptr, *done_n = nullptr;
   int* indices = nullptr;
   float *s_obs = nullptr, *s_next = nullptr, *s_act = nullptr, *s_rew = nullptr, *s_done = nullptr;  // staged explicit batch
@@ -150,6 +168,7 @@ int upload_table(b2g_sac* h, const std::vector<int>& v, const int** out) {
   CK(cudaMemcpyAsync(d, v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
   CK(cudaStreamSynchronize(h->stream));   // v may be a temporary
   *out = d;
+  h->host_tabs[d] = v;
   return 0;
 }
 
@@ -246,6 +265,25 @@ int finalize_group(b2g_sac* h, GemmGroup& g) {
   for (auto& d : g.host) {
     d.tiles_m = (d.M + bm - 1) / bm;
     d.tiles_n = (d.N + bn - 1) / bn;
+    {   // GG_CN_AFFINE4: column tables contiguous in aligned groups of 4, row offsets multiples of 4
+      auto grp4 = [&](const int* tab, int n) {
+        auto it = h->host_tabs.find(tab);
+        if (it == h->host_tabs.end() || (int)it->second.size() < n) return false;
+        const std::vector<int>& v = it->second;
+        for (int i = 0; i + 3 < n; i += 4)
+          if ((v[i] & 3) || v[i + 1] != v[i] + 1 || v[i + 2] != v[i] + 2 || v[i + 3] != v[i] + 3) return false;
+        return true;
+      };
+      auto mult4 = [&](const int* tab, int n) {
+        auto it = h->host_tabs.find(tab);
+        if (it == h->host_tabs.end() || (int)it->second.size() < n) return false;
+        for (int i = 0; i < n; ++i) if (it->second[i] & 3) return false;
+        return true;
+      };
+      bool ok = (d.N % 4 == 0) && grp4(d.cN, d.N) && mult4(d.cM, d.M);
+      if (ok && (d.flags & GG_EPI_MASK)) ok = (!d.kN || grp4(d.kN, d.N)) && (!d.kM || mult4(d.kM, d.M));
+      if (ok) d.flags |= GG_CN_AFFINE4;
+    }
     if (d.flags & GG_EPI_ATOMIC) {     // split-R sized for this engine's tile grid
       const int tiles = d.tiles_m * d.tiles_n;
       int sp = std::max(1, (g.tc ? 148 : 148) / std::max(1, tiles));
@@ -312,6 +350,15 @@ int build_groups(b2g_sac* h) {
     }
     TAB(fcA, iota_tab(B, 1024));
     TAB(fcW, iota_tab(1024, 512));
+    // transposed weight planes [N][R]: element (r, n) at n*R + r
+    const int* wT_r[4]; const int* wT_n[4];
+    {
+      const int Rs[4] = {64 * Ci, 512, 576, 1024}, Ns[4] = {32, 64, 64, 512};
+      for (int l = 0; l < 4; ++l) {
+        if (int rc = upload_table(h, iota_tab(Rs[l]), &wT_r[l])) return rc;
+        if (int rc = upload_table(h, iota_tab(Ns[l], Rs[l]), &wT_n[l])) return rc;
+      }
+    }
     // dZ row tables in the zero-bordered layouts
     std::vector<int> z2row(B * H2 * W2), z3row(B * H3 * W3);
     for (int b = 0; b < B; ++b) {
@@ -335,6 +382,15 @@ int build_groups(b2g_sac* h) {
         GemmDesc d = mk(in, rowoff[l], koff[l], h->p(nn(n, cname[l]) + "/w"), wrow[l], i64, out, crow[l], i64,
                         B * c.Ho * c.Wo, c.Co, c.k * c.k * c.Ci, GG_A_RVEC | GG_EPI_BIAS_RELU);
         d.bias = h->p(nn(n, cname[l]) + "/b");
+        if (h->use_planes) {
+          uint16_t* const* ip = l == 0 ? h->xp[n == 2 ? 1 : 0] : (l == 1 ? h->h1p[n] : h->h2p[n]);
+          uint16_t* const* op = l == 0 ? h->h1p[n] : (l == 1 ? h->h2p[n] : h->h3p[n]);
+          d.flags |= GG_PLANES | GG_B_RVEC | ((l == 0 && (c.Ci & 1)) ? GG_A_ALIGN4 : 0);
+          d.A_hi = ip[0]; d.A_lo = ip[1];
+          d.B_hi = h->wp[n][l][2]; d.B_lo = h->wp[n][l][3];
+          d.bR_p = wT_r[l]; d.bN_p = wT_n[l];
+          d.C_hi = op[0]; d.C_lo = op[1];
+        }
         g.host.push_back(d);
       }
       h->fwd_groups.push_back(g);
@@ -346,6 +402,12 @@ int build_groups(b2g_sac* h) {
         GemmDesc d = mk(h->h3[n], fcA, i1024, h->p(nn(n, "/cnn_fc1/w")), fcW, i512, h->F[n], rowFS, i512, B, 512, 1024,
                         GG_A_RVEC | GG_EPI_BIAS_RELU);
         d.bias = h->p(nn(n, "/cnn_fc1/b"));
+        if (h->use_planes) {
+          d.flags |= GG_PLANES | GG_B_RVEC;
+          d.A_hi = h->h3p[n][0]; d.A_lo = h->h3p[n][1];
+          d.B_hi = h->wp[n][3][2]; d.B_lo = h->wp[n][3][3];
+          d.bR_p = wT_r[3]; d.bN_p = wT_n[3];
+        }
         g.host.push_back(d);
       }
       h->fwd_groups.push_back(g);
@@ -369,6 +431,7 @@ int build_groups(b2g_sac* h) {
       GemmDesc d = mk(h->dz0_pi, rowH, i64, h->p("model/pi/fc0/kernel"), i64, kH, h->dZ4[0], row512, i512, B, 512, H,
                       GG_A_RVEC | GG_B_RVEC | GG_EPI_MASK);
       d.mask = h->F[0]; d.kM = rowFS; d.kN = i512;
+      if (h->use_planes) { d.C_hi = h->dZ4p[0][0]; d.C_lo = h->dZ4p[0][1]; }
       g.host.push_back(d);
       // values: [dz0_vf | dz0_q1 | dz0_q2] x [K0_vf ; K0_q1 ; K0_q2]^T
       std::vector<int> br(3 * H);
@@ -380,6 +443,7 @@ int build_groups(b2g_sac* h) {
       GemmDesc e = mk(h->dz0_v3, row3H, i3H, h->P, brv, kH, h->dZ4[1], row512, i512, B, 512, 3 * H,
                       GG_A_RVEC | GG_B_RVEC | GG_EPI_MASK);
       e.mask = h->F[1]; e.kM = rowFS; e.kN = i512;
+      if (h->use_planes) { e.C_hi = h->dZ4p[1][0]; e.C_lo = h->dZ4p[1][1]; }
       g.host.push_back(e);
       h->bwd_groups.push_back(g);
       // fc1 wgrad + dgrad
@@ -400,6 +464,12 @@ int build_groups(b2g_sac* h) {
         GemmDesc dg = mk(h->dZ4[n], row512, i512, h->p(nn(n, "/cnn_fc1/w")), i512, wfT, h->dZ3p[n], rowP3, cN3p, B, 1024, 512,
                          GG_A_RVEC | GG_B_RVEC | GG_EPI_MASK);
         dg.mask = h->h3[n]; dg.kM = fcA; dg.kN = i1024;
+        if (h->use_planes) {
+          dg.flags |= GG_PLANES;
+          dg.A_hi = h->dZ4p[n][0]; dg.A_lo = h->dZ4p[n][1];
+          dg.B_hi = h->wp[n][3][0]; dg.B_lo = h->wp[n][3][1];
+          dg.C_hi = h->dZ3pp[n][0]; dg.C_lo = h->dZ3pp[n][1];
+        }
         f.host.push_back(dg);
       }
       h->bwd_groups.push_back(f);
@@ -432,6 +502,12 @@ int build_groups(b2g_sac* h) {
         GemmDesc dg = mk(h->dZ3p[n], t_am, t_ar, h->p(nn(n, "/cnn3/w")), t_br, c64, h->dZ2p[n], t_cm, i64, B * H2 * W2, 64, 576,
                          GG_A_RVEC | GG_B_RVEC | GG_EPI_MASK);
         dg.mask = h->h2[n]; dg.kM = crow[1]; dg.kN = i64;
+        if (h->use_planes) {
+          dg.flags |= GG_PLANES;
+          dg.A_hi = h->dZ3pp[n][0]; dg.A_lo = h->dZ3pp[n][1];
+          dg.B_hi = h->wp[n][2][0]; dg.B_lo = h->wp[n][2][1];
+          dg.C_hi = h->dZ2pp[n][0]; dg.C_lo = h->dZ2pp[n][1];
+        }
         g.host.push_back(dg);
       }
       h->bwd_groups.push_back(g);
@@ -469,6 +545,11 @@ int build_groups(b2g_sac* h) {
             GemmDesc dg = mk(h->dZ2p[n], t_am, t_ar, h->p(nn(n, "/cnn2/w")), t_br, c64, h->dZ1[n], t_cm, i64, B * ny * nx, 32, 256,
                              GG_A_RVEC | GG_B_RVEC | GG_EPI_MASK);
             dg.mask = h->h1[n];
+            if (h->use_planes) {
+              dg.flags |= GG_PLANES;
+              dg.A_hi = h->dZ2pp[n][0]; dg.A_lo = h->dZ2pp[n][1];
+              dg.B_hi = h->wp[n][1][0]; dg.B_lo = h->wp[n][1][1];
+            }
             g.host.push_back(dg);
           }
         }
@@ -529,6 +610,26 @@ int build_groups(b2g_sac* h) {
     // heads_wgrad must run before heads_dgrad? no dependency; keep it first in the backward list
     h->bwd_groups.insert(h->bwd_groups.begin(), g);
   }
+  if (h->use_planes) {
+    const char* lname[4] = {"/cnn1/w", "/cnn2/w", "/cnn3/w", "/cnn_fc1/w"};
+    const int Rs[4] = {64 * h->Cimg, 512, 576, 1024}, Ns[4] = {32, 64, 64, 512};
+    std::vector<PlaneJob> jobs;
+    int start = 0;
+    for (int n = 0; n < 3; ++n)
+      for (int l = 0; l < 4; ++l) {
+        PlaneJob j{};
+        j.src = h->p(std::string(nets[n]) + lname[l]);
+        j.hi = h->wp[n][l][0]; j.lo = h->wp[n][l][1]; j.hiT = h->wp[n][l][2]; j.loT = h->wp[n][l][3];
+        j.R = Rs[l]; j.N = Ns[l]; j.tile_start = start;
+        start += ((j.R + 31) / 32) * ((j.N + 31) / 32);
+        jobs.push_back(j);
+      }
+    h->n_jobs = (int)jobs.size();
+    h->job_tiles = start;
+    if (int rc = dalloc(h, &h->d_jobs, jobs.size(), false)) return rc;
+    CK(cudaMemcpyAsync(h->d_jobs, jobs.data(), jobs.size() * sizeof(PlaneJob), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
   // one operand-contiguity mode per launch (the tcgen05 kernel is specialised on it): split mixed groups
   {
     std::vector<GemmGroup> split;
@@ -548,6 +649,10 @@ int build_groups(b2g_sac* h) {
   const char* sel = getenv("B2G_TC_GROUPS");   // debugging: comma-separated group names, "all" or "none"
   auto pick = [&](GemmGroup& g) {
     g.tc_eligible = g.name.find("conv") != std::string::npos || g.name.find("fc1_") != std::string::npos;
+    {   // head fc0 contractions (fwd / wgrad / dgrad) also run on the tensor engine unless B2G_TC_HEADS=0
+      const char* hd = getenv("B2G_TC_HEADS");
+      if (!(hd && hd[0] == '0') && g.name.find("heads_") != std::string::npos) g.tc_eligible = true;
+    }
     g.tc = g.tc_eligible && h->cfg.precision != B2G_PREC_FP32_SIMT;
     if (sel && g.tc_eligible && h->cfg.precision != B2G_PREC_FP32_SIMT) {
       const std::string s(sel);
@@ -621,6 +726,7 @@ GatherArgs make_gather(b2g_sac* h, bool from_replay, bool with_next) {
   g.H = h->cnn ? h->Hi : 0; g.W = h->cnn ? h->Wi : h->cfg.obs_dim; g.Cfull = h->cnn ? h->Cimg + 1 : 1;
   g.scale = h->cnn ? 255.f : 1.f;
   g.x_obs = h->x_obs; g.x_next = h->x_next;
+  g.x_obs_hi = h->xp[0][0]; g.x_obs_lo = h->xp[0][1]; g.x_next_hi = h->xp[1][0]; g.x_next_lo = h->xp[1][1];
   g.F_pi = h->F[0]; g.F_v = h->F[1]; g.F_t = h->F[2]; g.FS = h->FS; g.feat_col = 512;
   g.rew_out = h->rew_n; g.done_out = h->done_n; g.n_act = h->A;
   return g;
@@ -656,9 +762,26 @@ int issue_step(b2g_sac* h, bool sampled, bool apply, bool want_per_sample, Prof*
   int x3 = h->cfg.precision == B2G_PREC_BF16X3 ? 1 : 0;
   if (const char* dbg = getenv("B2G_TC_DEBUG")) x3 |= atoi(dbg) << 8;   // kernel bring-up toggles (gg_tc.cu)
   auto run_group = [&](GemmGroup& g) -> int {
+    const char* trn = getenv("B2G_TC_TRACE");
+    const bool trace = prof && prof->on && trn && g.name == trn && g.tc;
+    if (trace) {
+      CK(cudaMemsetAsync(h->dbg_trace, 0, 64 * 8 * sizeof(long long), s));
+      g_tc_trace = h->dbg_trace;
+    }
+    struct Reset { ~Reset() { g_tc_trace = nullptr; } } reset_;
     if (g.tc) CK(gg_tc_launch(g.host.data(), (int)g.host.size(), g.total_tiles, g.host[0].flags, x3, h->num_sms, s));
     else gg_simt_launch(g.dev, (int)g.host.size(), g.total_tiles, s);
     ++n; mark(g.name.c_str());
+    if (trace) {
+      std::vector<long long> t(64 * 8);
+      CK(cudaStreamSynchronize(s));
+      CK(cudaMemcpy(t.data(), h->dbg_trace, t.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+      const long long t0 = t[0];
+      fprintf(stderr, "trace %s (cycles since first stamp; per tile: prod_start prod_issued | mma_full mma_commit | epi_accfull epi_ld epi_stored)\n", g.name.c_str());
+      for (int i = 0; i < 12 && t[i * 8]; ++i)
+        fprintf(stderr, "  tile %2d: %7lld %7lld | %7lld %7lld | %7lld %7lld %7lld\n", i, t[i * 8] - t0, t[i * 8 + 1] - t0, t[i * 8 + 2] - t0,
+                t[i * 8 + 3] - t0, t[i * 8 + 4] - t0, t[i * 8 + 5] - t0, t[i * 8 + 6] - t0);
+    }
     return 0;
   };
   for (auto& g : h->fwd_groups) if (int rc = run_group(g)) return rc;
@@ -679,9 +802,19 @@ int issue_step(b2g_sac* h, bool sampled, bool apply, bool want_per_sample, Prof*
   oa.step_consts = h->step_consts; oa.tau = h->cfg.tau; oa.grad_scale = 1.0f / (float)h->cfg.nranks;
   oa.metrics = h->metrics; oa.apply = apply ? 1 : 0;
   optim_launch(oa, s); ++n; mark("adam_polyak");
+  if (h->use_planes && apply) { planes_launch(h->d_jobs, h->n_jobs, h->job_tiles, s); ++n; mark("weight_planes"); }
   CK(cudaGetLastError());
   if (n_launch) *n_launch = n;
   return 0;
+}
+
+// BF16 planes of the CNN weights follow every optimiser step inside the step itself; after a host upload
+// (b2g_set_param) they are refreshed here, outside any graph.
+void refresh_planes(b2g_sac* h) {
+  if (h->use_planes && h->planes_dirty) {
+    planes_launch(h->d_jobs, h->n_jobs, h->job_tiles, h->stream);
+    h->planes_dirty = false;
+  }
 }
 
 int set_lr(b2g_sac* h, float lr) {
@@ -805,7 +938,7 @@ int b2g_sac_create(const b2g_sac_cfg* cfg, b2g_sac** out) {
   const int B = h->B;
 #define DA(ptr, count) if ((rc = dalloc(h, &(ptr), (size_t)(count)))) return bail(rc)
   DA(h->P, h->n_all); DA(h->Mo, h->n_train); DA(h->Vo, h->n_train); DA(h->G, h->n_train + MET_COUNT);
-  DA(h->metrics, MET_COUNT); DA(h->counters, 8); DA(h->step_consts, 4); DA(h->d_lr, 1);
+  DA(h->dbg_trace, 64 * 8); DA(h->metrics, MET_COUNT); DA(h->counters, 8); DA(h->step_consts, 4); DA(h->d_lr, 1);
   const int64_t cap = cfg->buffer_capacity;
   DA(h->r_obs, cap * h->E); DA(h->r_next, cap * h->E); DA(h->r_act, cap * h->A); DA(h->r_rew, cap); DA(h->r_done, cap);
   DA(h->d_mean, h->E); DA(h->d_istd, h->E); DA(h->d_normc, 8);
@@ -819,6 +952,28 @@ int b2g_sac_create(const b2g_sac_cfg* cfg, b2g_sac** out) {
       DA(h->dZ4[n], (size_t)B * 512); DA(h->dZ3p[n], (size_t)B * (h->H3 + 4) * (h->W3 + 4) * 64);
       DA(h->dZ2p[n], (size_t)B * (h->H2 + 3) * (h->W2 + 3) * 64); DA(h->dZ1[n], (size_t)B * h->H1 * h->W1 * 32);
     }
+  }
+  h->use_planes = h->cnn && cfg->precision != B2G_PREC_FP32_SIMT;
+  if (const char* pl = getenv("B2G_TC_PLANES")) if (pl[0] == '0') h->use_planes = false;
+  if (h->use_planes) {
+    const size_t nx = (size_t)B * h->Hi * h->Wi * h->Cimg;
+    for (int k = 0; k < 2; ++k) { DA(h->xp[0][k], nx); DA(h->xp[1][k], nx); }
+    for (int n = 0; n < 3; ++n)
+      for (int k = 0; k < 2; ++k) {
+        DA(h->h1p[n][k], (size_t)B * h->H1 * h->W1 * 32); DA(h->h2p[n][k], (size_t)B * h->H2 * h->W2 * 64); DA(h->h3p[n][k], (size_t)B * 1024);
+      }
+    for (int n = 0; n < 2; ++n)
+      for (int k = 0; k < 2; ++k) {
+        DA(h->dZ4p[n][k], (size_t)B * 512); DA(h->dZ3pp[n][k], (size_t)B * (h->H3 + 4) * (h->W3 + 4) * 64);
+        DA(h->dZ2pp[n][k], (size_t)B * (h->H2 + 3) * (h->W2 + 3) * 64);
+      }
+    const size_t wsz[4] = {(size_t)64 * h->Cimg * 32, 512 * 64, 576 * 64, 1024 * 512};
+    for (int n = 0; n < 3; ++n)
+      for (int l = 0; l < 4; ++l)
+        for (int k = 0; k < 4; ++k) {
+          if (n == 2 && k < 2) continue;      // the target network only runs forward: transposed planes suffice
+          DA(h->wp[n][l][k], wsz[l]);
+        }
   }
   for (int n = 0; n < 3; ++n) DA(h->F[n], (size_t)B * h->FS);
   for (int q = 0; q < 5; ++q) DA(h->z0[q], B * h->H);
@@ -891,7 +1046,9 @@ static int copy_tensor(b2g_sac* h, const char* name, float* arena, float* host, 
 
 int b2g_get_param(b2g_sac* h, const char* name, float* dst, size_t numel) { return copy_tensor(h, name, h ? h->P : nullptr, dst, numel, true, false); }
 int b2g_set_param(b2g_sac* h, const char* name, const float* src, size_t numel) {
-  return copy_tensor(h, name, h ? h->P : nullptr, const_cast<float*>(src), numel, false, false);
+  int rc = copy_tensor(h, name, h ? h->P : nullptr, const_cast<float*>(src), numel, false, false);
+  if (rc == 0) h->planes_dirty = true;
+  return rc;
 }
 int b2g_get_grad(b2g_sac* h, const char* name, float* dst, size_t numel) {
   int rc = copy_tensor(h, name, h ? h->G : nullptr, dst, numel, true, true);
@@ -978,6 +1135,7 @@ int b2g_sac_step_async(b2g_sac* h, int n_steps, float lr) {
   if (h->r_size < 1) return fail(B2G_ESTATE, "replay buffer is empty");
   CK(cudaSetDevice(h->cfg.device));
   if (int rc = set_lr(h, lr)) return rc;
+  refresh_planes(h);
   if (h->use_graph) if (int rc = ensure_graph(h)) return rc;
   CK(cudaEventRecord(h->ev0, h->stream));
   for (int i = 0; i < n_steps; ++i) {
@@ -1001,6 +1159,7 @@ int b2g_sac_step_explicit(b2g_sac* h, const float* obs, const float* act, const 
   CK(cudaSetDevice(h->cfg.device));
   if (int rc = set_lr(h, lr)) return rc;
   const size_t B = h->B, E = h->E, A = h->A;
+  refresh_planes(h);
   CK(cudaEventRecord(h->ev0, h->stream));
   CK(cudaMemcpyAsync(h->s_obs, obs, B * E * sizeof(float), cudaMemcpyDefault, h->stream));
   CK(cudaMemcpyAsync(h->s_next, next_obs, B * E * sizeof(float), cudaMemcpyDefault, h->stream));
@@ -1022,6 +1181,7 @@ int b2g_sac_act(b2g_sac* h, const float* obs, int n, int deterministic, float* a
   if (!h || !obs || !act_out || n < 0) return fail(B2G_EINVAL, "bad argument");
   CK(cudaSetDevice(h->cfg.device));
   const size_t E = h->E, A = h->A;
+  refresh_planes(h);
   for (int done_n = 0; done_n < n; done_n += h->B) {
     const int chunk = std::min(h->B, n - done_n);
     CK(cudaMemcpyAsync(h->s_obs, obs + (size_t)done_n * E, chunk * E * sizeof(float), cudaMemcpyDefault, h->stream));
@@ -1059,6 +1219,7 @@ int b2g_profile_step(b2g_sac* h, float lr, const char** names, float* ms, int ca
   if (h->r_size < 1) return fail(B2G_ESTATE, "replay buffer is empty");
   CK(cudaSetDevice(h->cfg.device));
   if (int rc = set_lr(h, lr)) return rc;
+  refresh_planes(h);
   Prof prof;
   prof.on = true;
   int n = 0;

@@ -81,6 +81,8 @@ __global__ void __launch_bounds__(WARPS * 32) tail_kernel(TailArgs t) {
   float* red = acc + n_acc;                       // MET_COUNT + 1 (g_log_alpha)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
+  pdl_trigger();
+  pdl_wait();
   const float* k1s[S_NW] = {t.pi.k1, t.vf.k1, t.q1.k1, t.q2.k1, t.vt.k1};
   for (int w = 0; w < S_NW; ++w)
     for (int i = tid; i < H * H; i += blockDim.x) Wk1[w * H * LD + (i >> 6) * LD + (i & 63)] = k1s[w][i];
@@ -309,7 +311,7 @@ void tail_launch(const TailArgs& a, cudaStream_t s) {
     attr_set = true;
   }
   const int grid = (a.B + WARPS - 1) / WARPS;
-  tail_kernel<<<grid, WARPS * 32, smem, s>>>(a);
+  launch_pdl(tail_kernel, dim3(grid), dim3(WARPS * 32), smem, s, pdl_enabled(), a);
 }
 
 }  // namespace b2g
