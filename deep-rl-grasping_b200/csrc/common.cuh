@@ -45,6 +45,7 @@ enum GemmFlags : int {
   GG_COLSUM = 1 << 5,     // colsum[n] += sum_r B(r, n)   (bias gradients; tile_m == 0 only)
   GG_PLANES = 1 << 6,     // operands come pre-split as BF16 hi/lo planes (A_hi.., B_hi..), copied by cp.async
   GG_A_ALIGN4 = 1 << 7,   // plane A rows are only 8-byte aligned (conv1 with one image channel)
+  GG_MN_MAJOR = 1 << 9,   // planes mode, wgrad: both operands contiguous along their M / N index -> MN-major UMMA tiles
   GG_CN_AFFINE4 = 1 << 8, // host-verified: cN / kN contiguous inside aligned 4-column groups, outputs 16-byte aligned
 };
 
@@ -164,6 +165,9 @@ struct PlaneJob {
   int tile_start;              // first 32x32 tile of this job in the flattened launch
 };
 void planes_launch(const PlaneJob* dev_jobs, int njobs, int total_tiles, cudaStream_t s);
+// bias gradients: dst[n] += sum over rows of src[row_off[m] + n]  (optim.cu)
+struct ColsumJob { const float* src; const int* row_off; float* dst; int rows, N; int cta_start; };
+void colsum_launch(const ColsumJob* dev_jobs, int njobs, int total_ctas, cudaStream_t s);
 
 struct PrepArgs {          // 1-CTA kernel at the head of every step
   long long* counters;     // [0..2] Adam t per optimiser, [3] n_updates, [4] rng step counter

@@ -26,14 +26,20 @@ namespace {
 
 constexpr int TM = GG_TC_BM, TN = GG_TC_BN, TK = GG_TC_BK;   // tile: 128 x 64 x 64
 constexpr int STAGES = 4;
-constexpr int NPROD = 512;                              // producer threads (16 warps)
-constexpr int MMA_WARP = NPROD / 32;                    // warp 16
-constexpr int NEPI = 128;                               // epilogue threads (warps 17..20)
-constexpr int NTHREADS = NPROD + 32 + NEPI;             // 672
+// warp roles.  register-staged operands (fp32 sources): 16 producer warps, MMA warp, 4 epilogue warps (672 threads);
+// BF16-plane operands (cp.async): 8 producer warps, MMA warp, 8 epilogue warps (544 threads).
+template <bool planes> struct Roles {
+  static constexpr int NPROD = planes ? 256 : 512;
+  static constexpr int MMA_WARP = NPROD / 32;
+  static constexpr int NEPI = planes ? 256 : 128;
+  static constexpr int NTHREADS = NPROD + 32 + NEPI;
+  static constexpr int EPI_COLS = planes ? 32 : 64;      // accumulator columns handled by one epilogue warp
+};
 constexpr int A_BYTES = TM * TK * 2;                    // 16 KiB per (hi | lo)
 constexpr int B_BYTES = TN * TK * 2;                    // 8 KiB
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;  // 48 KiB
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
+constexpr int STG_BYTES = TM * TN * 4;                   // fp32 output staging tile (32 KiB): coalesced epilogue stores
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + 1024;
 constexpr int TMEM_COLS = 2 * TN;
 
 struct DescPack {
@@ -73,10 +79,16 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
+// MN-major, SWIZZLE_128B descriptor: atoms of 64 (M|N) x 8 (K) elements = 8 rows of 128 B; LBO = byte stride
+// between 64-element atoms along M|N, SBO = byte stride between 8-element atoms along K.
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) |
+         (2ull << 61);
+}
 // kind::f16 instruction descriptor: D=f32 (bits 4-5 = 1), A=B=BF16 (bits 7-9, 10-12 = 1), K-major A/B,
 // N>>3 at bit 17, M>>4 at bit 24.
-__device__ __forceinline__ uint32_t umma_idesc(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+__device__ __forceinline__ uint32_t umma_idesc(int m, int n, bool mn_major = false) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (mn_major ? (3u << 15) : 0u) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -152,8 +164,10 @@ __device__ __forceinline__ TileInfo tile_info(const DescPack& pk, int tile) {
 }
 
 template <bool a_rvec, bool b_rvec, bool planes>
-__global__ void __launch_bounds__(NTHREADS, 1) gg_tc_kernel(const __grid_constant__ DescPack pk, int x3_in) {
+__global__ void __launch_bounds__(Roles<planes>::NTHREADS, 1) gg_tc_kernel(const __grid_constant__ DescPack pk, int x3_in) {
   int x3 = x3_in;
+  constexpr int NPROD = Roles<planes>::NPROD, MMA_WARP = Roles<planes>::MMA_WARP, NEPI = Roles<planes>::NEPI;
+  constexpr int EPI_COLS = Roles<planes>::EPI_COLS;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[STAGES], bar_empty[STAGES], bar_acc_full[2], bar_acc_empty[2];
   __shared__ uint32_t tmem_slot;
@@ -191,26 +205,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) gg_tc_kernel(const __grid_constan
     // Operands are already split into BF16 hi/lo planes in HBM: every 16-byte chunk of a UMMA tile is one
     // cp.async straight into its swizzled slot -- no registers, no conversion; the ring depth is the prefetch
     // depth, and the slot's mbarrier is signalled by the copies themselves (cp.async.mbarrier.arrive.noinc).
-    const int c8 = tid & 7, q = tid >> 3;      // chunk, row (A rows q and q + 64; B row q)
+    const int c8 = tid & 7, q = tid >> 3;      // 16-byte chunk, row group: A rows q + 32 i (i < 4), B rows q + 32 i (i < 2)
     uint32_t gc = 0;
     // per-tile gather state, fetched ONE TILE AHEAD so that the row-offset / table round trips of tile i+1
     // overlap the copies of tile i (the ring keeps running across tile boundaries)
-    struct TState { TileInfo ti; int a_off[2]; bool a_ok[2]; int b_off; bool b_ok; int ta, tb; bool valid; };
+    struct TState { TileInfo ti; int a_off[4]; bool a_ok[4]; int b_off[2]; bool b_ok[2]; int ta, tb; bool valid; };
     auto fetch = [&](int tile) {
       TState t;
       t.valid = tile < pk.total_tiles;
       if (!t.valid) return t;
       t.ti = tile_info(pk, tile);
       const GemmDesc& d = pk.d[t.ti.p];
+      if (d.flags & GG_MN_MAJOR) return t;       // MN-major tiles fetch their (few) offsets in place
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int m = t.ti.m0 + q + 64 * i;
+      for (int i = 0; i < 4; ++i) {
+        const int m = t.ti.m0 + q + 32 * i;
         t.a_ok[i] = m < d.M;
         t.a_off[i] = t.a_ok[i] ? d.aM[m] : 0;
       }
-      const int nB = t.ti.n0 + q;
-      t.b_ok = nB < d.N;
-      t.b_off = t.b_ok ? (d.bN_p ? d.bN_p : d.bN)[nB] : 0;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int nB = t.ti.n0 + q + 32 * i;
+        t.b_ok[i] = nB < d.N;
+        t.b_off[i] = t.b_ok[i] ? (d.bN_p ? d.bN_p : d.bN)[nB] : 0;
+      }
       t.ta = t.tb = 0;
       if (t.ti.nchunks > 0) {
         t.ta = d.aR[t.ti.r_begin + c8 * 8];
@@ -224,7 +242,56 @@ __global__ void __launch_bounds__(NTHREADS, 1) gg_tc_kernel(const __grid_constan
       if (pk.trace && blockIdx.x == 0 && tid == 0 && tcount < 64) pk.trace[tcount * 8 + 0] = clock64();
       const TState nxt = fetch(tile + gridDim.x);
       const TileInfo ti = cur.ti;
-      if (ti.nchunks > 0) {
+      if (ti.nchunks > 0 && (pk.d[ti.p].flags & GG_MN_MAJOR)) {
+        // ---- wgrad: D[k, n] = sum_m act[m -> k] * dZ[m, n]; both operands are contiguous along their M / N
+        // index for a fixed reduction index m, so tiles are MN-major: row (r = m) x 16-byte groups along k / n.
+        const GemmDesc& d = pk.d[ti.p];
+        const bool align4 = d.flags & GG_A_ALIGN4;
+        const int c = tid & 7;                         // 16-byte group; reduction rows (tid >> 3) and (tid >> 3) + 32
+        // column-side offsets of this thread's groups (A: k groups c and c + 8; B: n group c) are tile constants
+        const int kg0 = ti.m0 + 8 * c, kg1 = ti.m0 + 8 * (c + 8), ng = ti.n0 + 8 * c;
+        const bool k0_ok = kg0 < d.M, k1_ok = kg1 < d.M, n_ok = ng < d.N;
+        const int ka0 = k0_ok ? d.aM[kg0] : 0, ka1 = k1_ok ? d.aM[kg1] : 0, nb_ = n_ok ? d.bN[ng] : 0;
+        for (int ch = 0; ch < ti.nchunks; ++ch, ++gc) {
+          const int s = gc % STAGES;
+          const uint32_t sA_hi = ring + s * STAGE_BYTES, sA_lo = sA_hi + A_BYTES;
+          const uint32_t sB_hi = sA_lo + A_BYTES, sB_lo = sB_hi + B_BYTES;
+          int ar[2], br[2];
+          bool r_ok[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int r = ti.r_begin + ch * TK + q + 32 * u;
+            r_ok[u] = r < ti.r_end;
+            ar[u] = r_ok[u] ? d.aR[r] : 0;
+            br[u] = r_ok[u] ? d.bR[r] : 0;
+          }
+          if (gc >= STAGES) mbar_wait(smem_u32(&bar_empty[s]), ((gc / STAGES) - 1) & 1);
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int rr = q + 32 * u;
+            const int ki = rr >> 3, kk = rr & 7;
+            const uint32_t swz = (uint32_t)((c ^ kk) << 4);
+            const uint32_t oA0 = (uint32_t)(ki * 2048 + kk * 128) + swz, oA1 = oA0 + 1024, oB = (uint32_t)(ki * 1024 + kk * 128) + swz;
+            const int nb0 = (r_ok[u] && k0_ok) ? 16 : 0, nb1 = (r_ok[u] && k1_ok) ? 16 : 0, nbb = (r_ok[u] && n_ok) ? 16 : 0;
+            const size_t e0 = (size_t)(ar[u] + ka0), e1 = (size_t)(ar[u] + ka1), eb = (size_t)(br[u] + nb_);
+            if (!align4) {
+              cp_async16(sA_hi + oA0, d.A_hi + e0, nb0);
+              cp_async16(sA_hi + oA1, d.A_hi + e1, nb1);
+              if (x3) { cp_async16(sA_lo + oA0, d.A_lo + e0, nb0); cp_async16(sA_lo + oA1, d.A_lo + e1, nb1); }
+            } else {
+              cp_async8(sA_hi + oA0, d.A_hi + e0, nb0 / 2); cp_async8(sA_hi + oA0 + 8, d.A_hi + e0 + 4, nb0 / 2);
+              cp_async8(sA_hi + oA1, d.A_hi + e1, nb1 / 2); cp_async8(sA_hi + oA1 + 8, d.A_hi + e1 + 4, nb1 / 2);
+              if (x3) {
+                cp_async8(sA_lo + oA0, d.A_lo + e0, nb0 / 2); cp_async8(sA_lo + oA0 + 8, d.A_lo + e0 + 4, nb0 / 2);
+                cp_async8(sA_lo + oA1, d.A_lo + e1, nb1 / 2); cp_async8(sA_lo + oA1 + 8, d.A_lo + e1 + 4, nb1 / 2);
+              }
+            }
+            cp_async16(sB_hi + oB, d.B_hi + eb, nbb);
+            if (x3) cp_async16(sB_lo + oB, d.B_lo + eb, nbb);
+          }
+          cp_async_arrive_noinc(smem_u32(&bar_full[s]));
+        }
+      } else if (ti.nchunks > 0) {
         const GemmDesc& d = pk.d[ti.p];
         const bool align4 = d.flags & GG_A_ALIGN4;
         const int* __restrict__ tabA = d.aR;
@@ -238,8 +305,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gg_tc_kernel(const __grid_constan
           const int nbytes = max(0, min(8, ti.r_end - r0)) * 2;
           if (gc >= STAGES) mbar_wait(smem_u32(&bar_empty[s]), ((gc / STAGES) - 1) & 1);
 #pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            const uint32_t o = sw128(q + 64 * i, c8);
+          for (int i = 0; i < 4; ++i) {
+            const uint32_t o = sw128(q + 32 * i, c8);
             const int nb = cur.a_ok[i] ? nbytes : 0;
             const size_t e = (size_t)(cur.a_off[i] + ta);
             if (!align4) {
@@ -254,10 +321,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) gg_tc_kernel(const __grid_constan
               }
             }
           }
-          {
-            const uint32_t o = sw128(q, c8);
-            const int nb = cur.b_ok ? nbytes : 0;
-            const size_t e = (size_t)(cur.b_off + tb);
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const uint32_t o = sw128(q + 32 * i, c8);
+            const int nb = cur.b_ok[i] ? nbytes : 0;
+            const size_t e = (size_t)(cur.b_off[i] + tb);
             cp_async16(sB_hi + o, d.B_hi + e, nb);
             if (x3) cp_async16(sB_lo + o, d.B_lo + e, nb);
           }
@@ -460,7 +528,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gg_tc_kernel(const __grid_constan
         const uint32_t buf = it & 1;
         if (it >= 2) mbar_wait(smem_u32(&bar_acc_empty[buf]), ((it >> 1) - 1) & 1);
         tc_fence_after();
-        const uint32_t idesc = umma_idesc(TM, ti.un);
+        const bool mnm = planes && (pk.d[ti.p].flags & GG_MN_MAJOR);
+        const uint32_t idesc = umma_idesc(TM, ti.un, mnm);
         const uint32_t acc = tmem + buf * TN;
         for (int ch = 0; ch < ti.nchunks; ++ch, ++gc) {
           const int s = gc % STAGES;
@@ -473,10 +542,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) gg_tc_kernel(const __grid_constan
 #pragma unroll
           for (int k = 0; k < TK / 16; ++k) {
             if (dbg_nomma) break;
-            const uint64_t ah = umma_desc(sA_hi + k * 32), bh = umma_desc(sB_hi + k * 32);
+            // K-major: 16 k = 32 bytes inside the 128-byte row.  MN-major: 16 k = two 8-row K-atoms.
+            const uint64_t ah = mnm ? umma_desc_mn(sA_hi + k * 4096, 1024, 2048) : umma_desc(sA_hi + k * 32);
+            const uint64_t bh = mnm ? umma_desc_mn(sB_hi + k * 2048, 1024, 1024) : umma_desc(sB_hi + k * 32);
             umma_bf16(acc, ah, bh, idesc, (ch | k) ? 1u : 0u);
             if (x3) {
-              const uint64_t al = umma_desc(sA_lo + k * 32), bl = umma_desc(sB_lo + k * 32);
+              const uint64_t al = mnm ? umma_desc_mn(sA_lo + k * 4096, 1024, 2048) : umma_desc(sA_lo + k * 32);
+              const uint64_t bl = mnm ? umma_desc_mn(sB_lo + k * 2048, 1024, 1024) : umma_desc(sB_lo + k * 32);
               umma_bf16(acc, ah, bl, idesc, 1u);
               umma_bf16(acc, al, bh, idesc, 1u);
             }
@@ -490,13 +562,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) gg_tc_kernel(const __grid_constan
     }
     __syncwarp();
   } else {
-    // =========================================================================== epilogue (4 warps)
-    // Column-side tables (cN, kN, bias) of the tile are staged in shared memory BEFORE the accumulator is
-    // waited for, so the per-round work after tcgen05.ld is: (mask loads ->) math -> stores, no dependent
-    // table round trips.  Fast path contract (GG_CN_AFFINE4, verified on the host): inside every aligned
-    // group of 4 columns cN / kN are contiguous and the output offset is 16-byte aligned.
+    // =========================================================================== epilogue warps
+    // Each warp owns 32 accumulator rows (its TMEM lane quarter) x EPI_COLS columns.  Column-side tables (cN, kN,
+    // bias) of the tile are staged in shared memory BEFORE the accumulator is waited for.  Phase A: TMEM -> (+bias,
+    // ReLU) -> the warp's private fp32 staging rows; the accumulator is handed back to the MMA warp right after the
+    // last tcgen05.ld.  Phase B: staging rows -> (ReLU mask) -> global, fully coalesced: LPR lanes cover one row's
+    // contiguous run (fp32 float4 + BF16 hi/lo uint2), 32/LPR rows per instruction, loads batched ahead of stores.
+    // Fast-path contract (GG_CN_AFFINE4, verified on the host): inside every aligned group of 4 columns cN / kN are
+    // contiguous and the output offset is 16-byte aligned.
+    const int ew = warp - (MMA_WARP + 1);          // epilogue warp index
     const int lq = warp & 3;                       // TMEM lane quarter this warp may access
-    const int et = tid - (MMA_WARP + 1) * 32;      // 0..127
+    const int col0 = (ew >> 2) * EPI_COLS;         // first accumulator column of this warp
+    const int et = tid - (MMA_WARP + 1) * 32;      // 0..NEPI-1
+    constexpr int LPR = EPI_COLS / 4, RPI = 32 / LPR;
+    const uint32_t stg = ring + STAGES * STAGE_BYTES + (uint32_t)ew * (32 * EPI_COLS * 4);
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < pk.total_tiles; tile += gridDim.x) {
       const TileInfo ti = tile_info(pk, tile);
@@ -519,14 +598,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) gg_tc_kernel(const __grid_constan
         s_bias[et - TN] = ((d.flags & GG_EPI_BIAS_RELU) && n < d.N) ? d.bias[n] : 0.f;
       }
       asm volatile("bar.sync 2, %0;" ::"n"(NEPI));
-      const bool tr = pk.trace && blockIdx.x == 0 && warp == MMA_WARP + 1 && lane == 0 && it < 64;
+      const bool tr = pk.trace && blockIdx.x == 0 && ew == 0 && lane == 0 && it < 64;
       mbar_wait(smem_u32(&bar_acc_full[buf]), (it >> 1) & 1);
       tc_fence_after();
       if (tr) pk.trace[it * 8 + 4] = clock64();
-      const bool fastp = d.flags & GG_CN_AFFINE4;
+      const bool fastp = (d.flags & GG_CN_AFFINE4) && (ti.n0 + ti.un <= d.N);
+      const int ncols_w = max(0, min(EPI_COLS, ti.un - col0));     // warp-uniform, multiple of 16
 #pragma unroll 1
-      for (int cb = 0; cb < TN; cb += 16) {
-        if (cb >= ti.un) break;                     // warp-uniform
+      for (int cb = col0; cb < col0 + ncols_w; cb += 16) {
         uint32_t v[16];
         const uint32_t taddr = tmem + buf * TN + ((uint32_t)(lq * 32) << 16) + (uint32_t)cb;
         asm volatile(
@@ -534,65 +613,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) gg_tc_kernel(const __grid_constan
             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
               "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
             : "r"(taddr));
-        // mask values of this round: independent global loads, in flight while the TMEM load completes
-        const int nb0 = ti.n0 + cb;
-        const bool full16 = nb0 + 16 <= d.N;
-        float4 mk[4];
-        const bool use_mask = (d.flags & GG_EPI_MASK) && m_ok && fastp && full16 && !dbg_nostore;
-        if (use_mask) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) mk[g] = ldg4(d.mask + km + s_kn[cb + 4 * g]);
-        }
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (cb + 16 >= ti.un) {                     // last TMEM read of this tile: hand the accumulator back
-          tc_fence_before();
-          mbar_arrive(smem_u32(&bar_acc_empty[buf]));
-          if (tr) pk.trace[it * 8 + 5] = clock64();
-        }
-        if (!m_ok || dbg_nostore) continue;
-        if (fastp && full16) {
-          float4 o[4];
+        if (dbg_nostore) continue;
+        if (fastp) {
+          // phase A: accumulator row -> (+bias, ReLU) -> this warp's staging rows (16-byte chunks XOR-swizzled by row)
 #pragma unroll
-          for (int g = 0; g < 4; ++g)
-            o[g] = make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2]),
-                               __uint_as_float(v[4 * g + 3]));
-          if (d.flags & GG_EPI_BIAS_RELU) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
+          for (int g = 0; g < 4; ++g) {
+            float4 o = make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2]),
+                                   __uint_as_float(v[4 * g + 3]));
+            if (d.flags & GG_EPI_BIAS_RELU) {
               const float4 bb = *reinterpret_cast<const float4*>(&s_bias[cb + 4 * g]);
-              o[g].x = fmaxf(o[g].x + bb.x, 0.f); o[g].y = fmaxf(o[g].y + bb.y, 0.f);
-              o[g].z = fmaxf(o[g].z + bb.z, 0.f); o[g].w = fmaxf(o[g].w + bb.w, 0.f);
+              o.x = fmaxf(o.x + bb.x, 0.f); o.y = fmaxf(o.y + bb.y, 0.f); o.z = fmaxf(o.z + bb.z, 0.f); o.w = fmaxf(o.w + bb.w, 0.f);
             }
+            const int c = ((cb - col0) >> 2) + g;
+            const uint32_t a = stg + (uint32_t)lane * (EPI_COLS * 4) + (uint32_t)((c ^ (lane & 7)) << 4);
+            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
           }
-          if (use_mask) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              o[g].x = mk[g].x > 0.f ? o[g].x : 0.f; o[g].y = mk[g].y > 0.f ? o[g].y : 0.f;
-              o[g].z = mk[g].z > 0.f ? o[g].z : 0.f; o[g].w = mk[g].w > 0.f ? o[g].w : 0.f;
-            }
-          }
-          if (d.C_hi) {      // BF16 hi/lo plane copy of the stored values (operand of the next contraction)
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const float x[8] = {o[g].x, o[g].y, o[g].z, o[g].w, 0.f, 0.f, 0.f, 0.f};
-              uint4 hi, lo;
-              split8(x, hi, lo);
-              const int c = cm + s_cn[cb + 4 * g];
-              *reinterpret_cast<uint2*>(d.C_hi + c) = make_uint2(hi.x, hi.y);
-              *reinterpret_cast<uint2*>(d.C_lo + c) = make_uint2(lo.x, lo.y);
-            }
-          }
-          if (d.flags & GG_EPI_ATOMIC) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              float* c = d.C + cm + s_cn[cb + 4 * g];
-              atomicAdd(c + 0, o[g].x); atomicAdd(c + 1, o[g].y); atomicAdd(c + 2, o[g].z); atomicAdd(c + 3, o[g].w);
-            }
-          } else {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) *reinterpret_cast<float4*>(d.C + cm + s_cn[cb + 4 * g]) = o[g];
-          }
-        } else {
+        } else if (m_ok) {
+          const int nb0 = ti.n0 + cb;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int n = nb0 + j;
@@ -610,6 +648,58 @@ __global__ void __launch_bounds__(NTHREADS, 1) gg_tc_kernel(const __grid_constan
             }
           }
         }
+      }
+      tc_fence_before();
+      mbar_arrive(smem_u32(&bar_acc_empty[buf]));   // this thread's TMEM reads of the tile are done
+      if (tr) pk.trace[it * 8 + 5] = clock64();
+      if (fastp && !dbg_nostore && ncols_w > 0) {
+        __syncwarp();
+        const int c = lane % LPR, sub = lane / LPR;
+        const bool act = c < (ncols_w >> 2);
+        const int cn = act ? s_cn[col0 + 4 * c] : 0, kn = act ? s_kn[col0 + 4 * c] : 0;
+#pragma unroll 1
+        for (int rr0 = 0; rr0 < 32; rr0 += 4 * RPI) {
+          // batch of 4 row groups: every shared / global LOAD first, then math + stores (the compiler cannot hoist
+          // loads over stores, so the batching is explicit)
+          float4 o[4], mk[4];
+          int cmr[4];
+          bool okr[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int row = rr0 + RPI * u + sub;
+            cmr[u] = __shfl_sync(0xffffffffu, cm, row);
+            const int km_r = __shfl_sync(0xffffffffu, km, row);
+            okr[u] = (__shfl_sync(0xffffffffu, (int)m_ok, row) != 0) && act;
+            o[u] = make_float4(0, 0, 0, 0);
+            mk[u] = make_float4(1, 1, 1, 1);
+            if (okr[u]) {
+              const uint32_t a = stg + (uint32_t)row * (EPI_COLS * 4) + (uint32_t)((c ^ (row & 7)) << 4);
+              asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(o[u].x), "=f"(o[u].y), "=f"(o[u].z), "=f"(o[u].w) : "r"(a));
+              if (d.flags & GG_EPI_MASK) mk[u] = ldg4(d.mask + km_r + kn);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (!okr[u]) continue;
+            float4 v4 = o[u];
+            v4.x = mk[u].x > 0.f ? v4.x : 0.f; v4.y = mk[u].y > 0.f ? v4.y : 0.f;
+            v4.z = mk[u].z > 0.f ? v4.z : 0.f; v4.w = mk[u].w > 0.f ? v4.w : 0.f;
+            if (d.flags & GG_EPI_ATOMIC) {
+              float* cp = d.C + cmr[u] + cn;
+              atomicAdd(cp + 0, v4.x); atomicAdd(cp + 1, v4.y); atomicAdd(cp + 2, v4.z); atomicAdd(cp + 3, v4.w);
+            } else {
+              *reinterpret_cast<float4*>(d.C + cmr[u] + cn) = v4;
+            }
+            if (d.C_hi) {
+              const float x[8] = {v4.x, v4.y, v4.z, v4.w, 0.f, 0.f, 0.f, 0.f};
+              uint4 hi, lo;
+              split8(x, hi, lo);
+              *reinterpret_cast<uint2*>(d.C_hi + cmr[u] + cn) = make_uint2(hi.x, hi.y);
+              *reinterpret_cast<uint2*>(d.C_lo + cmr[u] + cn) = make_uint2(lo.x, lo.y);
+            }
+          }
+        }
+        __syncwarp();      // staging rows are reused by the next tile
       }
       if (tr) pk.trace[it * 8 + 6] = clock64();
       ++it;
@@ -632,7 +722,7 @@ cudaError_t launch_mode(const DescPack& pk, int x3, int num_sms, cudaStream_t s)
     attr_set = true;
   }
   const int grid = pk.total_tiles < num_sms ? pk.total_tiles : num_sms;
-  return launch_pdl(gg_tc_kernel<AR, BR, PL>, dim3(grid), dim3(NTHREADS), SMEM_BYTES, s, pdl_enabled(), pk, x3);
+  return launch_pdl(gg_tc_kernel<AR, BR, PL>, dim3(grid), dim3(Roles<PL>::NTHREADS), SMEM_BYTES, s, pdl_enabled(), pk, x3);
 }
 }  // namespace
 

@@ -158,7 +158,47 @@ __global__ void __launch_bounds__(256) planes_kernel(const PlaneJob* __restrict_
     }
   }
 }
+
+// bias gradients as column sums of the (masked) gradient maps.  Thread = (row group, float4 column group);
+// 8 rows per thread, all table + data loads of a thread issued as one batch; block reduce, then N atomics.
+__global__ void __launch_bounds__(256) colsum_kernel(const ColsumJob* __restrict__ jobs, int njobs) {
+  __shared__ float red[512];
+  int j = 0;
+  while (j + 1 < njobs && (int)blockIdx.x >= jobs[j + 1].cta_start) ++j;
+  const ColsumJob job = jobs[j];
+  const int N = job.N, N4 = N >> 2, tid = threadIdx.x;
+  const int groups = 256 / N4;                 // N <= 1024
+  const int rows_per_cta = 8 * groups;
+  const int r0 = (blockIdx.x - job.cta_start) * rows_per_cta;
+  for (int i = tid; i < N; i += 256) red[i] = 0.f;
+  __syncthreads();
+  const int g = tid / N4, c4 = tid - g * N4;
+  if (g < groups) {
+    int off[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = r0 + g + i * groups;
+      off[i] = r < job.rows ? job.row_off[r] : -1;
+    }
+    float4 s = make_float4(0, 0, 0, 0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (off[i] >= 0) {
+        const float4 v = *reinterpret_cast<const float4*>(job.src + off[i] + 4 * c4);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      }
+    }
+    atomicAdd(&red[4 * c4 + 0], s.x); atomicAdd(&red[4 * c4 + 1], s.y);
+    atomicAdd(&red[4 * c4 + 2], s.z); atomicAdd(&red[4 * c4 + 3], s.w);
+  }
+  __syncthreads();
+  for (int i = tid; i < N; i += 256) atomicAdd(job.dst + i, red[i]);
+}
 }  // namespace
+
+void colsum_launch(const ColsumJob* dev_jobs, int njobs, int total_ctas, cudaStream_t s) {
+  if (total_ctas > 0) colsum_kernel<<<total_ctas, 256, 0, s>>>(dev_jobs, njobs);
+}
 
 void planes_launch(const PlaneJob* dev_jobs, int njobs, int total_tiles, cudaStream_t s) {
   if (total_tiles > 0) planes_kernel<<<total_tiles, 256, 0, s>>>(dev_jobs, njobs);

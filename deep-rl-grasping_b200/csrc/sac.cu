@@ -119,7 +119,10 @@ struct b2g_sac {
   // BF16 hi/lo planes ([..][0] = hi, [..][1] = lo) of the tensors that feed forward / dgrad contractions
   bool use_planes = false;
   uint16_t *xp[2][2]{}, *h1p[3][2]{}, *h2p[3][2]{}, *h3p[3][2]{};
-  uint16_t *dZ4p[2][2]{}, *dZ3pp[2][2]{}, *dZ2pp[2][2]{};
+  uint16_t *dZ4p[2][2]{}, *dZ3pp[2][2]{}, *dZ2pp[2][2]{}, *dZ1p[2][2]{};
+  bool wgrad_planes = false;
+  ColsumJob* d_colsum = nullptr;
+  int n_colsum = 0, colsum_ctas = 0;
   uint16_t* wp[3][4][4]{};          // [net][cnn1,cnn2,cnn3,fc1][hi, lo, hiT, loT]
   PlaneJob* d_jobs = nullptr;
   int n_jobs = 0, job_tiles = 0;
@@ -460,6 +463,10 @@ int build_groups(b2g_sac* h) {
         GemmDesc w = mk(h->h3[n], i1024, fcA, h->dZ4[n], row512, i512, h->g(nn(n, "/cnn_fc1/w")), fcW, i512, 1024, 512, B,
                         GG_COLSUM);
         w.colsum = h->g(nn(n, "/cnn_fc1/b"));
+        if (h->wgrad_planes) {
+          w.flags = (w.flags & ~GG_COLSUM) | GG_PLANES | GG_MN_MAJOR;
+          w.A_hi = h->h3p[n][0]; w.A_lo = h->h3p[n][1]; w.B_hi = h->dZ4p[n][0]; w.B_lo = h->dZ4p[n][1];
+        }
         f.host.push_back(w);
         GemmDesc dg = mk(h->dZ4[n], row512, i512, h->p(nn(n, "/cnn_fc1/w")), i512, wfT, h->dZ3p[n], rowP3, cN3p, B, 1024, 512,
                          GG_A_RVEC | GG_B_RVEC | GG_EPI_MASK);
@@ -498,6 +505,10 @@ int build_groups(b2g_sac* h) {
         GemmDesc w = mk(h->h2[n], koff[2], rowoff[2], h->dZ3p[n], dz3row, i64, h->g(nn(n, "/cnn3/w")), wrow[2], i64, 576, 64, R,
                         GG_COLSUM | GG_EPI_ATOMIC, split_for(9, R));
         w.colsum = h->g(nn(n, "/cnn3/b"));
+        if (h->wgrad_planes) {
+          w.flags = (w.flags & ~GG_COLSUM) | GG_PLANES | GG_MN_MAJOR;
+          w.A_hi = h->h2p[n][0]; w.A_lo = h->h2p[n][1]; w.B_hi = h->dZ3pp[n][0]; w.B_lo = h->dZ3pp[n][1];
+        }
         g.host.push_back(w);
         GemmDesc dg = mk(h->dZ3p[n], t_am, t_ar, h->p(nn(n, "/cnn3/w")), t_br, c64, h->dZ2p[n], t_cm, i64, B * H2 * W2, 64, 576,
                          GG_A_RVEC | GG_B_RVEC | GG_EPI_MASK);
@@ -522,6 +533,10 @@ int build_groups(b2g_sac* h) {
         GemmDesc w = mk(h->h1[n], koff[1], rowoff[1], h->dZ2p[n], dz2row, i64, h->g(nn(n, "/cnn2/w")), wrow[1], i64, 512, 64, R,
                         GG_COLSUM | GG_EPI_ATOMIC, split_for(8, R));
         w.colsum = h->g(nn(n, "/cnn2/b"));
+        if (h->wgrad_planes) {
+          w.flags = (w.flags & ~GG_COLSUM) | GG_PLANES | GG_MN_MAJOR;
+          w.A_hi = h->h1p[n][0]; w.A_lo = h->h1p[n][1]; w.B_hi = h->dZ2pp[n][0]; w.B_lo = h->dZ2pp[n][1];
+        }
         g.host.push_back(w);
       }
       for (int py = 0; py < 2; ++py)
@@ -549,6 +564,7 @@ int build_groups(b2g_sac* h) {
               dg.flags |= GG_PLANES;
               dg.A_hi = h->dZ2pp[n][0]; dg.A_lo = h->dZ2pp[n][1];
               dg.B_hi = h->wp[n][1][0]; dg.B_lo = h->wp[n][1][1];
+              dg.C_hi = h->dZ1p[n][0]; dg.C_lo = h->dZ1p[n][1];
             }
             g.host.push_back(dg);
           }
@@ -564,9 +580,36 @@ int build_groups(b2g_sac* h) {
         GemmDesc w = mk(h->x_obs, koff[0], rowoff[0], h->dZ1[n], crow[0], i64, h->g(nn(n, "/cnn1/w")), wrow[0], i64, M, 32, R,
                         GG_COLSUM | GG_EPI_ATOMIC, split_for((M + 63) / 64, R, 74));
         w.colsum = h->g(nn(n, "/cnn1/b"));
+        if (h->wgrad_planes) {
+          w.flags = (w.flags & ~GG_COLSUM) | GG_PLANES | GG_MN_MAJOR | ((Ci & 1) ? GG_A_ALIGN4 : 0);
+          w.A_hi = h->xp[0][0]; w.A_lo = h->xp[0][1]; w.B_hi = h->dZ1p[n][0]; w.B_lo = h->dZ1p[n][1];
+        }
         g.host.push_back(w);
       }
       h->bwd_groups.push_back(g);
+    }
+    if (h->wgrad_planes) {     // bias gradients (column sums of the gradient maps) as one small launch
+      TAB(row512b, iota_tab(B, 512));
+      std::vector<ColsumJob> jobs;
+      int start = 0;
+      for (int n = 0; n < 2; ++n) {
+        const float* srcs[4] = {h->dZ1[n], h->dZ2p[n], h->dZ3p[n], h->dZ4[n]};
+        const int* rows[4] = {crow[0], dz2row, dz3row, row512b};
+        const int nrows[4] = {B * H1 * W1, B * H2 * W2, B * H3 * W3, B};
+        const int Ns[4] = {32, 64, 64, 512};
+        const char* bn[4] = {"/cnn1/b", "/cnn2/b", "/cnn3/b", "/cnn_fc1/b"};
+        for (int l = 0; l < 4; ++l) {
+          ColsumJob j{srcs[l], rows[l], h->g(nn(n, bn[l])), nrows[l], Ns[l], start};
+          const int rows_per_cta = 8 * (256 / (Ns[l] / 4));
+          start += (nrows[l] + rows_per_cta - 1) / rows_per_cta;
+          jobs.push_back(j);
+        }
+      }
+      h->n_colsum = (int)jobs.size();
+      h->colsum_ctas = start;
+      if (int rc = dalloc(h, &h->d_colsum, jobs.size(), false)) return rc;
+      CK(cudaMemcpyAsync(h->d_colsum, jobs.data(), jobs.size() * sizeof(ColsumJob), cudaMemcpyHostToDevice, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
     }
   }
 
@@ -787,6 +830,9 @@ int issue_step(b2g_sac* h, bool sampled, bool apply, bool want_per_sample, Prof*
   for (auto& g : h->fwd_groups) if (int rc = run_group(g)) return rc;
   tail_launch(make_tail(h, want_per_sample), s); ++n; mark("heads_tail");
   for (auto& g : h->bwd_groups) if (int rc = run_group(g)) return rc;
+  if (h->wgrad_planes && h->cfg.precision != B2G_PREC_FP32_SIMT) {
+    colsum_launch(h->d_colsum, h->n_colsum, h->colsum_ctas, s); ++n; mark("bias_grads");
+  }
   if (h->cfg.nranks > 1) {
     // losses/means ride behind the gradients in the same buffer
     CK(cudaMemcpyAsync(h->G + h->n_train, h->metrics, MET_GN_PI * sizeof(float), cudaMemcpyDeviceToDevice, s)); ++n;
@@ -955,6 +1001,8 @@ int b2g_sac_create(const b2g_sac_cfg* cfg, b2g_sac** out) {
   }
   h->use_planes = h->cnn && cfg->precision != B2G_PREC_FP32_SIMT;
   if (const char* pl = getenv("B2G_TC_PLANES")) if (pl[0] == '0') h->use_planes = false;
+  h->wgrad_planes = h->use_planes;
+  if (const char* pl = getenv("B2G_TC_WGRAD_PLANES")) h->wgrad_planes = h->use_planes && pl[0] != '0';
   if (h->use_planes) {
     const size_t nx = (size_t)B * h->Hi * h->Wi * h->Cimg;
     for (int k = 0; k < 2; ++k) { DA(h->xp[0][k], nx); DA(h->xp[1][k], nx); }
@@ -966,6 +1014,7 @@ int b2g_sac_create(const b2g_sac_cfg* cfg, b2g_sac** out) {
       for (int k = 0; k < 2; ++k) {
         DA(h->dZ4p[n][k], (size_t)B * 512); DA(h->dZ3pp[n][k], (size_t)B * (h->H3 + 4) * (h->W3 + 4) * 64);
         DA(h->dZ2pp[n][k], (size_t)B * (h->H2 + 3) * (h->W2 + 3) * 64);
+        DA(h->dZ1p[n][k], (size_t)B * h->H1 * h->W1 * 32);
       }
     const size_t wsz[4] = {(size_t)64 * h->Cimg * 32, 512 * 64, 576 * 64, 1024 * 512};
     for (int n = 0; n < 3; ++n)
