@@ -234,19 +234,34 @@ def main():
     pin = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory().numpy() for k, v in dict(tr, eps=eps).items()}
     h2d = sum(v.nbytes for v in pin.values())
     d2h = 7 * B * 4 + B * 5 * 4 + 16 * 4 + 64 + 8
-    e2e_steps = max(10, min(args.steps, 100))
+    e2e_steps = max(10, min(args.steps, 200))
     for _ in range(3):
-        L.step_explicit(pin["obs"], pin["act"], pin["rew"], pin["next_obs"], pin["done"], pin["eps"], lr=LR)
+        L.step_host_pipelined(pin["obs"], pin["act"], pin["rew"], pin["next_obs"], pin["done"], pin["eps"], lr=LR)
+    L.pipeline_flush()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        L.step_explicit(pin["obs"], pin["act"], pin["rew"], pin["next_obs"], pin["done"], pin["eps"], lr=LR)
+    for _ in range(e2e_steps):        # every step: H2D of its batch (pinned) + D2H of a step's losses; copy k overlaps compute k-1
+        L.step_host_pipelined(pin["obs"], pin["act"], pin["rew"], pin["next_obs"], pin["done"], pin["eps"], lr=LR)
+    last = L.pipeline_flush()
     torch.cuda.synchronize()
     el = time.perf_counter() - t0
+    assert np.isfinite(last["qf1_loss"])
     t = torch.tensor([el], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e = world * e2e_steps / float(t.item())
+    # un-pipelined variant of the same call (b2g_sac_step_explicit: copy, step, read back, return)
+    t0 = time.perf_counter()
+    for _ in range(max(10, e2e_steps // 4)):
+        L.step_explicit(pin["obs"], pin["act"], pin["rew"], pin["next_obs"], pin["done"], pin["eps"], lr=LR)
+    e2e_sync = world * max(10, e2e_steps // 4) / (time.perf_counter() - t0)
+    # the learn() loop of the SB-shaped front end: one new transition enters the device replay per gradient step
+    one = {k: v[:1] for k, v in pin.items() if k != "eps"}
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        L.replay_add(one["obs"], one["act"], one["rew"], one["next_obs"], one["done"])
+        L.step(1, lr=LR)
+    e2e_learn = world * e2e_steps / (time.perf_counter() - t0)
 
     # ---- dominant-kernel roofline: per-launch device time of every group of ONE step (CUDA events on
     # the learner's stream between launches), on rank 0
@@ -281,7 +296,10 @@ def main():
                        "precision": {"fp32": "fp32 FFMA (B2G_PREC_FP32_SIMT)", "bf16x3": "tcgen05 BF16 hi/lo split x3, fp32 TMEM accumulate (B2G_PREC_BF16X3; passes 1e-4 parity)", "bf16": "tcgen05 single-pass BF16 (fast mode, ~5e-4 on Q)"}[args.precision], "parallelism": f"dp{world}",
                        "sync_steps_per_s": sync_steps_per_s},
             "clocks": clk.summary(),
-            "e2e": {"value": e2e, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+            "e2e": {"value": e2e, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16 * 4 + 8 + 64, "steps": e2e_steps,
+                    "api": "b2g_sac_step_host_pipelined: full 256-sample batch from pinned host memory every step, losses read back every step (one step late)",
+                    "unpipelined_steps_per_s": e2e_sync,
+                    "learn_loop_steps_per_s": e2e_learn, "learn_loop_h2d_bytes_per_step": int(sum(v.nbytes for v in one.values()))},
             "gpu_launches": L.launches_per_step() * args.steps,
             "roofline": roofline, "cpu_baseline": cpu,
         }

@@ -18,7 +18,7 @@ SYMBOLS = [
     "b2g_last_error", "b2g_version", "b2g_nccl_unique_id", "b2g_sac_create", "b2g_sac_destroy", "b2g_sync",
     "b2g_param_count", "b2g_param_info", "b2g_get_param", "b2g_set_param", "b2g_get_grad", "b2g_get_adam",
     "b2g_reset_optimizer", "b2g_replay_add", "b2g_replay_size", "b2g_set_norm_stats", "b2g_sac_step",
-    "b2g_sac_step_async", "b2g_sac_step_explicit", "b2g_sac_act", "b2g_launches_per_step", "b2g_last_step_ms",
+    "b2g_sac_step_async", "b2g_sac_step_explicit", "b2g_sac_step_host_pipelined", "b2g_sac_pipeline_flush", "b2g_sac_act", "b2g_launches_per_step", "b2g_last_step_ms",
     "b2g_profile_step",
 ]
 
@@ -78,6 +78,8 @@ def load():
     lib.b2g_sac_step.argtypes = [vp, C.c_int, C.c_float, C.POINTER(SacMetrics)]
     lib.b2g_sac_step_async.argtypes = [vp, C.c_int, C.c_float]
     lib.b2g_sac_step_explicit.argtypes = [vp, fp, fp, fp, fp, fp, fp, C.c_float, C.c_int, C.POINTER(SacMetrics), fp, fp]
+    lib.b2g_sac_step_host_pipelined.argtypes = [vp, fp, fp, fp, fp, fp, fp, C.c_float, C.POINTER(SacMetrics), C.POINTER(C.c_int)]
+    lib.b2g_sac_pipeline_flush.argtypes = [vp, C.POINTER(SacMetrics)]
     lib.b2g_sac_act.argtypes = [vp, fp, C.c_int, C.c_int, fp]
     lib.b2g_launches_per_step.argtypes = [vp]
     lib.b2g_last_step_ms.argtypes = [vp]

@@ -132,6 +132,15 @@ struct b2g_sac {
   float *per_sample = nullptr, *pi_out = nullptr, *eps = nullptr, *rew_n = nullptr, *done_n = nullptr;
   int* indices = nullptr;
   float *s_obs = nullptr, *s_next = nullptr, *s_act = nullptr, *s_rew = nullptr, *s_done = nullptr;  // staged explicit batch
+  // pipelined host-batch path: the big obs / next_obs copies ping-pong on a copy stream
+  float *ps_obs[2]{}, *ps_next[2]{};
+  cudaStream_t cstream = nullptr;
+  cudaEvent_t ev_h2d[2]{}, ev_consumed[2]{}, ev_met[2]{};
+  float* pm_met[2]{};            // pinned: MET_COUNT floats + [log_alpha, grad log_alpha]
+  long long* pm_cnt[2]{};        // pinned counters
+  long long pipe_k = 0;
+  bool pipe_pending = false;
+  cudaEvent_t record_after_gather = nullptr;
   long long* counters = nullptr;
   double* step_consts = nullptr;
   float* d_lr = nullptr;
@@ -801,6 +810,7 @@ int issue_step(b2g_sac* h, bool sampled, bool apply, bool want_per_sample, Prof*
   pa.seed = h->cfg.seed + 0x9E3779B97F4A7C15ull * (unsigned long long)h->cfg.rank; pa.gen = sampled ? 1 : 0; pa.apply = apply ? 1 : 0;
   prep_launch(pa, s); ++n; mark("prep");
   gather_launch(make_gather(h, sampled, true), s); ++n; mark("gather_normalize");
+  if (h->record_after_gather) CK(cudaEventRecord(h->record_after_gather, s));   // staged batch consumed
   CK(cudaMemsetAsync(h->G, 0, (size_t)(h->n_train + MET_COUNT) * sizeof(float), s)); ++n; mark("zero_grads");
   int x3 = h->cfg.precision == B2G_PREC_BF16X3 ? 1 : 0;
   if (const char* dbg = getenv("B2G_TC_DEBUG")) x3 |= atoi(dbg) << 8;   // kernel bring-up toggles (gg_tc.cu)
@@ -893,6 +903,18 @@ int fetch_metrics(b2g_sac* h, b2g_sac_metrics* out) {
   return 0;
 }
 
+void fill_metrics(const b2g_sac* h, const float* m, const long long* cnt, b2g_sac_metrics* out) {
+  const float inv = 1.0f / (float)h->cfg.nranks;
+  out->policy_loss = m[MET_POLICY_LOSS] * inv; out->qf1_loss = m[MET_QF1_LOSS] * inv; out->qf2_loss = m[MET_QF2_LOSS] * inv;
+  out->value_loss = m[MET_VALUE_LOSS] * inv; out->ent_coef_loss = m[MET_ENT_COEF_LOSS] * inv; out->entropy = m[MET_ENTROPY] * inv;
+  out->mean_q1 = m[MET_MEAN_Q1] * inv; out->mean_q2 = m[MET_MEAN_Q2] * inv; out->mean_v = m[MET_MEAN_V] * inv;
+  out->mean_logp = m[MET_MEAN_LOGP] * inv;
+  out->grad_norm_pi = sqrtf(m[MET_GN_PI]); out->grad_norm_values = sqrtf(m[MET_GN_VALUES]);
+  out->grad_ent = m[MET_COUNT + 1] * inv;
+  out->ent_coef = expf(m[MET_COUNT]);
+  out->n_updates = cnt[3];
+}
+
 int find_tensor(const b2g_sac* h, const char* name) {
   if (!name) return -1;
   std::string n(name);
@@ -928,6 +950,14 @@ int b2g_sac_destroy(b2g_sac* h) {
   for (void* q : h->allocs) cudaFree(q);
   if (h->h_met) cudaFreeHost(h->h_met);
   if (h->h_cnt) cudaFreeHost(h->h_cnt);
+  for (int j = 0; j < 2; ++j) {
+    if (h->ev_h2d[j]) cudaEventDestroy(h->ev_h2d[j]);
+    if (h->ev_consumed[j]) cudaEventDestroy(h->ev_consumed[j]);
+    if (h->ev_met[j]) cudaEventDestroy(h->ev_met[j]);
+    if (h->pm_met[j]) cudaFreeHost(h->pm_met[j]);
+    if (h->pm_cnt[j]) cudaFreeHost(h->pm_cnt[j]);
+  }
+  if (h->cstream) cudaStreamDestroy(h->cstream);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -1034,6 +1064,16 @@ int b2g_sac_create(const b2g_sac_cfg* cfg, b2g_sac** out) {
   if (cudaMallocHost((void**)&h->h_met, MET_COUNT * sizeof(float)) != cudaSuccess ||
       cudaMallocHost((void**)&h->h_cnt, 8 * sizeof(long long)) != cudaSuccess)
     return bail(fail(B2G_ECUDA, "cudaMallocHost failed"));
+  for (int j = 0; j < 2; ++j) {
+    if ((rc = dalloc(h, &h->ps_obs[j], (size_t)B * h->E)) || (rc = dalloc(h, &h->ps_next[j], (size_t)B * h->E))) return bail(rc);
+    if (cudaEventCreateWithFlags(&h->ev_h2d[j], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_consumed[j], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_met[j], cudaEventDisableTiming) != cudaSuccess ||
+        cudaMallocHost((void**)&h->pm_met[j], (MET_COUNT + 2) * sizeof(float)) != cudaSuccess ||
+        cudaMallocHost((void**)&h->pm_cnt[j], 8 * sizeof(long long)) != cudaSuccess)
+      return bail(fail(B2G_ECUDA, "pipelined-path resources"));
+  }
+  if (cudaStreamCreateWithFlags(&h->cstream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(B2G_ECUDA, "copy stream"));
   // identity normalisation until b2g_set_norm_stats is called
   {
     std::vector<double> ones(h->E, 1.0);
@@ -1223,6 +1263,61 @@ int b2g_sac_step_explicit(b2g_sac* h, const float* obs, const float* act, const 
   if (pi_out) CK(cudaMemcpyAsync(pi_out, h->pi_out, B * A * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
   if (int rc = fetch_metrics(h, out)) return rc;
   cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1);
+  return 0;
+}
+
+int b2g_sac_step_host_pipelined(b2g_sac* h, const float* obs, const float* act, const float* rew, const float* next_obs,
+                                const float* done, const float* eps, float lr, b2g_sac_metrics* prev_out, int* have_prev) {
+  if (!h || !obs || !act || !rew || !next_obs || !done || !eps) return fail(B2G_EINVAL, "NULL argument");
+  CK(cudaSetDevice(h->cfg.device));
+  if (int rc = set_lr(h, lr)) return rc;
+  refresh_planes(h);
+  const size_t B = h->B, E = h->E, A = h->A;
+  const long long k = h->pipe_k++;
+  const int j = (int)(k & 1);
+  // (1) copy stream: this step's observations into staging slot j (free once the gather of step k-2 has run)
+  if (k >= 2) CK(cudaStreamWaitEvent(h->cstream, h->ev_consumed[j], 0));
+  CK(cudaMemcpyAsync(h->ps_obs[j], obs, B * E * sizeof(float), cudaMemcpyHostToDevice, h->cstream));
+  CK(cudaMemcpyAsync(h->ps_next[j], next_obs, B * E * sizeof(float), cudaMemcpyHostToDevice, h->cstream));
+  CK(cudaEventRecord(h->ev_h2d[j], h->cstream));
+  // (2) compute stream: small tensors in order, then the step on slot j
+  CK(cudaMemcpyAsync(h->s_act, act, B * A * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->s_rew, rew, B * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->s_done, done, B * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->eps, eps, B * A * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamWaitEvent(h->stream, h->ev_h2d[j], 0));
+  float* keep_obs = h->s_obs; float* keep_next = h->s_next;
+  h->s_obs = h->ps_obs[j]; h->s_next = h->ps_next[j];
+  h->record_after_gather = h->ev_consumed[j];
+  int n = 0;
+  int rc = issue_step(h, false, true, false, nullptr, &n);
+  h->record_after_gather = nullptr;
+  h->s_obs = keep_obs; h->s_next = keep_next;
+  if (rc) return rc;
+  // (3) this step's losses -> pinned slot j (read back by the NEXT call, or by b2g_sac_pipeline_flush)
+  CK(cudaMemcpyAsync(h->pm_met[j], h->metrics, MET_COUNT * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(h->pm_met[j] + MET_COUNT, h->p("model/log_ent_coef"), sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(h->pm_met[j] + MET_COUNT + 1, h->g("model/log_ent_coef"), sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(h->pm_cnt[j], h->counters, 8 * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaEventRecord(h->ev_met[j], h->stream));
+  // (4) hand back the PREVIOUS step's losses: blocks only until step k-1 has finished, while step k's copies run
+  if (have_prev) *have_prev = h->pipe_pending ? 1 : 0;
+  if (h->pipe_pending) {
+    CK(cudaEventSynchronize(h->ev_met[j ^ 1]));
+    if (prev_out) fill_metrics(h, h->pm_met[j ^ 1], h->pm_cnt[j ^ 1], prev_out);
+  }
+  h->pipe_pending = true;
+  return 0;
+}
+
+int b2g_sac_pipeline_flush(b2g_sac* h, b2g_sac_metrics* last_out) {
+  if (!h) return fail(B2G_EINVAL, "NULL handle");
+  CK(cudaSetDevice(h->cfg.device));
+  if (!h->pipe_pending) return fail(B2G_ESTATE, "no pipelined step in flight");
+  const int j = (int)((h->pipe_k - 1) & 1);
+  CK(cudaEventSynchronize(h->ev_met[j]));
+  if (last_out) fill_metrics(h, h->pm_met[j], h->pm_cnt[j], last_out);
+  h->pipe_pending = false;
   return 0;
 }
 

@@ -182,6 +182,22 @@ class Learner:
         out["pi"] = pi
         return out
 
+    def step_host_pipelined(self, obs, act, rew, next_obs, done, eps, lr: float = 3e-4):
+        """Enqueue one step on a HOST batch (arrays must stay alive until the next call / flush; pinned float32
+        arrays overlap the copy with the previous step).  Returns the previous step's losses, or None."""
+        B = self.batch_size
+        arrs = [_f32(obs), _f32(act), _f32(np.reshape(rew, -1)), _f32(next_obs), _f32(np.reshape(done, -1)), _f32(eps)]
+        assert arrs[0].size == B * self.obs_elems and arrs[1].size == B * self.n_act and arrs[2].size == B
+        self._pipe_keep = (getattr(self, "_pipe_keep", ()) + (arrs,))[-2:]   # host buffers stay alive while copies fly
+        m, have = _lib.SacMetrics(), C.c_int(0)
+        _lib.check(self.lib.b2g_sac_step_host_pipelined(self.h, *[_fp(a) for a in arrs], lr, C.byref(m), C.byref(have)))
+        return m.as_dict() if have.value else None
+
+    def pipeline_flush(self) -> dict:
+        m = _lib.SacMetrics()
+        _lib.check(self.lib.b2g_sac_pipeline_flush(self.h, C.byref(m)))
+        return m.as_dict()
+
     def act(self, obs, deterministic: bool = True) -> np.ndarray:
         obs = _f32(obs).reshape(-1, self.obs_elems)
         out = np.empty((obs.shape[0], self.n_act), np.float32)

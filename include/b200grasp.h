@@ -112,6 +112,15 @@ int b2g_sac_step_explicit(b2g_sac* h, const float* obs, const float* act, const 
                           const float* done, const float* eps, float lr, int apply_update, b2g_sac_metrics* out,
                           float* per_sample, float* pi_out);
 
+/* Same work as b2g_sac_step_explicit(apply_update = 1) for a caller that keeps its replay buffer on the HOST
+ * (as stable-baselines does): the step is enqueued and the call returns the losses of the PREVIOUSLY enqueued step
+ * (*have_prev = 0 on the first call), so the host->device copy of step k overlaps the compute of step k-1.  The
+ * host arrays must stay valid until the next call or b2g_sac_pipeline_flush (use pinned memory for true overlap). */
+int b2g_sac_step_host_pipelined(b2g_sac* h, const float* obs, const float* act, const float* rew, const float* next_obs,
+                                const float* done, const float* eps, float lr, b2g_sac_metrics* prev_out, int* have_prev);
+/* waits for the last pipelined step and returns its losses */
+int b2g_sac_pipeline_flush(b2g_sac* h, b2g_sac_metrics* last_out);
+
 /* policy_tf.step (SAC.predict, utils.py:71): obs are RAW, normalised with the current stats.
  * deterministic -> tanh(mu); else tanh(mu + eps*std) with eps from the handle's generator. */
 int b2g_sac_act(b2g_sac* h, const float* obs, int n, int deterministic, float* act_out);

@@ -216,3 +216,24 @@ def test_sampled_step_from_replay_and_policy_act():
     a_sto = L.act(raw["obs"][:5], deterministic=False)
     assert a_sto.shape == (5, 5) and np.abs(a_sto).max() <= 1.0 and np.abs(a_sto - a_gpu).max() > 0
     L.close()
+
+
+def test_pipelined_host_batch_path_equals_explicit_path():
+    """b2g_sac_step_host_pipelined (copy/compute overlap, losses one step late) must produce the same
+    parameters and losses as b2g_sac_step_explicit on the same two batches."""
+    cfg, params, vn = load_case("sac_depth")
+    B = 16
+    batches = [make_batch(vn, B, seed=300 + i) for i in range(3)]
+    A = make_learner(cfg, vn, B, params, precision=0)
+    Bm = make_learner(cfg, vn, B, params, precision=0)
+    outs_a = [A.step_explicit(r["obs"], r["act"], r["rew"], r["next_obs"], r["done"], e, lr=LR) for r, _, e in batches]
+    prev = [Bm.step_host_pipelined(r["obs"], r["act"], r["rew"], r["next_obs"], r["done"], e, lr=LR) for r, _, e in batches]
+    assert prev[0] is None
+    outs_b = prev[1:] + [Bm.pipeline_flush()]
+    for a, b in zip(outs_a, outs_b):
+        for k in ("policy_loss", "qf1_loss", "value_loss", "grad_norm_values", "n_updates"):
+            assert abs(a[k] - b[k]) <= 2e-5 * max(1.0, abs(a[k])), (k, a[k], b[k])
+    pa, pb = A.get_parameters(), Bm.get_parameters()
+    for n in pa:
+        assert np.abs(pa[n] - pb[n]).max() <= 1e-6 + 1e-5 * np.abs(pa[n]).max(), n
+    A.close(); Bm.close()
