@@ -577,27 +577,44 @@ __global__ void __launch_bounds__(Roles<planes>::NTHREADS, 1) gg_tc_kernel(const
     constexpr int LPR = EPI_COLS / 4, RPI = 32 / LPR;
     const uint32_t stg = ring + STAGES * STAGE_BYTES + (uint32_t)ew * (32 * EPI_COLS * 4);
     uint32_t it = 0;
+    int staged_p = -1, staged_n0 = -1;             // which (problem, column block) the staged tables belong to
+    // row-side offsets are fetched one tile ahead (their round trip overlaps the current tile's work)
+    auto row_fetch = [&](int tile, int& cm_o, int& km_o, bool& ok_o) {
+      cm_o = km_o = 0; ok_o = false;
+      if (tile >= pk.total_tiles) return;
+      const TileInfo t2 = tile_info(pk, tile);
+      if (t2.nchunks == 0) return;
+      const GemmDesc& d2 = pk.d[t2.p];
+      const int m2 = t2.m0 + lq * 32 + lane;
+      ok_o = m2 < d2.M;
+      cm_o = ok_o ? d2.cM[m2] : 0;
+      km_o = (ok_o && (d2.flags & GG_EPI_MASK)) ? (d2.kM ? d2.kM[m2] : cm_o) : 0;
+    };
+    int cm_n, km_n; bool ok_n;
+    row_fetch(blockIdx.x, cm_n, km_n, ok_n);
     for (int tile = blockIdx.x; tile < pk.total_tiles; tile += gridDim.x) {
       const TileInfo ti = tile_info(pk, tile);
+      const int cm = cm_n, km = km_n;
+      const bool m_ok = ok_n;
+      row_fetch(tile + gridDim.x, cm_n, km_n, ok_n);
       if (ti.nchunks == 0) continue;
       const GemmDesc& d = pk.d[ti.p];
       const uint32_t buf = it & 1;
-      const int m = ti.m0 + lq * 32 + lane;
-      const bool m_ok = m < d.M;
-      const int cm = m_ok ? d.cM[m] : 0;           // issued before the wait: overlaps the mainloop
-      const int km = (m_ok && (d.flags & GG_EPI_MASK)) ? (d.kM ? d.kM[m] : cm) : 0;
-      asm volatile("bar.sync 2, %0;" ::"n"(NEPI));  // previous tile's readers of the staged tables are done
-      if (et < TN) {
-        const int n = ti.n0 + et;
-        const bool ok = n < d.N;
-        const int cn = ok ? d.cN[n] : 0;
-        s_cn[et] = cn;
-        s_kn[et] = ok ? (d.kN ? d.kN[n] : cn) : 0;
-      } else if (et < 2 * TN) {
-        const int n = ti.n0 + et - TN;
-        s_bias[et - TN] = ((d.flags & GG_EPI_BIAS_RELU) && n < d.N) ? d.bias[n] : 0.f;
+      if (ti.p != staged_p || ti.n0 != staged_n0) {   // block-uniform: every epilogue warp walks the same tiles
+        asm volatile("bar.sync 2, %0;" ::"n"(NEPI));  // previous readers of the staged tables are done
+        if (et < TN) {
+          const int n = ti.n0 + et;
+          const bool ok = n < d.N;
+          const int cn = ok ? d.cN[n] : 0;
+          s_cn[et] = cn;
+          s_kn[et] = ok ? (d.kN ? d.kN[n] : cn) : 0;
+        } else if (et < 2 * TN) {
+          const int n = ti.n0 + et - TN;
+          s_bias[et - TN] = ((d.flags & GG_EPI_BIAS_RELU) && n < d.N) ? d.bias[n] : 0.f;
+        }
+        asm volatile("bar.sync 2, %0;" ::"n"(NEPI));
+        staged_p = ti.p; staged_n0 = ti.n0;
       }
-      asm volatile("bar.sync 2, %0;" ::"n"(NEPI));
       const bool tr = pk.trace && blockIdx.x == 0 && ew == 0 && lane == 0 && it < 64;
       mbar_wait(smem_u32(&bar_acc_full[buf]), (it >> 1) & 1);
       tc_fence_after();
