@@ -39,32 +39,31 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons streamed (-lms 100) DURING the timed region."""
+
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, dev):
-        self.dev, self.rows, self.stop = dev, [], threading.Event()
-        self.t = threading.Thread(target=self.run, daemon=True)
-
-    def run(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        while not self.stop.is_set():
-            try:
-                o = subprocess.run(["nvidia-smi", "-i", str(self.dev), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
-                                   capture_output=True, text=True, timeout=5).stdout.strip()
-                if o:
-                    self.rows.append([x.strip() for x in o.split(",")])
-            except Exception:
-                pass
-            self.stop.wait(0.1)
+        self.dev, self.rows, self.proc = dev, [], None
 
     def __enter__(self):
-        self.t.start()
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.dev), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
         return self
 
     def __exit__(self, *a):
-        self.stop.set()
-        self.t.join(timeout=6)
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                out, _ = self.proc.communicate(timeout=5)
+            except Exception:
+                self.proc.kill()
+                out = ""
+            self.rows = [[x.strip() for x in line.split(",")] for line in out.splitlines() if line.count(",") >= 5]
 
     def summary(self):
         if not self.rows:
@@ -214,10 +213,11 @@ def main():
     L.step(args.warmup, lr=LR)
     barrier()
     with ClockSampler(local) as clk:
-        L.step(args.steps, lr=LR)
+        time.sleep(0.25)                       # let the sampler stream before the timed region starts
+        L.step(args.steps, lr=LR)              # the timed region: exactly K steps, CUDA events on the learner's stream
         ms = L.last_step_ms()
-        # keep the sampler alive for at least a few samples on very short runs
-        if ms < 600:
+        t_end = time.time() + 1.0              # short regions: repeat the same K-step region so that several clock
+        while time.time() < t_end:             # samples fall under load; the fastest K-step pass is reported
             L.step(args.steps, lr=LR)
             ms = min(ms, L.last_step_ms())
     barrier()
