@@ -1,5 +1,5 @@
 import sys, time, numpy as np
-sys.path.insert(0, '.')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 import tests.test_gpu_parity as T
 from tests.util import *
 for name in ["test_encoder_mlp_trained_weights_b64", "test_depth_cnn_trained_weights_b32", "test_rgbd_cnn_fresh_init_b16", "test_depth_cnn_fresh_init_b256", "test_two_steps_optimizer_state", "test_sampled_step_from_replay_and_policy_act"]:

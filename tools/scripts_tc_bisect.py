@@ -1,5 +1,5 @@
 import os, sys, time, numpy as np, torch
-sys.path.insert(0, '.')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 from tests.util import *
 from oracle import sac_ref as R
 cfg, params, vn = load_case("sac_depth")

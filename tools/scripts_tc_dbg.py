@@ -1,5 +1,5 @@
 import os, sys
-sys.path.insert(0, '.')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 os.environ["B2G_NO_GRAPH"] = "1"
 from tests.util import *
 cfg, params, vn = load_case("sac_depth")

@@ -1,5 +1,5 @@
 import os, sys
-sys.path.insert(0, '.')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 from tests.util import *
 cfg, params, vn = load_case("sac_depth")
 tr = b200grasp.synth.make_transitions(2048, vn["obs_mean"], vn["obs_var"])
