@@ -688,7 +688,12 @@ int build_groups(b2g_sac* h) {
     for (auto& g : h->bwd_groups) {
       std::vector<GemmDesc> wg, dg;
       for (auto& d : g.host) ((d.flags & GG_A_RVEC) ? dg : wg).push_back(d);
-      if (wg.empty() || dg.empty()) { split.push_back(g); continue; }
+      // the cp.async (planes) kernel picks K-major / MN-major per tile at run time, so a layer's wgrad and dgrad
+      // share one launch when every problem of the group is in planes mode
+      bool all_planes = true;
+      for (auto& d : g.host) all_planes = all_planes && (d.flags & GG_PLANES);
+      if (const char* mg = getenv("B2G_TC_MERGE_BWD")) if (mg[0] == '0') all_planes = false;
+      if (wg.empty() || dg.empty() || all_planes) { split.push_back(g); continue; }
       GemmGroup a = g, b = g;
       const std::string base = g.name.substr(0, g.name.find('_'));
       a.name = base + "_wgrad"; a.host = wg;
