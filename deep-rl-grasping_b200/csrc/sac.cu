@@ -56,6 +56,9 @@ struct NcclApi {
   int (*CommInitRank)(void**, int, UId, int) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
   int (*CommDestroy)(void*) = nullptr;
+  int (*CommSplit)(void*, int, int, void**, void*) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
 };
 NcclApi g_nccl;
@@ -74,6 +77,9 @@ int load_nccl(const char* path) {
   g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(g_nccl.lib, "ncclAllReduce");
   g_nccl.CommDestroy = (int (*)(void*))dlsym(g_nccl.lib, "ncclCommDestroy");
   g_nccl.GetErrorString = (const char* (*)(int))dlsym(g_nccl.lib, "ncclGetErrorString");
+  g_nccl.CommSplit = (int (*)(void*, int, int, void**, void*))dlsym(g_nccl.lib, "ncclCommSplit");
+  g_nccl.GroupStart = (int (*)())dlsym(g_nccl.lib, "ncclGroupStart");
+  g_nccl.GroupEnd = (int (*)())dlsym(g_nccl.lib, "ncclGroupEnd");
   if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce)
     return fail(B2G_ENCCL, "libnccl is missing symbols");
   return 0;
@@ -150,6 +156,13 @@ struct b2g_sac {
   cudaGraphExec_t graph_exec = nullptr;
   bool use_graph = true;
   void* nccl_comm = nullptr;
+  void* nccl_comm2 = nullptr;          // second communicator: early all-reduce on the side stream
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool overlap_ar = false;
+  int ar_sms = 16;
+  ColsumJob* d_colsum_early = nullptr;
+  int n_colsum_early = 0, colsum_early_ctas = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   float last_ms = 0.f;
   int launches = 0;
@@ -599,8 +612,8 @@ int build_groups(b2g_sac* h) {
     }
     if (h->wgrad_planes) {     // bias gradients (column sums of the gradient maps) as one small launch
       TAB(row512b, iota_tab(B, 512));
-      std::vector<ColsumJob> jobs;
-      int start = 0;
+      std::vector<ColsumJob> jobs, early;
+      int start = 0, estart = 0;
       for (int n = 0; n < 2; ++n) {
         const float* srcs[4] = {h->dZ1[n], h->dZ2p[n], h->dZ3p[n], h->dZ4[n]};
         const int* rows[4] = {crow[0], dz2row, dz3row, row512b};
@@ -608,12 +621,21 @@ int build_groups(b2g_sac* h) {
         const int Ns[4] = {32, 64, 64, 512};
         const char* bn[4] = {"/cnn1/b", "/cnn2/b", "/cnn3/b", "/cnn_fc1/b"};
         for (int l = 0; l < 4; ++l) {
-          ColsumJob j{srcs[l], rows[l], h->g(nn(n, bn[l])), nrows[l], Ns[l], start};
           const int rows_per_cta = 8 * (256 / (Ns[l] / 4));
-          start += (nrows[l] + rows_per_cta - 1) / rows_per_cta;
-          jobs.push_back(j);
+          const int ctas = (nrows[l] + rows_per_cta - 1) / rows_per_cta;
+          if (l == 3) {       // cnn_fc1 bias: ready as soon as dZ4 exists -> part of the early all-reduce range
+            early.push_back(ColsumJob{srcs[l], rows[l], h->g(nn(n, bn[l])), nrows[l], Ns[l], estart});
+            estart += ctas;
+          } else {
+            jobs.push_back(ColsumJob{srcs[l], rows[l], h->g(nn(n, bn[l])), nrows[l], Ns[l], start});
+            start += ctas;
+          }
         }
       }
+      h->n_colsum_early = (int)early.size();
+      h->colsum_early_ctas = estart;
+      if (int rc = dalloc(h, &h->d_colsum_early, early.size(), false)) return rc;
+      CK(cudaMemcpyAsync(h->d_colsum_early, early.data(), early.size() * sizeof(ColsumJob), cudaMemcpyHostToDevice, h->stream));
       h->n_colsum = (int)jobs.size();
       h->colsum_ctas = start;
       if (int rc = dalloc(h, &h->d_colsum, jobs.size(), false)) return rc;
@@ -819,6 +841,7 @@ int issue_step(b2g_sac* h, bool sampled, bool apply, bool want_per_sample, Prof*
   CK(cudaMemsetAsync(h->G, 0, (size_t)(h->n_train + MET_COUNT) * sizeof(float), s)); ++n; mark("zero_grads");
   int x3 = h->cfg.precision == B2G_PREC_BF16X3 ? 1 : 0;
   if (const char* dbg = getenv("B2G_TC_DEBUG")) x3 |= atoi(dbg) << 8;   // kernel bring-up toggles (gg_tc.cu)
+  int sm_reserve = 0;     // SMs left free for a concurrently running collective (persistent GEMM grids are 1 CTA / SM)
   auto run_group = [&](GemmGroup& g) -> int {
     const char* trn = getenv("B2G_TC_TRACE");
     const bool trace = prof && prof->on && trn && g.name == trn && g.tc;
@@ -827,7 +850,7 @@ int issue_step(b2g_sac* h, bool sampled, bool apply, bool want_per_sample, Prof*
       g_tc_trace = h->dbg_trace;
     }
     struct Reset { ~Reset() { g_tc_trace = nullptr; } } reset_;
-    if (g.tc) CK(gg_tc_launch(g.host.data(), (int)g.host.size(), g.total_tiles, g.host[0].flags, x3, h->num_sms, s));
+    if (g.tc) CK(gg_tc_launch(g.host.data(), (int)g.host.size(), g.total_tiles, g.host[0].flags, x3, h->num_sms - sm_reserve, s));
     else gg_simt_launch(g.dev, (int)g.host.size(), g.total_tiles, s);
     ++n; mark(g.name.c_str());
     if (trace) {
@@ -844,16 +867,54 @@ int issue_step(b2g_sac* h, bool sampled, bool apply, bool want_per_sample, Prof*
   };
   for (auto& g : h->fwd_groups) if (int rc = run_group(g)) return rc;
   tail_launch(make_tail(h, want_per_sample), s); ++n; mark("heads_tail");
-  for (auto& g : h->bwd_groups) if (int rc = run_group(g)) return rc;
-  if (h->wgrad_planes && h->cfg.precision != B2G_PREC_FP32_SIMT) {
-    colsum_launch(h->d_colsum, h->n_colsum, h->colsum_ctas, s); ++n; mark("bias_grads");
+  const bool planes_bias = h->wgrad_planes && h->cfg.precision != B2G_PREC_FP32_SIMT;
+  // index of the last backward group that touches cnn_fc1 / the heads: everything up to it produces the gradients of
+  // [cnn_fc1 .. end] of both trainable blocks (+ log_ent_coef + the loss scalars) -- 84 % of the bytes
+  int last_fc1 = -1;
+  for (size_t i = 0; i < h->bwd_groups.size(); ++i)
+    if (h->bwd_groups[i].name.find("fc1") != std::string::npos || h->bwd_groups[i].name.find("heads") != std::string::npos) last_fc1 = (int)i;
+  const bool overlap = h->overlap_ar && h->cnn && last_fc1 >= 0 && last_fc1 + 1 < (int)h->bwd_groups.size();
+  const int64_t pi_fc1 = h->tensors[h->tindex.at("model/pi/" + std::string(h->cnn ? "cnn_fc1/w" : "fc0/kernel"))].off;
+  const int64_t v_fc1 = h->tensors[h->tindex.at("model/values_fn/" + std::string(h->cnn ? "cnn_fc1/w" : "vf/fc0/kernel"))].off;
+  auto nccl_ck = [&](int rc) -> int {
+    if (rc != 0) return fail(B2G_ENCCL, std::string("nccl: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
+    return 0;
+  };
+  for (size_t i = 0; i < h->bwd_groups.size(); ++i) {
+    if (int rc = run_group(h->bwd_groups[i])) return rc;
+    if ((int)i == last_fc1) {
+      if (planes_bias && h->n_colsum_early) { colsum_launch(h->d_colsum_early, h->n_colsum_early, h->colsum_early_ctas, s); ++n; mark("bias_grads_fc1"); }
+      if (overlap) {
+        // early all-reduce on the side stream / second communicator, overlapping the conv backward
+        CK(cudaMemcpyAsync(h->G + h->n_train, h->metrics, MET_GN_PI * sizeof(float), cudaMemcpyDeviceToDevice, s)); ++n;
+        CK(cudaEventRecord(h->ev_fork, s));
+        CK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+        if (int rc = nccl_ck(g_nccl.GroupStart())) return rc;
+        if (int rc = nccl_ck(g_nccl.AllReduce(h->G + pi_fc1, h->G + pi_fc1, (size_t)(h->n_pi - pi_fc1), 7, 0, h->nccl_comm2, h->side))) return rc;
+        if (int rc = nccl_ck(g_nccl.AllReduce(h->G + v_fc1, h->G + v_fc1, (size_t)(h->n_train + MET_COUNT - v_fc1), 7, 0, h->nccl_comm2, h->side))) return rc;
+        if (int rc = nccl_ck(g_nccl.GroupEnd())) return rc;
+        ++n;
+        CK(cudaEventRecord(h->ev_join, h->side));
+        sm_reserve = h->ar_sms;
+      }
+    }
   }
+  if (planes_bias) { colsum_launch(h->d_colsum, h->n_colsum, h->colsum_ctas, s); ++n; mark("bias_grads"); }
   if (h->cfg.nranks > 1) {
-    // losses/means ride behind the gradients in the same buffer
-    CK(cudaMemcpyAsync(h->G + h->n_train, h->metrics, MET_GN_PI * sizeof(float), cudaMemcpyDeviceToDevice, s)); ++n;
-    int rc = g_nccl.AllReduce(h->G, h->G, (size_t)(h->n_train + MET_COUNT), /*ncclFloat32*/ 7, /*ncclSum*/ 0, h->nccl_comm, s);
-    if (rc != 0) return fail(B2G_ENCCL, std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
-    ++n;
+    if (overlap) {
+      // late all-reduce: the conv gradients of both blocks (0.29 MB each), then join the early one
+      if (int rc = nccl_ck(g_nccl.GroupStart())) return rc;
+      if (int rc = nccl_ck(g_nccl.AllReduce(h->G, h->G, (size_t)pi_fc1, 7, 0, h->nccl_comm, s))) return rc;
+      if (int rc = nccl_ck(g_nccl.AllReduce(h->G + h->n_pi, h->G + h->n_pi, (size_t)(v_fc1 - h->n_pi), 7, 0, h->nccl_comm, s))) return rc;
+      if (int rc = nccl_ck(g_nccl.GroupEnd())) return rc;
+      ++n;
+      CK(cudaStreamWaitEvent(s, h->ev_join, 0));
+    } else {
+      // losses/means ride behind the gradients in the same buffer
+      CK(cudaMemcpyAsync(h->G + h->n_train, h->metrics, MET_GN_PI * sizeof(float), cudaMemcpyDeviceToDevice, s)); ++n;
+      if (int rc = nccl_ck(g_nccl.AllReduce(h->G, h->G, (size_t)(h->n_train + MET_COUNT), /*ncclFloat32*/ 7, /*ncclSum*/ 0, h->nccl_comm, s))) return rc;
+      ++n;
+    }
     CK(cudaMemcpyAsync(h->metrics, h->G + h->n_train, MET_GN_PI * sizeof(float), cudaMemcpyDeviceToDevice, s)); ++n;
     mark("allreduce");
   }
@@ -951,7 +1012,11 @@ int b2g_sac_destroy(b2g_sac* h) {
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+  if (h->nccl_comm2 && g_nccl.CommDestroy) g_nccl.CommDestroy(h->nccl_comm2);
   if (h->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->nccl_comm);
+  if (h->side) cudaStreamDestroy(h->side);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   for (void* q : h->allocs) cudaFree(q);
   if (h->h_met) cudaFreeHost(h->h_met);
   if (h->h_cnt) cudaFreeHost(h->h_cnt);
@@ -1094,6 +1159,22 @@ int b2g_sac_create(const b2g_sac_cfg* cfg, b2g_sac** out) {
     memcpy(id.b, cfg->nccl_id, 128);
     int nrc = g_nccl.CommInitRank(&h->nccl_comm, cfg->nranks, id, cfg->rank);
     if (nrc != 0) return bail(fail(B2G_ENCCL, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "?")));
+    {   // second communicator + side stream for the early (overlapped) all-reduce
+      const char* ov = getenv("B2G_AR_OVERLAP");
+      // opt-in (B2G_AR_OVERLAP=1): verified bit-correct at N=2, but measured gain is ~1 % because the persistent GEMM
+      // grids occupy every SM (even with SMs reserved the collective's launch latency dominates), see DESIGN.md section 5
+      if ((ov && ov[0] == '1') && g_nccl.CommSplit && g_nccl.GroupStart && g_nccl.GroupEnd) {
+        if (g_nccl.CommSplit(h->nccl_comm, 0, cfg->rank, &h->nccl_comm2, nullptr) == 0 && h->nccl_comm2 &&
+            cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) == cudaSuccess) {
+          h->overlap_ar = true;
+          if (const char* e = getenv("B2G_AR_SMS")) h->ar_sms = atoi(e);
+          g_nccl.AllReduce(h->G, h->G, 1024, 7, 0, h->nccl_comm2, h->side);     // warm-up
+          cudaStreamSynchronize(h->side);
+        }
+      }
+    }
     // warm the communicator up outside any stream capture (NCCL allocates its channels lazily)
     nrc = g_nccl.AllReduce(h->G, h->G, (size_t)(h->n_train + MET_COUNT), 7, 0, h->nccl_comm, h->stream);
     if (nrc != 0 || cudaStreamSynchronize(h->stream) != cudaSuccess) return bail(fail(B2G_ENCCL, "NCCL warm-up all-reduce failed"));
