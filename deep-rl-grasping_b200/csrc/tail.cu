@@ -84,9 +84,15 @@ __global__ void __launch_bounds__(WARPS * 32) tail_kernel(TailArgs t) {
   pdl_trigger();
   pdl_wait();
   const float* k1s[S_NW] = {t.pi.k1, t.vf.k1, t.q1.k1, t.q2.k1, t.vt.k1};
+  // stage the five 64x64 fc1 kernels (row stride 65) with 4-byte cp.async: all 80 copies of a thread are in flight
+  // at once (a load->store loop serialises into ~80 round trips and dominated this kernel, profiles/ncu_tail_r1.md)
   for (int w = 0; w < S_NW; ++w)
-    for (int i = tid; i < H * H; i += blockDim.x) Wk1[w * H * LD + (i >> 6) * LD + (i & 63)] = k1s[w][i];
+    for (int i = tid; i < H * H; i += blockDim.x) {
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&Wk1[w * H * LD + (i >> 6) * LD + (i & 63)]);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(k1s[w] + i) : "memory");
+    }
   for (int i = tid; i < n_acc + MET_COUNT + 1; i += blockDim.x) acc[i] = 0.f;
+  asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
 
   float* a_kmu = acc;
@@ -271,7 +277,11 @@ __global__ void __launch_bounds__(WARPS * 32) tail_kernel(TailArgs t) {
 __global__ void __launch_bounds__(WARPS * 32) act_kernel(TailArgs t, int n, int deterministic, float* act_out) {
   __shared__ float Wk1[H * LD];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < H * H; i += blockDim.x) Wk1[(i >> 6) * LD + (i & 63)] = t.pi.k1[i];
+  for (int i = tid; i < H * H; i += blockDim.x) {
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&Wk1[(i >> 6) * LD + (i & 63)]);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(t.pi.k1 + i) : "memory");
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
   const int A = t.A;
   for (int b = blockIdx.x * WARPS + warp; b < n; b += gridDim.x * WARPS) {
