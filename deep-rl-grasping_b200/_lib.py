@@ -20,7 +20,26 @@ SYMBOLS = [
     "b2g_reset_optimizer", "b2g_replay_add", "b2g_replay_size", "b2g_set_norm_stats", "b2g_sac_step",
     "b2g_sac_step_async", "b2g_sac_step_explicit", "b2g_sac_step_host_pipelined", "b2g_sac_pipeline_flush", "b2g_sac_act", "b2g_launches_per_step", "b2g_last_step_ms",
     "b2g_profile_step",
+    "b2g_bdq_create", "b2g_bdq_destroy", "b2g_bdq_param_count", "b2g_bdq_param_info", "b2g_bdq_get_param", "b2g_bdq_set_param",
+    "b2g_bdq_get_grad", "b2g_bdq_replay_add", "b2g_bdq_replay_size", "b2g_bdq_set_norm_stats", "b2g_bdq_step",
+    "b2g_bdq_step_explicit", "b2g_bdq_act",
 ]
+
+
+class BdqCfg(C.Structure):
+    _fields_ = [
+        ("obs_dim", C.c_int32), ("n_branches", C.c_int32), ("n_bins", C.c_int32), ("trunk0", C.c_int32), ("trunk1", C.c_int32),
+        ("branch_hidden", C.c_int32), ("batch", C.c_int32), ("buffer_capacity", C.c_int64), ("gamma", C.c_float),
+        ("target_update_freq", C.c_int32), ("trunk_grad_rescale", C.c_int32), ("seed", C.c_uint64), ("device", C.c_int32),
+        ("rank", C.c_int32), ("nranks", C.c_int32),
+    ]
+
+
+class BdqMetrics(C.Structure):
+    _fields_ = [("loss", C.c_float), ("mean_q", C.c_float), ("grad_norm", C.c_float), ("n_updates", C.c_int64)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
 
 
 class SacCfg(C.Structure):
@@ -85,6 +104,19 @@ def load():
     lib.b2g_last_step_ms.argtypes = [vp]
     lib.b2g_last_step_ms.restype = C.c_float
     lib.b2g_profile_step.argtypes = [vp, C.c_float, C.POINTER(C.c_char_p), fp, C.c_int]
+    lib.b2g_bdq_create.argtypes = [C.POINTER(BdqCfg), C.POINTER(vp)]
+    lib.b2g_bdq_destroy.argtypes = [vp]
+    lib.b2g_bdq_param_count.argtypes = [vp]
+    lib.b2g_bdq_param_info.argtypes = [vp, C.c_int, C.c_char_p, C.c_size_t, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
+    for f in ("b2g_bdq_get_param", "b2g_bdq_set_param", "b2g_bdq_get_grad"):
+        getattr(lib, f).argtypes = [vp, C.c_char_p, fp, C.c_size_t]
+    lib.b2g_bdq_replay_add.argtypes = [vp, fp, fp, fp, fp, fp, C.c_int64]
+    lib.b2g_bdq_replay_size.argtypes = [vp]
+    lib.b2g_bdq_replay_size.restype = C.c_int64
+    lib.b2g_bdq_set_norm_stats.argtypes = [vp, dp, dp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int]
+    lib.b2g_bdq_step.argtypes = [vp, C.c_int, C.c_float, C.POINTER(BdqMetrics)]
+    lib.b2g_bdq_step_explicit.argtypes = [vp, fp, fp, fp, fp, fp, fp, C.c_float, C.c_int, C.POINTER(BdqMetrics), fp]
+    lib.b2g_bdq_act.argtypes = [vp, fp, C.c_int, C.POINTER(C.c_int32)]
     _lib = lib
     return lib
 

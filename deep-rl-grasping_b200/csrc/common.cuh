@@ -45,6 +45,8 @@ enum GemmFlags : int {
   GG_COLSUM = 1 << 5,     // colsum[n] += sum_r B(r, n)   (bias gradients; tile_m == 0 only)
   GG_PLANES = 1 << 6,     // operands come pre-split as BF16 hi/lo planes (A_hi.., B_hi..), copied by cp.async
   GG_A_ALIGN4 = 1 << 7,   // plane A rows are only 8-byte aligned (conv1 with one image channel)
+  GG_EPI_BIAS = 1 << 10,  // C = acc + bias[n] (no activation; output layers)
+  GG_EPI_SCALE = 1 << 11, // C = acc * alpha (after mask)
   GG_MN_MAJOR = 1 << 9,   // planes mode, wgrad: both operands contiguous along their M / N index -> MN-major UMMA tiles
   GG_CN_AFFINE4 = 1 << 8, // host-verified: cN / kN contiguous inside aligned 4-column groups, outputs 16-byte aligned
 };
@@ -65,6 +67,7 @@ struct GemmDesc {
   const uint16_t* B_hi; const uint16_t* B_lo;
   const int* bR_p; const int* bN_p;
   uint16_t* C_hi; uint16_t* C_lo;      // optional plane copy of the output (feeds the next contraction)
+  float alpha;                         // GG_EPI_SCALE
   int M, N, R;
   int flags;
   int splitR;

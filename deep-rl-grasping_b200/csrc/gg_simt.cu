@@ -204,10 +204,12 @@ __global__ void __launch_bounds__(256) gg_simt_kernel(const GemmDesc* __restrict
         const int cn = d.cN[n];
         co[j] = cm + cn;
         if (d.flags & GG_EPI_BIAS_RELU) v[j] = fmaxf(v[j] + d.bias[n], 0.f);
+        if (d.flags & GG_EPI_BIAS) v[j] += d.bias[n];
         if (d.flags & GG_EPI_MASK) {
           const int kn = d.kN ? d.kN[n] : cn;
           v[j] = d.mask[km + kn] > 0.f ? v[j] : 0.f;
         }
+        if (d.flags & GG_EPI_SCALE) v[j] *= d.alpha;
       }
     }
     if (d.C_hi) {

@@ -35,7 +35,8 @@ bool pdl_enabled() {
 }
 }  // namespace b2g
 
-static thread_local std::string g_err;
+thread_local std::string g_b2g_err;     // shared with bdq.cu
+#define g_err g_b2g_err
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 #define CK(call)                                                                                  \
   do {                                                                                            \

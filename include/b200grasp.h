@@ -133,6 +133,55 @@ float b2g_last_step_ms(const b2g_sac* h);
  * names/ms arrays of capacity cap; returns the number of groups */
 int b2g_profile_step(b2g_sac* h, float lr, const char** names, float* ms, int cap);
 
+/* ------------------------------------------------------------------------------------------------
+ * BDQ (branching dueling Q-network) learner -- the `sb.BDQ` object of train_stable_baselines.py:103-104 and
+ * sb_helper.py:202-226 (author's fork `bdq_sb`, absent from the reference tree: parity unpinned).
+ * Variable names / shapes follow trained_models/BDQ_8pads/BDQ_simple_8pads.zip.  Actions are stored as branch
+ * bin indices (floats holding integers); bin k of a branch maps to linspace(-1, 1, n_bins)[k].
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct b2g_bdq b2g_bdq;
+typedef struct b2g_bdq_cfg {
+  int32_t obs_dim;             /* 100 in the shipped zips                                                */
+  int32_t n_branches;          /* action dimensions (3 simplified / 5 full); <= 8                        */
+  int32_t n_bins;              /* num_actions_pad (config/gripper_grasp.yaml:112)                        */
+  int32_t trunk0, trunk1;      /* layers[0] = common_net                                                 */
+  int32_t branch_hidden;       /* layers[1] = layers[2] (branch and state-value hidden width)            */
+  int32_t batch;
+  int64_t buffer_capacity;
+  float gamma;
+  int32_t target_update_freq;  /* hard copy every N updates (target_network_update_freq)                 */
+  int32_t trunk_grad_rescale;  /* 1: scale the gradient entering the trunk by 1/(n_branches+1) (paper)   */
+  uint64_t seed;
+  int32_t device;
+  int32_t rank, nranks;        /* nranks must be 1 in this revision                                      */
+} b2g_bdq_cfg;
+typedef struct b2g_bdq_metrics {
+  float loss, mean_q, grad_norm;
+  int64_t n_updates;
+} b2g_bdq_metrics;
+
+int b2g_bdq_create(const b2g_bdq_cfg* cfg, b2g_bdq** out);
+int b2g_bdq_destroy(b2g_bdq* h);
+int b2g_bdq_param_count(const b2g_bdq* h);
+int b2g_bdq_param_info(const b2g_bdq* h, int idx, char* name, size_t name_cap, int64_t* rows, int64_t* cols, int32_t* ndim);
+int b2g_bdq_get_param(b2g_bdq* h, const char* name, float* dst, size_t numel);
+int b2g_bdq_set_param(b2g_bdq* h, const char* name, const float* src, size_t numel);
+int b2g_bdq_get_grad(b2g_bdq* h, const char* name, float* dst, size_t numel);
+int b2g_bdq_replay_add(b2g_bdq* h, const float* obs, const float* act_idx, const float* rew, const float* next_obs,
+                       const float* done, int64_t n);
+int64_t b2g_bdq_replay_size(const b2g_bdq* h);
+int b2g_bdq_set_norm_stats(b2g_bdq* h, const double* obs_mean, const double* obs_var, double ret_var, double clip_obs,
+                           double clip_rew, double eps, int norm_obs, int norm_reward);
+/* n_steps x { uniform sample -> forward (online s, online s', target s') -> double-Q TD loss -> backward -> Adam ->
+ * hard target copy every target_update_freq updates } */
+int b2g_bdq_step(b2g_bdq* h, int n_steps, float lr, b2g_bdq_metrics* out);
+/* parity entry point: caller-supplied batch (+ optional importance weights); td_out (may be NULL): [batch, n_branches] */
+int b2g_bdq_step_explicit(b2g_bdq* h, const float* obs, const float* act_idx, const float* rew, const float* next_obs,
+                          const float* done, const float* weights, float lr, int apply_update, b2g_bdq_metrics* out,
+                          float* td_out);
+/* greedy branch indices argmax_n Q_d(s, n) of the online network for n observations */
+int b2g_bdq_act(b2g_bdq* h, const float* obs, int n, int32_t* act_idx_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -127,6 +127,20 @@ def test_golden_step_vector_is_reproducible():
     assert abs(res["grad_norm_values"] - float(gold["grad_norm_values"])) <= 1e-4 * float(gold["grad_norm_values"])
 
 
+def test_bdq_param_inventory_matches_shipped_zips():
+    from oracle import bdq_ref as Q
+    man = json.load(open(os.path.join(GOLD, "zip_manifest.json")))
+    for key, cfg in (("bdq_8pads", Q.BDQConfig(100, 3, 8, (64, 64), 32, 32)), ("bdq_33big", Q.BDQConfig(100, 3, 33, (512, 256), 128, 128))):
+        specs = dict(Q.all_specs(cfg))
+        z = man[key]["shapes"]
+        assert set(specs) == set(z), set(specs) ^ set(z)
+        for n, shp in specs.items():
+            assert list(shp) == z[n], (key, n)
+        assert sum(int(np.prod(s)) for s in specs.values()) == man[key]["n_floats"]
+    d = man["bdq_8pads"]["data"]
+    assert d["double_q"] is True and d["target_network_update_freq"] == 1000 and d["num_actions_pad"] == 8 and d["batch_size"] == 64
+
+
 # ------------------------------------------------------------------ C ABI
 def test_shared_library_exports_every_declared_symbol():
     hdr = open(os.path.join(ROOT, "include", "b200grasp.h")).read()
@@ -271,10 +285,14 @@ dist.barrier(); dist.destroy_process_group(); print("ok", rank)
 
 
 def test_world_size_2_gloo_host_path(tmp_path):
+    import socket
     script = tmp_path / "w.py"
     script.write_text(_WORKER % ROOT)
+    with socket.socket() as sk:                 # a free port (a fixed one can sit in TIME_WAIT between runs)
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-                        "--master-port", "29733", str(script)], capture_output=True, text=True, timeout=300,
+                        "--master-port", str(port), str(script)], capture_output=True, text=True, timeout=300,
                        env=dict(os.environ, OMP_NUM_THREADS="2"))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "ok 0" in r.stdout and "ok 1" in r.stdout
