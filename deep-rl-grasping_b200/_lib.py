@@ -23,7 +23,19 @@ SYMBOLS = [
     "b2g_bdq_create", "b2g_bdq_destroy", "b2g_bdq_param_count", "b2g_bdq_param_info", "b2g_bdq_get_param", "b2g_bdq_set_param",
     "b2g_bdq_get_grad", "b2g_bdq_replay_add", "b2g_bdq_replay_size", "b2g_bdq_set_norm_stats", "b2g_bdq_step",
     "b2g_bdq_step_explicit", "b2g_bdq_act",
+    "b2g_encoder_create", "b2g_encoder_destroy", "b2g_encoder_n_layers", "b2g_encoder_layer_shape", "b2g_encoder_set_weights",
+    "b2g_encoder_encode",
 ]
+
+ENC_MAX_LAYERS = 8
+
+
+class EncoderCfg(C.Structure):
+    _fields_ = [
+        ("height", C.c_int32), ("width", C.c_int32), ("channels", C.c_int32), ("n_layers", C.c_int32),
+        ("filters", C.c_int32 * ENC_MAX_LAYERS), ("kernel", C.c_int32 * ENC_MAX_LAYERS), ("strides", C.c_int32 * ENC_MAX_LAYERS),
+        ("encoding_dim", C.c_int32), ("alpha", C.c_float), ("max_batch", C.c_int32), ("device", C.c_int32),
+    ]
 
 
 class BdqCfg(C.Structure):
@@ -117,6 +129,12 @@ def load():
     lib.b2g_bdq_step.argtypes = [vp, C.c_int, C.c_float, C.POINTER(BdqMetrics)]
     lib.b2g_bdq_step_explicit.argtypes = [vp, fp, fp, fp, fp, fp, fp, C.c_float, C.c_int, C.POINTER(BdqMetrics), fp]
     lib.b2g_bdq_act.argtypes = [vp, fp, C.c_int, C.POINTER(C.c_int32)]
+    lib.b2g_encoder_create.argtypes = [C.POINTER(EncoderCfg), C.POINTER(vp)]
+    lib.b2g_encoder_destroy.argtypes = [vp]
+    lib.b2g_encoder_n_layers.argtypes = [vp]
+    lib.b2g_encoder_layer_shape.argtypes = [vp, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    lib.b2g_encoder_set_weights.argtypes = [vp, C.c_int, fp, C.c_size_t, fp, C.c_size_t]
+    lib.b2g_encoder_encode.argtypes = [vp, fp, C.c_int, fp]
     _lib = lib
     return lib
 

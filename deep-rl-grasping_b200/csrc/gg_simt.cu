@@ -42,6 +42,7 @@ __global__ void __launch_bounds__(256) gg_simt_kernel(const GemmDesc* __restrict
   const int r_end = min(d.R, r_begin + chunk);
   const bool a_rvec = d.flags & GG_A_RVEC, b_rvec = d.flags & GG_B_RVEC;
   const bool do_colsum = (d.flags & GG_COLSUM) && tm == 0;
+  const bool a_scalar = d.flags & GG_A_SCALAR;
   const float* __restrict__ A = d.A;
   const float* __restrict__ Bp = d.B;
 
@@ -89,7 +90,7 @@ __global__ void __launch_bounds__(256) gg_simt_kernel(const GemmDesc* __restrict
       const int r = rk + a_r;
       ra = make_float4(0, 0, 0, 0);
       if (a_ok[0] && r < r_end) {
-        if (r + 3 < r_end) {
+        if (r + 3 < r_end && !a_scalar) {
           ra = ld4(A + a_off[0] + d.aR[r]);
         } else {
           float v[4] = {0, 0, 0, 0};
@@ -205,6 +206,10 @@ __global__ void __launch_bounds__(256) gg_simt_kernel(const GemmDesc* __restrict
         co[j] = cm + cn;
         if (d.flags & GG_EPI_BIAS_RELU) v[j] = fmaxf(v[j] + d.bias[n], 0.f);
         if (d.flags & GG_EPI_BIAS) v[j] += d.bias[n];
+        if (d.flags & GG_EPI_BIAS_LRELU) {
+          v[j] += d.bias[n];
+          v[j] = v[j] > 0.f ? v[j] : d.alpha * v[j];
+        }
         if (d.flags & GG_EPI_MASK) {
           const int kn = d.kN ? d.kN[n] : cn;
           v[j] = d.mask[km + kn] > 0.f ? v[j] : 0.f;

@@ -45,3 +45,16 @@ def make_eps(n: int, n_act: int = 5, seed: int = DATA_SEED + 1) -> np.ndarray:
 
 def make_indices(n_batch: int, n_slots: int, seed: int = DATA_SEED + 2) -> np.ndarray:
     return np.random.default_rng(seed).integers(0, n_slots, n_batch).astype(np.int64)
+
+
+def make_depth_scenes(n: int, seed: int = 0, size: int = 64) -> np.ndarray:
+    """Depth-like synthetic frames [n, size, size, 1] float32 for the perception encoder: background filtered to 0
+    (as sensor.py:207-213 zeroes plane/robot/table/tray pixels), 1-4 box-shaped objects at 0.15-0.5 m."""
+    rng = np.random.default_rng(seed)
+    imgs = np.zeros((n, size, size, 1), np.float32)
+    for i in range(n):
+        for _ in range(int(rng.integers(1, 5))):
+            y, x = rng.integers(5, size - 14, 2)
+            h, w = rng.integers(5, 14, 2)
+            imgs[i, y:y + h, x:x + w, 0] = rng.uniform(0.15, 0.5)
+    return imgs

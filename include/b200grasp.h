@@ -182,6 +182,36 @@ int b2g_bdq_step_explicit(b2g_bdq* h, const float* obs, const float* act_idx, co
 /* greedy branch indices argmax_n Q_d(s, n) of the online network for n observations */
 int b2g_bdq_act(b2g_bdq* h, const float* obs, int n, int32_t* act_idx_out);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Row a12: auto-encoder ENCODER forward (perception for the `encoded depth` observation).
+ * Replaces SimpleAutoEncoder.encode  (/root/reference/manipulation_main/gripperEnv/encoders.py:59-61; graph :87-108)
+ * called per env step from EncodedDepthImgSensor.get_state (manipulation_main/gripperEnv/sensor.py:218-222).
+ * Layer spec = config.yaml `network` (filters / kernel_size / strides, padding 'same'), LeakyReLU(alpha) after every
+ * conv and after Dense(encoding_dim).  Weights are the Keras arrays from model.h5: conv kernels [k,k,in,out], dense
+ * kernel [flat,out] (flatten order H,W,C), biases [out].
+ * ------------------------------------------------------------------------------------------------------------ */
+#define B2G_ENC_MAX_LAYERS 8
+typedef struct b2g_encoder b2g_encoder;
+typedef struct b2g_encoder_cfg {
+  int32_t height, width, channels;      /* Input(shape=(64, 64, 1)) in the reference */
+  int32_t n_layers;                     /* conv layers */
+  int32_t filters[B2G_ENC_MAX_LAYERS];
+  int32_t kernel[B2G_ENC_MAX_LAYERS];
+  int32_t strides[B2G_ENC_MAX_LAYERS];
+  int32_t encoding_dim;
+  float alpha;                          /* LeakyReLU slope, config.get('alpha', 0.1) */
+  int32_t max_batch;
+  int32_t device;
+} b2g_encoder_cfg;
+int b2g_encoder_create(const b2g_encoder_cfg* cfg, b2g_encoder** out);
+int b2g_encoder_destroy(b2g_encoder* h);
+int b2g_encoder_n_layers(const b2g_encoder* h);                      /* conv layers + 1 (dense) */
+int b2g_encoder_layer_shape(const b2g_encoder* h, int layer, int64_t* kernel_numel, int64_t* bias_numel);
+int b2g_encoder_set_weights(b2g_encoder* h, int layer, const float* kernel, size_t kernel_numel, const float* bias,
+                            size_t bias_numel);
+/* imgs: host [n, height, width, channels] fp32 -> out: host [n, encoding_dim]; B2G_ESTATE until every layer is loaded */
+int b2g_encoder_encode(b2g_encoder* h, const float* imgs, int n, float* out);
+
 #ifdef __cplusplus
 }
 #endif

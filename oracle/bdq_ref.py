@@ -130,8 +130,8 @@ def bdq_step(params: Dict[str, np.ndarray], opt, batch: Dict[str, np.ndarray], l
         v = (ADAM_B2 * opt["v"].get(n, 0.0) + (1 - ADAM_B2) * grads[n] ** 2).astype(np_dt)
         new_opt["m"][n], new_opt["v"][n] = m, v
         new_p[n] = (new_p[n] - lr_t * m / (np.sqrt(v) + np_dt(ADAM_EPS))).astype(np_dt)
-    out = dict(loss=float(loss), q_sa=q_sa.detach().numpy(), y=y.numpy(), td=td.detach().numpy(), a_star=a_star.numpy(),
-               priorities=td.detach().abs().sum(1).numpy(), mean_q=float(q_sa.mean()),
+    out = dict(loss=float(loss.detach()), q_sa=q_sa.detach().numpy(), y=y.numpy(), td=td.detach().numpy(), a_star=a_star.numpy(),
+               priorities=td.detach().abs().sum(1).numpy(), mean_q=float(q_sa.detach().mean()),
                grad_norm=float(np.sqrt(sum(float((g.astype(np.float64) ** 2).sum()) for g in grads.values()))))
     return out, grads, new_p, new_opt
 

@@ -280,7 +280,7 @@ flat /= world
 ref = np.concatenate([g_full[n].reshape(-1) for n in g_full])
 assert np.abs(flat.numpy() - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max()), np.abs(flat.numpy() - ref).max()
 assert dist_utils.weak_scaling_value(100.0, world) == 200.0
-dist.barrier(); dist.destroy_process_group(); print("ok", rank)
+dist.barrier(); dist.destroy_process_group(); print("ok " + str(rank), flush=True)
 '''
 
 
