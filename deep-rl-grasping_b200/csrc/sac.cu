@@ -159,6 +159,9 @@ struct b2g_sac {
   void* nccl_comm = nullptr;
   void* nccl_comm2 = nullptr;          // second communicator: early all-reduce on the side stream
   cudaStream_t side = nullptr;
+  cudaStream_t aux = nullptr;              // leaf work off the critical chain (zeroing, weight planes, leaf wgrads, bias sums)
+  cudaEvent_t ev_aux[6]{};
+  bool fork_leaves = false;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool overlap_ar = false;
   int ar_sms = 16;
@@ -836,14 +839,27 @@ int issue_step(b2g_sac* h, bool sampled, bool apply, bool want_per_sample, Prof*
   pa.counters = h->counters; pa.step_consts = h->step_consts; pa.lr = h->d_lr; pa.metrics = h->metrics;
   pa.indices = h->indices; pa.eps = h->eps; pa.B = h->B; pa.A = h->A; pa.replay_size = nullptr;  /* device counter [5] */
   pa.seed = h->cfg.seed + 0x9E3779B97F4A7C15ull * (unsigned long long)h->cfg.rank; pa.gen = sampled ? 1 : 0; pa.apply = apply ? 1 : 0;
+  // Leaf work runs on a second stream (parallel branches once captured in the step graph): zeroing the gradient
+  // arena and refreshing the BF16 weight planes overlap prep + gather; heads_wgrad and the bias column sums overlap
+  // the dgrad chain.  Profiling (per-launch events) keeps everything serial on one stream.
+  const bool fork = h->fork_leaves && !(prof && prof->on);
+  cudaStream_t ax = fork ? h->aux : s;
+  if (fork) {
+    CK(cudaEventRecord(h->ev_aux[0], s));
+    CK(cudaStreamWaitEvent(ax, h->ev_aux[0], 0));
+    CK(cudaMemsetAsync(h->G, 0, (size_t)(h->n_train + MET_COUNT) * sizeof(float), ax)); ++n;
+    if (h->use_planes) { planes_launch(h->d_jobs, h->n_jobs, h->job_tiles, ax); ++n; }
+    CK(cudaEventRecord(h->ev_aux[1], ax));
+  }
   prep_launch(pa, s); ++n; mark("prep");
   gather_launch(make_gather(h, sampled, true), s); ++n; mark("gather_normalize");
   if (h->record_after_gather) CK(cudaEventRecord(h->record_after_gather, s));   // staged batch consumed
-  CK(cudaMemsetAsync(h->G, 0, (size_t)(h->n_train + MET_COUNT) * sizeof(float), s)); ++n; mark("zero_grads");
+  if (fork) CK(cudaStreamWaitEvent(s, h->ev_aux[1], 0));
+  else { CK(cudaMemsetAsync(h->G, 0, (size_t)(h->n_train + MET_COUNT) * sizeof(float), s)); ++n; mark("zero_grads"); }
   int x3 = h->cfg.precision == B2G_PREC_BF16X3 ? 1 : 0;
   if (const char* dbg = getenv("B2G_TC_DEBUG")) x3 |= atoi(dbg) << 8;   // kernel bring-up toggles (gg_tc.cu)
   int sm_reserve = 0;     // SMs left free for a concurrently running collective (persistent GEMM grids are 1 CTA / SM)
-  auto run_group = [&](GemmGroup& g) -> int {
+  auto run_group = [&](GemmGroup& g, cudaStream_t s) -> int {
     const char* trn = getenv("B2G_TC_TRACE");
     const bool trace = prof && prof->on && trn && g.name == trn && g.tc;
     if (trace) {
@@ -866,7 +882,7 @@ int issue_step(b2g_sac* h, bool sampled, bool apply, bool want_per_sample, Prof*
     }
     return 0;
   };
-  for (auto& g : h->fwd_groups) if (int rc = run_group(g)) return rc;
+  for (auto& g : h->fwd_groups) if (int rc = run_group(g, s)) return rc;
   tail_launch(make_tail(h, want_per_sample), s); ++n; mark("heads_tail");
   const bool planes_bias = h->wgrad_planes && h->cfg.precision != B2G_PREC_FP32_SIMT;
   // index of the last backward group that touches cnn_fc1 / the heads: everything up to it produces the gradients of
@@ -882,9 +898,23 @@ int issue_step(b2g_sac* h, bool sampled, bool apply, bool want_per_sample, Prof*
     return 0;
   };
   for (size_t i = 0; i < h->bwd_groups.size(); ++i) {
-    if (int rc = run_group(h->bwd_groups[i])) return rc;
+    const bool leaf = fork && h->bwd_groups[i].name == "heads_wgrad";
+    if (fork && planes_bias && i + 1 == h->bwd_groups.size()) {
+      // every gradient map the conv bias sums read exists once the next-to-last group (conv2_bwd) is issued:
+      // the sums overlap conv1_wgrad
+      CK(cudaEventRecord(h->ev_aux[4], s)); CK(cudaStreamWaitEvent(ax, h->ev_aux[4], 0));
+      colsum_launch(h->d_colsum, h->n_colsum, h->colsum_ctas, ax); ++n;
+    }
+    if (leaf) {           // consumes only what the tail wrote; nothing downstream but the optimiser reads its output
+      CK(cudaEventRecord(h->ev_aux[2], s));
+      CK(cudaStreamWaitEvent(ax, h->ev_aux[2], 0));
+    }
+    if (int rc = run_group(h->bwd_groups[i], leaf ? ax : s)) return rc;
     if ((int)i == last_fc1) {
-      if (planes_bias && h->n_colsum_early) { colsum_launch(h->d_colsum_early, h->n_colsum_early, h->colsum_early_ctas, s); ++n; mark("bias_grads_fc1"); }
+      if (planes_bias && h->n_colsum_early) {
+        if (fork) { CK(cudaEventRecord(h->ev_aux[3], s)); CK(cudaStreamWaitEvent(ax, h->ev_aux[3], 0)); }
+        colsum_launch(h->d_colsum_early, h->n_colsum_early, h->colsum_early_ctas, ax); ++n; mark("bias_grads_fc1");
+      }
       if (overlap) {
         // early all-reduce on the side stream / second communicator, overlapping the conv backward
         CK(cudaMemcpyAsync(h->G + h->n_train, h->metrics, MET_GN_PI * sizeof(float), cudaMemcpyDeviceToDevice, s)); ++n;
@@ -900,7 +930,8 @@ int issue_step(b2g_sac* h, bool sampled, bool apply, bool want_per_sample, Prof*
       }
     }
   }
-  if (planes_bias) { colsum_launch(h->d_colsum, h->n_colsum, h->colsum_ctas, s); ++n; mark("bias_grads"); }
+  if (planes_bias && !fork) { colsum_launch(h->d_colsum, h->n_colsum, h->colsum_ctas, s); ++n; mark("bias_grads"); }
+  if (fork) { CK(cudaEventRecord(h->ev_aux[5], ax)); CK(cudaStreamWaitEvent(s, h->ev_aux[5], 0)); }
   if (h->cfg.nranks > 1) {
     if (overlap) {
       // late all-reduce: the conv gradients of both blocks (0.29 MB each), then join the early one
@@ -925,7 +956,10 @@ int issue_step(b2g_sac* h, bool sampled, bool apply, bool want_per_sample, Prof*
   oa.step_consts = h->step_consts; oa.tau = h->cfg.tau; oa.grad_scale = 1.0f / (float)h->cfg.nranks;
   oa.metrics = h->metrics; oa.apply = apply ? 1 : 0;
   optim_launch(oa, s); ++n; mark("adam_polyak");
-  if (h->use_planes && apply) { planes_launch(h->d_jobs, h->n_jobs, h->job_tiles, s); ++n; mark("weight_planes"); }
+  if (h->use_planes && apply) {
+    // with fork: refreshed on the aux branch at the head of the next step (the API entry points mark them stale)
+    if (!fork) { planes_launch(h->d_jobs, h->n_jobs, h->job_tiles, s); ++n; mark("weight_planes"); }
+  }
   CK(cudaGetLastError());
   if (n_launch) *n_launch = n;
   return 0;
@@ -933,7 +967,11 @@ int issue_step(b2g_sac* h, bool sampled, bool apply, bool want_per_sample, Prof*
 
 // BF16 planes of the CNN weights follow every optimiser step inside the step itself; after a host upload
 // (b2g_set_param) they are refreshed here, outside any graph.
-void refresh_planes(b2g_sac* h) {
+void refresh_planes(b2g_sac* h, bool for_step = false) {
+  if (for_step && h->fork_leaves) {     // the step refreshes the planes itself and leaves them one update behind
+    h->planes_dirty = true;
+    return;
+  }
   if (h->use_planes && h->planes_dirty) {
     planes_launch(h->d_jobs, h->n_jobs, h->job_tiles, h->stream);
     h->planes_dirty = false;
@@ -1016,6 +1054,8 @@ int b2g_sac_destroy(b2g_sac* h) {
   if (h->nccl_comm2 && g_nccl.CommDestroy) g_nccl.CommDestroy(h->nccl_comm2);
   if (h->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->nccl_comm);
   if (h->side) cudaStreamDestroy(h->side);
+  if (h->aux) { cudaStreamSynchronize(h->aux); cudaStreamDestroy(h->aux); }
+  for (auto& e : h->ev_aux) if (e) cudaEventDestroy(e);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   for (void* q : h->allocs) cudaFree(q);
@@ -1145,6 +1185,15 @@ int b2g_sac_create(const b2g_sac_cfg* cfg, b2g_sac** out) {
       return bail(fail(B2G_ECUDA, "pipelined-path resources"));
   }
   if (cudaStreamCreateWithFlags(&h->cstream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(B2G_ECUDA, "copy stream"));
+  {   // leaf branch of the step (B2G_FORK=0 keeps the step on one stream)
+    const char* fk = getenv("B2G_FORK");
+    if (!(fk && atoi(fk) == 0)) {
+      if (cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(B2G_ECUDA, "aux stream"));
+      for (auto& e : h->ev_aux)
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return bail(fail(B2G_ECUDA, "aux events"));
+      h->fork_leaves = true;
+    }
+  }
   // identity normalisation until b2g_set_norm_stats is called
   {
     std::vector<double> ones(h->E, 1.0);
@@ -1311,7 +1360,7 @@ int b2g_sac_step_async(b2g_sac* h, int n_steps, float lr) {
   if (h->r_size < 1) return fail(B2G_ESTATE, "replay buffer is empty");
   CK(cudaSetDevice(h->cfg.device));
   if (int rc = set_lr(h, lr)) return rc;
-  refresh_planes(h);
+  refresh_planes(h, true);
   if (h->use_graph) if (int rc = ensure_graph(h)) return rc;
   CK(cudaEventRecord(h->ev0, h->stream));
   for (int i = 0; i < n_steps; ++i) {
@@ -1335,7 +1384,7 @@ int b2g_sac_step_explicit(b2g_sac* h, const float* obs, const float* act, const 
   CK(cudaSetDevice(h->cfg.device));
   if (int rc = set_lr(h, lr)) return rc;
   const size_t B = h->B, E = h->E, A = h->A;
-  refresh_planes(h);
+  refresh_planes(h, true);
   CK(cudaEventRecord(h->ev0, h->stream));
   CK(cudaMemcpyAsync(h->s_obs, obs, B * E * sizeof(float), cudaMemcpyDefault, h->stream));
   CK(cudaMemcpyAsync(h->s_next, next_obs, B * E * sizeof(float), cudaMemcpyDefault, h->stream));
@@ -1358,7 +1407,7 @@ int b2g_sac_step_host_pipelined(b2g_sac* h, const float* obs, const float* act, 
   if (!h || !obs || !act || !rew || !next_obs || !done || !eps) return fail(B2G_EINVAL, "NULL argument");
   CK(cudaSetDevice(h->cfg.device));
   if (int rc = set_lr(h, lr)) return rc;
-  refresh_planes(h);
+  refresh_planes(h, true);
   const size_t B = h->B, E = h->E, A = h->A;
   const long long k = h->pipe_k++;
   const int j = (int)(k & 1);
