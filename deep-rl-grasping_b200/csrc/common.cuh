@@ -158,6 +158,7 @@ struct OptimArgs {
   float grad_scale;                                  // 1/nranks after a sum all-reduce
   float* metrics;                                    // MET_GN_* accumulators
   int apply;                                         // 0 = only grad norms
+  long long* bump_counter;                           // rng step counter advanced once per step (nullptr: prep did it)
 };
 void optim_launch(const OptimArgs& a, cudaStream_t s);
 
@@ -182,6 +183,8 @@ struct PrepArgs {          // 1-CTA kernel at the head of every step
   int* indices; float* eps;// generated when gen != 0
   int B, A; const long long* replay_size;   // nullptr -> counters[5]
   unsigned long long seed; int gen; int apply;
+  int defer_bump;          // 1: the rng step counter [4] is advanced by the optimiser kernel at the end of the step
+  int skip_indices;        // 1: the gather kernel draws the replay slots itself (same Philox stream)
 };
 void prep_launch(const PrepArgs& a, cudaStream_t s);
 
@@ -199,7 +202,33 @@ struct GatherArgs {
   uint16_t* x_obs_hi; uint16_t* x_obs_lo; uint16_t* x_next_hi; uint16_t* x_next_lo;   // optional BF16 planes of x
   float* F_pi; float* F_v; float* F_t; int FS; int feat_col; // feature rows: direct feature -> col feat_col; MLP: whole obs -> cols 0..
   float* rew_out; float* done_out; int n_act;
+  // in-kernel slot draw (indices == nullptr && rng_counters != nullptr): Philox stream 0 of prep_kernel, same values
+  const long long* rng_counters;   // [4] = rng step, [5] = replay size
+  unsigned long long seed;
+  int* indices_out;                // optional record of the drawn slots
 };
 void gather_launch(const GatherArgs& a, cudaStream_t s);
+
+// Philox4x32-10 (counter-based RNG shared by prep_kernel and the in-kernel replay slot draw)
+#ifdef __CUDACC__
+__device__ __forceinline__ void philox_round(uint4& c, uint2& k) {
+  const unsigned hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+  const unsigned hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+  c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+  k.x += 0x9E3779B9u; k.y += 0xBB67AE85u;
+}
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) philox_round(c, k);
+  return c;
+}
+// replay slot of sample b at rng step `step`: element (b & 3) of block b >> 2 of stream 0, scaled to [0, rsz)
+__device__ __forceinline__ int philox_slot(unsigned long long seed, unsigned long long step, int b, unsigned long long rsz) {
+  const uint4 r = philox4x32_10(make_uint4((unsigned)step, (unsigned)(step >> 32), (unsigned)(b >> 2), 0u),
+                                make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
+  const unsigned v = (b & 3) == 0 ? r.x : (b & 3) == 1 ? r.y : (b & 3) == 2 ? r.z : r.w;
+  return (int)(((unsigned long long)v * rsz) >> 32);
+}
+#endif
 
 }  // namespace b2g

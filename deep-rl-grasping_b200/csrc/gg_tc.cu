@@ -137,6 +137,11 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ float4 ldg4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+// Descriptor fields live in the kernel-parameter constant bank behind a run-time problem index; left alone the
+// compiler re-reads them with register-indexed LDCs at every use inside the copy / store loops (hundreds of dependent
+// constant loads per tile).  pin() makes a value opaque so that it stays in a register for the whole tile.
+template <class T> __device__ __forceinline__ T* pin(T* p) { asm volatile("" : "+l"(p)); return p; }
+__device__ __forceinline__ int pin(int v) { asm volatile("" : "+r"(v)); return v; }
 
 struct TileInfo {
   int p, m0, n0, tm, r_begin, r_end, nchunks, un;
@@ -146,18 +151,23 @@ __device__ __forceinline__ TileInfo tile_info(const DescPack& pk, int tile) {
   while (p + 1 < pk.n && tile >= pk.d[p + 1].tile_start) ++p;
   const GemmDesc& d = pk.d[p];
   int t = tile - d.tile_start;
-  const int per = d.tiles_m * d.tiles_n;
-  const int split = t / per;
-  t -= split * per;
+  // run-time integer divisions only where they are needed: most problems have one column block and no split-R
+  const int splitR = d.splitR, tiles_n = d.tiles_n, R = d.R;
+  int split = 0;
+  if (splitR > 1) {
+    const int per = d.tiles_m * tiles_n;
+    split = t / per;
+    t -= split * per;
+  }
   TileInfo ti;
   ti.p = p;
-  ti.tm = t / d.tiles_n;
-  const int tn = t - ti.tm * d.tiles_n;
+  ti.tm = tiles_n == 1 ? t : t / tiles_n;
+  const int tn = t - ti.tm * tiles_n;
   ti.m0 = ti.tm * TM;
   ti.n0 = tn * TN;
-  const int chunk_r = (((d.R + d.splitR - 1) / d.splitR) + TK - 1) / TK * TK;
+  const int chunk_r = ((splitR > 1 ? (R + splitR - 1) / splitR : R) + TK - 1) / TK * TK;
   ti.r_begin = split * chunk_r;
-  ti.r_end = min(d.R, ti.r_begin + chunk_r);
+  ti.r_end = min(R, ti.r_begin + chunk_r);
   ti.nchunks = ti.r_end > ti.r_begin ? (ti.r_end - ti.r_begin + TK - 1) / TK : 0;
   ti.un = min(TN, ((d.N - ti.n0) + 15) / 16 * 16);   // UMMA N for this tile (multiple of 16)
   return ti;
@@ -238,15 +248,26 @@ __global__ void __launch_bounds__(Roles<planes>::NTHREADS, 1) gg_tc_kernel(const
     };
     TState cur = fetch(blockIdx.x);
     int tcount = 0;
+    int pin_p = -1, pflags = 0;
+    const uint16_t* pA_hi = nullptr; const uint16_t* pA_lo = nullptr; const uint16_t* pB_hi = nullptr; const uint16_t* pB_lo = nullptr;
+    const int* tabA = nullptr; const int* tabB_k = nullptr; const int* tabB_mn = nullptr;
     for (int tile = blockIdx.x; tile < pk.total_tiles; tile += gridDim.x, ++tcount) {
       if (pk.trace && blockIdx.x == 0 && tid == 0 && tcount < 64) pk.trace[tcount * 8 + 0] = clock64();
       const TState nxt = fetch(tile + gridDim.x);
       const TileInfo ti = cur.ti;
-      if (ti.nchunks > 0 && (pk.d[ti.p].flags & GG_MN_MAJOR)) {
+      if (ti.p != pin_p) {
+        const GemmDesc& dd = pk.d[ti.p];
+        pflags = pin(dd.flags);
+        pA_hi = pin(dd.A_hi); pA_lo = pin(dd.A_lo); pB_hi = pin(dd.B_hi); pB_lo = pin(dd.B_lo);
+        tabA = pin(dd.aR); tabB_mn = pin(dd.bR); tabB_k = pin(dd.bR_p ? dd.bR_p : dd.bR);
+        pin_p = ti.p;
+      }
+      if (ti.nchunks > 0 && (pflags & GG_MN_MAJOR)) {
         // ---- wgrad: D[k, n] = sum_m act[m -> k] * dZ[m, n]; both operands are contiguous along their M / N
         // index for a fixed reduction index m, so tiles are MN-major: row (r = m) x 16-byte groups along k / n.
         const GemmDesc& d = pk.d[ti.p];
-        const bool align4 = d.flags & GG_A_ALIGN4;
+        const bool align4 = pflags & GG_A_ALIGN4;
+        const int* const tabB = tabB_mn;
         const int c = tid & 7;                         // 16-byte group; reduction rows (tid >> 3) and (tid >> 3) + 32
         // column-side offsets of this thread's groups (A: k groups c and c + 8; B: n group c) are tile constants
         const int kg0 = ti.m0 + 8 * c, kg1 = ti.m0 + 8 * (c + 8), ng = ti.n0 + 8 * c;
@@ -262,8 +283,8 @@ __global__ void __launch_bounds__(Roles<planes>::NTHREADS, 1) gg_tc_kernel(const
           for (int u = 0; u < 2; ++u) {
             const int r = ti.r_begin + ch * TK + q + 32 * u;
             r_ok[u] = r < ti.r_end;
-            ar[u] = r_ok[u] ? d.aR[r] : 0;
-            br[u] = r_ok[u] ? d.bR[r] : 0;
+            ar[u] = r_ok[u] ? tabA[r] : 0;
+            br[u] = r_ok[u] ? tabB[r] : 0;
           }
           if (gc >= STAGES) mbar_wait(smem_u32(&bar_empty[s]), ((gc / STAGES) - 1) & 1);
 #pragma unroll
@@ -275,27 +296,25 @@ __global__ void __launch_bounds__(Roles<planes>::NTHREADS, 1) gg_tc_kernel(const
             const int nb0 = (r_ok[u] && k0_ok) ? 16 : 0, nb1 = (r_ok[u] && k1_ok) ? 16 : 0, nbb = (r_ok[u] && n_ok) ? 16 : 0;
             const size_t e0 = (size_t)(ar[u] + ka0), e1 = (size_t)(ar[u] + ka1), eb = (size_t)(br[u] + nb_);
             if (!align4) {
-              cp_async16(sA_hi + oA0, d.A_hi + e0, nb0);
-              cp_async16(sA_hi + oA1, d.A_hi + e1, nb1);
-              if (x3) { cp_async16(sA_lo + oA0, d.A_lo + e0, nb0); cp_async16(sA_lo + oA1, d.A_lo + e1, nb1); }
+              cp_async16(sA_hi + oA0, pA_hi + e0, nb0);
+              cp_async16(sA_hi + oA1, pA_hi + e1, nb1);
+              if (x3) { cp_async16(sA_lo + oA0, pA_lo + e0, nb0); cp_async16(sA_lo + oA1, pA_lo + e1, nb1); }
             } else {
-              cp_async8(sA_hi + oA0, d.A_hi + e0, nb0 / 2); cp_async8(sA_hi + oA0 + 8, d.A_hi + e0 + 4, nb0 / 2);
-              cp_async8(sA_hi + oA1, d.A_hi + e1, nb1 / 2); cp_async8(sA_hi + oA1 + 8, d.A_hi + e1 + 4, nb1 / 2);
+              cp_async8(sA_hi + oA0, pA_hi + e0, nb0 / 2); cp_async8(sA_hi + oA0 + 8, pA_hi + e0 + 4, nb0 / 2);
+              cp_async8(sA_hi + oA1, pA_hi + e1, nb1 / 2); cp_async8(sA_hi + oA1 + 8, pA_hi + e1 + 4, nb1 / 2);
               if (x3) {
-                cp_async8(sA_lo + oA0, d.A_lo + e0, nb0 / 2); cp_async8(sA_lo + oA0 + 8, d.A_lo + e0 + 4, nb0 / 2);
-                cp_async8(sA_lo + oA1, d.A_lo + e1, nb1 / 2); cp_async8(sA_lo + oA1 + 8, d.A_lo + e1 + 4, nb1 / 2);
+                cp_async8(sA_lo + oA0, pA_lo + e0, nb0 / 2); cp_async8(sA_lo + oA0 + 8, pA_lo + e0 + 4, nb0 / 2);
+                cp_async8(sA_lo + oA1, pA_lo + e1, nb1 / 2); cp_async8(sA_lo + oA1 + 8, pA_lo + e1 + 4, nb1 / 2);
               }
             }
-            cp_async16(sB_hi + oB, d.B_hi + eb, nbb);
-            if (x3) cp_async16(sB_lo + oB, d.B_lo + eb, nbb);
+            cp_async16(sB_hi + oB, pB_hi + eb, nbb);
+            if (x3) cp_async16(sB_lo + oB, pB_lo + eb, nbb);
           }
           cp_async_arrive_noinc(smem_u32(&bar_full[s]));
         }
       } else if (ti.nchunks > 0) {
-        const GemmDesc& d = pk.d[ti.p];
-        const bool align4 = d.flags & GG_A_ALIGN4;
-        const int* __restrict__ tabA = d.aR;
-        const int* __restrict__ tabB = d.bR_p ? d.bR_p : d.bR;
+        const bool align4 = pflags & GG_A_ALIGN4;
+        const int* const tabB = tabB_k;
         int ta = cur.ta, tb = cur.tb;
         for (int ch = 0; ch < ti.nchunks; ++ch, ++gc) {
           const int s = gc % STAGES;
@@ -310,14 +329,14 @@ __global__ void __launch_bounds__(Roles<planes>::NTHREADS, 1) gg_tc_kernel(const
             const int nb = cur.a_ok[i] ? nbytes : 0;
             const size_t e = (size_t)(cur.a_off[i] + ta);
             if (!align4) {
-              cp_async16(sA_hi + o, d.A_hi + e, nb);
-              if (x3) cp_async16(sA_lo + o, d.A_lo + e, nb);
+              cp_async16(sA_hi + o, pA_hi + e, nb);
+              if (x3) cp_async16(sA_lo + o, pA_lo + e, nb);
             } else {
-              cp_async8(sA_hi + o, d.A_hi + e, min(nb, 8));
-              cp_async8(sA_hi + o + 8, d.A_hi + e + 4, max(nb - 8, 0));
+              cp_async8(sA_hi + o, pA_hi + e, min(nb, 8));
+              cp_async8(sA_hi + o + 8, pA_hi + e + 4, max(nb - 8, 0));
               if (x3) {
-                cp_async8(sA_lo + o, d.A_lo + e, min(nb, 8));
-                cp_async8(sA_lo + o + 8, d.A_lo + e + 4, max(nb - 8, 0));
+                cp_async8(sA_lo + o, pA_lo + e, min(nb, 8));
+                cp_async8(sA_lo + o + 8, pA_lo + e + 4, max(nb - 8, 0));
               }
             }
           }
@@ -326,8 +345,8 @@ __global__ void __launch_bounds__(Roles<planes>::NTHREADS, 1) gg_tc_kernel(const
             const uint32_t o = sw128(q + 32 * i, c8);
             const int nb = cur.b_ok[i] ? nbytes : 0;
             const size_t e = (size_t)(cur.b_off[i] + tb);
-            cp_async16(sB_hi + o, d.B_hi + e, nb);
-            if (x3) cp_async16(sB_lo + o, d.B_lo + e, nb);
+            cp_async16(sB_hi + o, pB_hi + e, nb);
+            if (x3) cp_async16(sB_lo + o, pB_lo + e, nb);
           }
           cp_async_arrive_noinc(smem_u32(&bar_full[s]));
           if (ch + 1 < ti.nchunks) { ta = tabA[r0 + TK]; tb = tabB[r0 + TK]; }
@@ -352,8 +371,8 @@ __global__ void __launch_bounds__(Roles<planes>::NTHREADS, 1) gg_tc_kernel(const
       const TileInfo ti = tile_info(pk, tile);
       if (ti.nchunks == 0) continue;
       const GemmDesc& d = pk.d[ti.p];
-      const float* __restrict__ A = d.A;
-      const float* __restrict__ Bp = d.B;
+      const float* __restrict__ A = pin(d.A);
+      const float* __restrict__ Bp = pin(d.B);
       const bool do_colsum = (d.flags & GG_COLSUM) && ti.tm == 0 && !b_rvec;
       int a_off[4], b_off[4];
       bool a_ok[4], b_ok[4];
@@ -371,8 +390,8 @@ __global__ void __launch_bounds__(Roles<planes>::NTHREADS, 1) gg_tc_kernel(const
       // r-offset table entries of the thread's 8 r values: loaded one chunk ahead so that the operand
       // loads of a chunk are a single batch of independent LDG.128 (one round trip).
       // r-contiguous operands need entries 0 and 4 only; block (m-/n-contiguous) operands need all 8.
-      const int* __restrict__ tabA = d.aR;
-      const int* __restrict__ tabB = d.bR;
+      const int* __restrict__ tabA = pin(d.aR);
+      const int* __restrict__ tabB = pin(d.bR);
       const bool blk_is_B = !a_rvec && !a_thread;           // wgrad: this thread gathers the B operand
       const int* __restrict__ tabBlk = a_rvec ? tabB : (blk_is_B ? tabB : tabA);
       int t2a[2] = {0, 0}, t2b[2] = {0, 0};                 // r-contiguous A / B
@@ -572,9 +591,9 @@ __global__ void __launch_bounds__(Roles<planes>::NTHREADS, 1) gg_tc_kernel(const
     // contiguous and the output offset is 16-byte aligned.
     const int ew = warp - (MMA_WARP + 1);          // epilogue warp index
     const int lq = warp & 3;                       // TMEM lane quarter this warp may access
-    const int col0 = (ew >> 2) * EPI_COLS;         // first accumulator column of this warp
     const int et = tid - (MMA_WARP + 1) * 32;      // 0..NEPI-1
-    constexpr int LPR = EPI_COLS / 4, RPI = 32 / LPR;
+    int pinned_p = -1, dflags = 0, dN = 0;
+    float* dC = nullptr; uint16_t* dChi = nullptr; uint16_t* dClo = nullptr; const float* dmask = nullptr;
     const uint32_t stg = ring + STAGES * STAGE_BYTES + (uint32_t)ew * (32 * EPI_COLS * 4);
     uint32_t it = 0;
     int staged_p = -1, staged_n0 = -1;             // which (problem, column block) the staged tables belong to
@@ -615,12 +634,22 @@ __global__ void __launch_bounds__(Roles<planes>::NTHREADS, 1) gg_tc_kernel(const
         asm volatile("bar.sync 2, %0;" ::"n"(NEPI));
         staged_p = ti.p; staged_n0 = ti.n0;
       }
+      if (ti.p != pinned_p) {      // register copies of everything the store loops need from the descriptor
+        dflags = pin(d.flags); dN = pin(d.N);
+        dC = pin(d.C); dChi = pin(d.C_hi); dClo = pin(d.C_lo); dmask = pin(d.mask);
+        pinned_p = ti.p;
+      }
+      // column split between the two warps of a TMEM lane quarter (8 epilogue warps, planes mode): 32 + 32 columns,
+      // or 16 + 16 when the tile is at most 32 wide (conv1 fwd / wgrad, conv2 dgrad) so that no warp idles
+      const int ecols = (NEPI == 256 && ti.un <= 32) ? 16 : EPI_COLS;
+      const int col0 = (ew >> 2) * ecols;            // first accumulator column of this warp
+      const int lpr_log = ecols == 16 ? 2 : (EPI_COLS == 64 ? 4 : 3), LPR = 1 << lpr_log, RPI = 32 >> lpr_log;
       const bool tr = pk.trace && blockIdx.x == 0 && ew == 0 && lane == 0 && it < 64;
       mbar_wait(smem_u32(&bar_acc_full[buf]), (it >> 1) & 1);
       tc_fence_after();
       if (tr) pk.trace[it * 8 + 4] = clock64();
-      const bool fastp = (d.flags & GG_CN_AFFINE4) && (ti.n0 + ti.un <= d.N);
-      const int ncols_w = max(0, min(EPI_COLS, ti.un - col0));     // warp-uniform, multiple of 16
+      const bool fastp = (dflags & GG_CN_AFFINE4) && (ti.n0 + ti.un <= dN);
+      const int ncols_w = max(0, min(ecols, ti.un - col0));        // warp-uniform, multiple of 16
 #pragma unroll 1
       for (int cb = col0; cb < col0 + ncols_w; cb += 16) {
         uint32_t v[16];
@@ -638,7 +667,7 @@ __global__ void __launch_bounds__(Roles<planes>::NTHREADS, 1) gg_tc_kernel(const
           for (int g = 0; g < 4; ++g) {
             float4 o = make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2]),
                                    __uint_as_float(v[4 * g + 3]));
-            if (d.flags & GG_EPI_BIAS_RELU) {
+            if (dflags & GG_EPI_BIAS_RELU) {
               const float4 bb = *reinterpret_cast<const float4*>(&s_bias[cb + 4 * g]);
               o.x = fmaxf(o.x + bb.x, 0.f); o.y = fmaxf(o.y + bb.y, 0.f); o.z = fmaxf(o.z + bb.z, 0.f); o.w = fmaxf(o.w + bb.w, 0.f);
             }
@@ -651,17 +680,17 @@ __global__ void __launch_bounds__(Roles<planes>::NTHREADS, 1) gg_tc_kernel(const
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int n = nb0 + j;
-            if (n >= d.N) break;
+            if (n >= dN) break;
             float o = __uint_as_float(v[j]);
             const int cnj = s_cn[cb + j];
-            if (d.flags & GG_EPI_BIAS_RELU) o = fmaxf(o + s_bias[cb + j], 0.f);
-            if (d.flags & GG_EPI_MASK) o = d.mask[km + s_kn[cb + j]] > 0.f ? o : 0.f;
-            if (d.flags & GG_EPI_ATOMIC) atomicAdd(d.C + cm + cnj, o);
-            else d.C[cm + cnj] = o;
-            if (d.C_hi) {
+            if (dflags & GG_EPI_BIAS_RELU) o = fmaxf(o + s_bias[cb + j], 0.f);
+            if (dflags & GG_EPI_MASK) o = dmask[km + s_kn[cb + j]] > 0.f ? o : 0.f;
+            if (dflags & GG_EPI_ATOMIC) atomicAdd(dC + cm + cnj, o);
+            else dC[cm + cnj] = o;
+            if (dChi) {
               const __nv_bfloat16 h = __float2bfloat16_rn(o);
-              d.C_hi[cm + cnj] = __bfloat16_as_ushort(h);
-              d.C_lo[cm + cnj] = __bfloat16_as_ushort(__float2bfloat16_rn(o - __bfloat162float(h)));
+              dChi[cm + cnj] = __bfloat16_as_ushort(h);
+              dClo[cm + cnj] = __bfloat16_as_ushort(__float2bfloat16_rn(o - __bfloat162float(h)));
             }
           }
         }
@@ -671,7 +700,7 @@ __global__ void __launch_bounds__(Roles<planes>::NTHREADS, 1) gg_tc_kernel(const
       if (tr) pk.trace[it * 8 + 5] = clock64();
       if (fastp && !dbg_nostore && ncols_w > 0) {
         __syncwarp();
-        const int c = lane % LPR, sub = lane / LPR;
+        const int c = lane & (LPR - 1), sub = lane >> lpr_log;
         const bool act = c < (ncols_w >> 2);
         const int cn = act ? s_cn[col0 + 4 * c] : 0, kn = act ? s_kn[col0 + 4 * c] : 0;
 #pragma unroll 1
@@ -692,7 +721,7 @@ __global__ void __launch_bounds__(Roles<planes>::NTHREADS, 1) gg_tc_kernel(const
             if (okr[u]) {
               const uint32_t a = stg + (uint32_t)row * (EPI_COLS * 4) + (uint32_t)((c ^ (row & 7)) << 4);
               asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(o[u].x), "=f"(o[u].y), "=f"(o[u].z), "=f"(o[u].w) : "r"(a));
-              if (d.flags & GG_EPI_MASK) mk[u] = ldg4(d.mask + km_r + kn);
+              if (dflags & GG_EPI_MASK) mk[u] = ldg4(dmask + km_r + kn);
             }
           }
 #pragma unroll
@@ -701,18 +730,18 @@ __global__ void __launch_bounds__(Roles<planes>::NTHREADS, 1) gg_tc_kernel(const
             float4 v4 = o[u];
             v4.x = mk[u].x > 0.f ? v4.x : 0.f; v4.y = mk[u].y > 0.f ? v4.y : 0.f;
             v4.z = mk[u].z > 0.f ? v4.z : 0.f; v4.w = mk[u].w > 0.f ? v4.w : 0.f;
-            if (d.flags & GG_EPI_ATOMIC) {
-              float* cp = d.C + cmr[u] + cn;
+            if (dflags & GG_EPI_ATOMIC) {
+              float* cp = dC + cmr[u] + cn;
               atomicAdd(cp + 0, v4.x); atomicAdd(cp + 1, v4.y); atomicAdd(cp + 2, v4.z); atomicAdd(cp + 3, v4.w);
             } else {
-              *reinterpret_cast<float4*>(d.C + cmr[u] + cn) = v4;
+              *reinterpret_cast<float4*>(dC + cmr[u] + cn) = v4;
             }
-            if (d.C_hi) {
+            if (dChi) {
               const float x[8] = {v4.x, v4.y, v4.z, v4.w, 0.f, 0.f, 0.f, 0.f};
               uint4 hi, lo;
               split8(x, hi, lo);
-              *reinterpret_cast<uint2*>(d.C_hi + cmr[u] + cn) = make_uint2(hi.x, hi.y);
-              *reinterpret_cast<uint2*>(d.C_lo + cmr[u] + cn) = make_uint2(lo.x, lo.y);
+              *reinterpret_cast<uint2*>(dChi + cmr[u] + cn) = make_uint2(hi.x, hi.y);
+              *reinterpret_cast<uint2*>(dClo + cmr[u] + cn) = make_uint2(lo.x, lo.y);
             }
           }
         }

@@ -17,17 +17,6 @@
 namespace b2g {
 namespace {
 
-__device__ __forceinline__ void philox_round(uint4& c, uint2& k) {
-  const unsigned hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
-  const unsigned hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
-  c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
-  k.x += 0x9E3779B9u; k.y += 0xBB67AE85u;
-}
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
-#pragma unroll
-  for (int i = 0; i < 10; ++i) philox_round(c, k);
-  return c;
-}
 __device__ __forceinline__ float u01(unsigned x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
 
 __global__ void prep_kernel(PrepArgs a) {
@@ -43,7 +32,7 @@ __global__ void prep_kernel(PrepArgs a) {
       }
       a.counters[3] += 1;
     }
-    if (a.gen) a.counters[4] += 1;
+    if (a.gen && !a.defer_bump) a.counters[4] += 1;
   }
   if (tid < MET_COUNT) a.metrics[tid] = 0.f;
   __syncthreads();
@@ -52,7 +41,7 @@ __global__ void prep_kernel(PrepArgs a) {
   const uint2 key = make_uint2((unsigned)a.seed, (unsigned)(a.seed >> 32));
   // stream 0: replay indices; stream 1: policy noise
   const unsigned long long rsz = (unsigned long long)(a.replay_size ? a.replay_size[0] : a.counters[5]);
-  for (int i = tid; i < (a.B + 3) / 4; i += blockDim.x) {
+  for (int i = tid; i < (a.skip_indices ? 0 : (a.B + 3) / 4); i += blockDim.x) {
     const uint4 r = philox4x32_10(make_uint4((unsigned)step, (unsigned)(step >> 32), (unsigned)i, 0u), key);
     const unsigned v[4] = {r.x, r.y, r.z, r.w};
     for (int j = 0; j < 4; ++j) {
@@ -120,6 +109,7 @@ __global__ void __launch_bounds__(256) optim_kernel(OptimArgs a) {
     for (int w = 0; w < 8; ++w) v += red[threadIdx.x][w];
     atomicAdd(a.metrics + MET_GN_PI + threadIdx.x, v);
   }
+  if (a.bump_counter && blockIdx.x == 0 && threadIdx.x == 0) *a.bump_counter += 1;
 }
 
 // weights -> BF16 hi/lo planes; 32x32 smem-tiled transpose for the [N,R] copy (both sides coalesced)

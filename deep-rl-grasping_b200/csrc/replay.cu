@@ -18,7 +18,12 @@ __global__ void __launch_bounds__(256) gather_kernel(GatherArgs g) {
   const int which = blockIdx.z;               // 0 = obs, 1 = next_obs
   const bool cnn = g.H > 0;
   const int E = cnn ? g.H * g.W * g.Cfull : g.W;
-  const long long slot = g.indices ? (long long)g.indices[b] : (long long)b;
+  long long slot = b;
+  if (g.indices) slot = g.indices[b];
+  else if (g.rng_counters) {
+    slot = philox_slot(g.seed, (unsigned long long)g.rng_counters[4], b, (unsigned long long)g.rng_counters[5]);
+    if (g.indices_out && which == 0 && blockIdx.x == 0 && threadIdx.x == 0) g.indices_out[b] = (int)slot;
+  }
   const float* __restrict__ src = (which ? g.next_obs : g.obs) + (size_t)slot * E;
   const int cimg = g.Cfull - 1;
   const double ret_istd = g.normc[0], clip_obs = g.normc[1], clip_rew = g.normc[2];

@@ -160,7 +160,7 @@ struct b2g_sac {
   void* nccl_comm2 = nullptr;          // second communicator: early all-reduce on the side stream
   cudaStream_t side = nullptr;
   cudaStream_t aux = nullptr;              // leaf work off the critical chain (zeroing, weight planes, leaf wgrads, bias sums)
-  cudaEvent_t ev_aux[6]{};
+  cudaEvent_t ev_aux[7]{};
   bool fork_leaves = false;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool overlap_ar = false;
@@ -844,15 +844,24 @@ int issue_step(b2g_sac* h, bool sampled, bool apply, bool want_per_sample, Prof*
   // the dgrad chain.  Profiling (per-launch events) keeps everything serial on one stream.
   const bool fork = h->fork_leaves && !(prof && prof->on);
   cudaStream_t ax = fork ? h->aux : s;
+  GatherArgs ga = make_gather(h, sampled, true);
   if (fork) {
+    // aux branch: weight planes (needed by conv1_fwd), then the bookkeeping kernel (Adam step sizes, policy noise,
+    // metric accumulators) and the gradient zeroing (needed from the tail on).  The gather draws its replay slots
+    // in-kernel from the same Philox stream, so the critical chain starts with the gather itself.
+    pa.defer_bump = 1; pa.skip_indices = 1;
+    if (sampled) { ga.indices = nullptr; ga.rng_counters = h->counters; ga.seed = pa.seed; ga.indices_out = h->indices; }
     CK(cudaEventRecord(h->ev_aux[0], s));
     CK(cudaStreamWaitEvent(ax, h->ev_aux[0], 0));
-    CK(cudaMemsetAsync(h->G, 0, (size_t)(h->n_train + MET_COUNT) * sizeof(float), ax)); ++n;
     if (h->use_planes) { planes_launch(h->d_jobs, h->n_jobs, h->job_tiles, ax); ++n; }
     CK(cudaEventRecord(h->ev_aux[1], ax));
+    prep_launch(pa, ax); ++n;
+    CK(cudaMemsetAsync(h->G, 0, (size_t)(h->n_train + MET_COUNT) * sizeof(float), ax)); ++n;
+    CK(cudaEventRecord(h->ev_aux[6], ax));
+  } else {
+    prep_launch(pa, s); ++n; mark("prep");
   }
-  prep_launch(pa, s); ++n; mark("prep");
-  gather_launch(make_gather(h, sampled, true), s); ++n; mark("gather_normalize");
+  gather_launch(ga, s); ++n; mark("gather_normalize");
   if (h->record_after_gather) CK(cudaEventRecord(h->record_after_gather, s));   // staged batch consumed
   if (fork) CK(cudaStreamWaitEvent(s, h->ev_aux[1], 0));
   else { CK(cudaMemsetAsync(h->G, 0, (size_t)(h->n_train + MET_COUNT) * sizeof(float), s)); ++n; mark("zero_grads"); }
@@ -883,6 +892,7 @@ int issue_step(b2g_sac* h, bool sampled, bool apply, bool want_per_sample, Prof*
     return 0;
   };
   for (auto& g : h->fwd_groups) if (int rc = run_group(g, s)) return rc;
+  if (fork) CK(cudaStreamWaitEvent(s, h->ev_aux[6], 0));
   tail_launch(make_tail(h, want_per_sample), s); ++n; mark("heads_tail");
   const bool planes_bias = h->wgrad_planes && h->cfg.precision != B2G_PREC_FP32_SIMT;
   // index of the last backward group that touches cnn_fc1 / the heads: everything up to it produces the gradients of
@@ -955,6 +965,7 @@ int issue_step(b2g_sac* h, bool sampled, bool apply, bool want_per_sample, Prof*
   oa.n_pi = (int)h->n_pi; oa.n_values = (int)h->n_values; oa.n_ent = (int)h->n_ent; oa.n_target = (int)h->n_target;
   oa.step_consts = h->step_consts; oa.tau = h->cfg.tau; oa.grad_scale = 1.0f / (float)h->cfg.nranks;
   oa.metrics = h->metrics; oa.apply = apply ? 1 : 0;
+  oa.bump_counter = (fork && sampled) ? h->counters + 4 : nullptr;
   optim_launch(oa, s); ++n; mark("adam_polyak");
   if (h->use_planes && apply) {
     // with fork: refreshed on the aux branch at the head of the next step (the API entry points mark them stale)
