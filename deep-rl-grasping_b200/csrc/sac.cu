@@ -162,6 +162,7 @@ struct b2g_sac {
   cudaStream_t aux = nullptr;              // leaf work off the critical chain (zeroing, weight planes, leaf wgrads, bias sums)
   cudaEvent_t ev_aux[7]{};
   bool fork_leaves = false;
+  bool fc0_split = true;                   // split-R heads_fc0 (needs z0 zeroed every step)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool overlap_ar = false;
   int ar_sms = 16;
@@ -659,8 +660,11 @@ int build_groups(b2g_sac* h) {
       const int R = (q == 2 || q == 3) ? fd + A : fd;
       g.host.push_back(mk(h->F[fnet[q]], rowFS, iFS, h->p(hk[q]), kH, i64, h->z0[q], rowH, i64, B, H, R, GG_A_RVEC));
     }
-    h->fwd_groups.push_back(g);
     GemmGroup a = g;
+    // training step: the 516-deep reduction of each head is split over several CTAs (atomic accumulation into the
+    // pre-zeroed z0 block) -- 10 tiles would otherwise each walk 9 r-chunks serially on 10 of the 148 SMs
+    if (h->fc0_split) for (auto& d : g.host) d.flags |= GG_EPI_ATOMIC;
+    h->fwd_groups.push_back(g);
     a.name = "act_heads_fc0";
     a.host.resize(1);
     h->act_groups.push_back(a);
@@ -854,6 +858,7 @@ int issue_step(b2g_sac* h, bool sampled, bool apply, bool want_per_sample, Prof*
     CK(cudaEventRecord(h->ev_aux[0], s));
     CK(cudaStreamWaitEvent(ax, h->ev_aux[0], 0));
     if (h->use_planes) { planes_launch(h->d_jobs, h->n_jobs, h->job_tiles, ax); ++n; }
+    if (h->fc0_split) { CK(cudaMemsetAsync(h->z0[0], 0, (size_t)5 * h->B * h->H * sizeof(float), ax)); ++n; }
     CK(cudaEventRecord(h->ev_aux[1], ax));
     prep_launch(pa, ax); ++n;
     CK(cudaMemsetAsync(h->G, 0, (size_t)(h->n_train + MET_COUNT) * sizeof(float), ax)); ++n;
@@ -864,7 +869,11 @@ int issue_step(b2g_sac* h, bool sampled, bool apply, bool want_per_sample, Prof*
   gather_launch(ga, s); ++n; mark("gather_normalize");
   if (h->record_after_gather) CK(cudaEventRecord(h->record_after_gather, s));   // staged batch consumed
   if (fork) CK(cudaStreamWaitEvent(s, h->ev_aux[1], 0));
-  else { CK(cudaMemsetAsync(h->G, 0, (size_t)(h->n_train + MET_COUNT) * sizeof(float), s)); ++n; mark("zero_grads"); }
+  else {
+    CK(cudaMemsetAsync(h->G, 0, (size_t)(h->n_train + MET_COUNT) * sizeof(float), s)); ++n;
+    if (h->fc0_split) { CK(cudaMemsetAsync(h->z0[0], 0, (size_t)5 * h->B * h->H * sizeof(float), s)); ++n; }
+    mark("zero_grads");
+  }
   int x3 = h->cfg.precision == B2G_PREC_BF16X3 ? 1 : 0;
   if (const char* dbg = getenv("B2G_TC_DEBUG")) x3 |= atoi(dbg) << 8;   // kernel bring-up toggles (gg_tc.cu)
   int sm_reserve = 0;     // SMs left free for a concurrently running collective (persistent GEMM grids are 1 CTA / SM)
@@ -1177,7 +1186,9 @@ int b2g_sac_create(const b2g_sac_cfg* cfg, b2g_sac** out) {
         }
   }
   for (int n = 0; n < 3; ++n) DA(h->F[n], (size_t)B * h->FS);
-  for (int q = 0; q < 5; ++q) DA(h->z0[q], B * h->H);
+  DA(h->z0[0], 5 * B * h->H);                      // one block: zeroed with a single memset per step
+  for (int q = 1; q < 5; ++q) h->z0[q] = h->z0[0] + (size_t)q * B * h->H;
+  { const char* e = getenv("B2G_FC0_SPLIT"); h->fc0_split = !(e && atoi(e) == 0); }
   for (int q = 0; q < 4; ++q) { DA(h->a0[q], B * h->H); DA(h->dz1[q], B * h->H); }
   DA(h->dz0_pi, B * h->H); DA(h->dz0_v3, B * 3 * h->H);
   DA(h->per_sample, 7 * B); DA(h->pi_out, B * h->A); DA(h->eps, B * h->A + 4); DA(h->rew_n, B); DA(h->done_n, B);
