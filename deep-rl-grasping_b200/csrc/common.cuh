@@ -48,6 +48,8 @@ enum GemmFlags : int {
   GG_EPI_BIAS = 1 << 10,  // C = acc + bias[n] (no activation; output layers)
   GG_EPI_SCALE = 1 << 11, // C = acc * alpha (after mask)
   GG_A_SCALAR = 1 << 12,  // fp32 engine, with GG_A_RVEC: no 4-element contiguity along r -> element-wise gather (1-channel convs)
+  GG_A_ROWLANES = 1 << 14, // planes K-major producer: lanes walk 8 consecutive rows of one 16-byte column group (conv1: adjacent
+                           // output pixels overlap in the image, so a warp copy touches 4-8 lines instead of 32)
   GG_EPI_BIAS_LRELU = 1 << 13, // C = leaky_relu(acc + bias[n], slope alpha)   (Keras LeakyReLU; encoder.cu)
   GG_MN_MAJOR = 1 << 9,   // planes mode, wgrad: both operands contiguous along their M / N index -> MN-major UMMA tiles
   GG_CN_AFFINE4 = 1 << 8, // host-verified: cN / kN contiguous inside aligned 4-column groups, outputs 16-byte aligned

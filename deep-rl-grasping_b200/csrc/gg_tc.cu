@@ -219,17 +219,23 @@ __global__ void __launch_bounds__(Roles<planes>::NTHREADS, 1) gg_tc_kernel(const
     uint32_t gc = 0;
     // per-tile gather state, fetched ONE TILE AHEAD so that the row-offset / table round trips of tile i+1
     // overlap the copies of tile i (the ring keeps running across tile boundaries)
-    struct TState { TileInfo ti; int a_off[4]; bool a_ok[4]; int b_off[2]; bool b_ok[2]; int ta, tb; bool valid; };
+    // qa / ca: this thread's A row group and 16-byte column group.  Default: 8 lanes span one row's 128 bytes
+    // (dense rows: one line per row).  GG_A_ROWLANES: 8 lanes span 8 consecutive rows of one column group.
+    struct TState { TileInfo ti; int a_off[4]; bool a_ok[4]; int b_off[2]; bool b_ok[2]; int ta, tb; int qa, ca; bool valid; };
     auto fetch = [&](int tile) {
       TState t;
       t.valid = tile < pk.total_tiles;
       if (!t.valid) return t;
       t.ti = tile_info(pk, tile);
       const GemmDesc& d = pk.d[t.ti.p];
-      if (d.flags & GG_MN_MAJOR) return t;       // MN-major tiles fetch their (few) offsets in place
+      const int dfl = d.flags;
+      if (dfl & GG_MN_MAJOR) return t;           // MN-major tiles fetch their (few) offsets in place
+      const bool rl = dfl & GG_A_ROWLANES;
+      t.qa = rl ? (tid & 7) + 8 * (tid >> 6) : q;
+      t.ca = rl ? (tid >> 3) & 7 : c8;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int m = t.ti.m0 + q + 32 * i;
+        const int m = t.ti.m0 + t.qa + 32 * i;
         t.a_ok[i] = m < d.M;
         t.a_off[i] = t.a_ok[i] ? d.aM[m] : 0;
       }
@@ -241,7 +247,7 @@ __global__ void __launch_bounds__(Roles<planes>::NTHREADS, 1) gg_tc_kernel(const
       }
       t.ta = t.tb = 0;
       if (t.ti.nchunks > 0) {
-        t.ta = d.aR[t.ti.r_begin + c8 * 8];
+        t.ta = d.aR[t.ti.r_begin + t.ca * 8];
         t.tb = (d.bR_p ? d.bR_p : d.bR)[t.ti.r_begin + c8 * 8];
       }
       return t;
@@ -268,7 +274,11 @@ __global__ void __launch_bounds__(Roles<planes>::NTHREADS, 1) gg_tc_kernel(const
         const GemmDesc& d = pk.d[ti.p];
         const bool align4 = pflags & GG_A_ALIGN4;
         const int* const tabB = tabB_mn;
-        const int c = tid & 7;                         // 16-byte group; reduction rows (tid >> 3) and (tid >> 3) + 32
+        // 16-byte group c; reduction rows qq and qq + 32.  GG_A_ROWLANES: 8 lanes walk 8 consecutive reduction rows
+        // (adjacent output pixels: overlapping image patches, contiguous dZ rows) instead of the 8 groups of one row
+        const bool rl = pflags & GG_A_ROWLANES;
+        const int c = rl ? (tid >> 3) & 7 : tid & 7;
+        const int qq = rl ? (tid & 7) + 8 * (tid >> 6) : q;
         // column-side offsets of this thread's groups (A: k groups c and c + 8; B: n group c) are tile constants
         const int kg0 = ti.m0 + 8 * c, kg1 = ti.m0 + 8 * (c + 8), ng = ti.n0 + 8 * c;
         const bool k0_ok = kg0 < d.M, k1_ok = kg1 < d.M, n_ok = ng < d.N;
@@ -281,7 +291,7 @@ __global__ void __launch_bounds__(Roles<planes>::NTHREADS, 1) gg_tc_kernel(const
           bool r_ok[2];
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
-            const int r = ti.r_begin + ch * TK + q + 32 * u;
+            const int r = ti.r_begin + ch * TK + qq + 32 * u;
             r_ok[u] = r < ti.r_end;
             ar[u] = r_ok[u] ? tabA[r] : 0;
             br[u] = r_ok[u] ? tabB[r] : 0;
@@ -289,7 +299,7 @@ __global__ void __launch_bounds__(Roles<planes>::NTHREADS, 1) gg_tc_kernel(const
           if (gc >= STAGES) mbar_wait(smem_u32(&bar_empty[s]), ((gc / STAGES) - 1) & 1);
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
-            const int rr = q + 32 * u;
+            const int rr = qq + 32 * u;
             const int ki = rr >> 3, kk = rr & 7;
             const uint32_t swz = (uint32_t)((c ^ kk) << 4);
             const uint32_t oA0 = (uint32_t)(ki * 2048 + kk * 128) + swz, oA1 = oA0 + 1024, oB = (uint32_t)(ki * 1024 + kk * 128) + swz;
@@ -320,13 +330,13 @@ __global__ void __launch_bounds__(Roles<planes>::NTHREADS, 1) gg_tc_kernel(const
           const int s = gc % STAGES;
           const uint32_t sA_hi = ring + s * STAGE_BYTES, sA_lo = sA_hi + A_BYTES;
           const uint32_t sB_hi = sA_lo + A_BYTES, sB_lo = sB_hi + B_BYTES;
-          const int r0 = ti.r_begin + ch * TK + c8 * 8;
-          const int nbytes = max(0, min(8, ti.r_end - r0)) * 2;
+          const int r0 = ti.r_begin + ch * TK + c8 * 8, r0a = ti.r_begin + ch * TK + cur.ca * 8;
+          const int nbytes = max(0, min(8, ti.r_end - r0)) * 2, nbytes_a = max(0, min(8, ti.r_end - r0a)) * 2;
           if (gc >= STAGES) mbar_wait(smem_u32(&bar_empty[s]), ((gc / STAGES) - 1) & 1);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const uint32_t o = sw128(q + 32 * i, c8);
-            const int nb = cur.a_ok[i] ? nbytes : 0;
+            const uint32_t o = sw128(cur.qa + 32 * i, cur.ca);
+            const int nb = cur.a_ok[i] ? nbytes_a : 0;
             const size_t e = (size_t)(cur.a_off[i] + ta);
             if (!align4) {
               cp_async16(sA_hi + o, pA_hi + e, nb);
@@ -349,7 +359,7 @@ __global__ void __launch_bounds__(Roles<planes>::NTHREADS, 1) gg_tc_kernel(const
             if (x3) cp_async16(sB_lo + o, pB_lo + e, nb);
           }
           cp_async_arrive_noinc(smem_u32(&bar_full[s]));
-          if (ch + 1 < ti.nchunks) { ta = tabA[r0 + TK]; tb = tabB[r0 + TK]; }
+          if (ch + 1 < ti.nchunks) { ta = tabA[r0a + TK]; tb = tabB[r0 + TK]; }
         }
       }
       if (pk.trace && blockIdx.x == 0 && tid == 0 && tcount < 64) pk.trace[tcount * 8 + 1] = clock64();

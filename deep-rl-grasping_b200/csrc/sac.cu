@@ -162,6 +162,7 @@ struct b2g_sac {
   cudaStream_t aux = nullptr;              // leaf work off the critical chain (zeroing, weight planes, leaf wgrads, bias sums)
   cudaEvent_t ev_aux[7]{};
   bool fork_leaves = false;
+  bool a_rowlanes = true;                  // conv1 fwd gather with row-major lane order (B2G_ROWLANES=0 disables)
   bool fc0_split = true;                   // split-R heads_fc0 (needs z0 zeroed every step)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool overlap_ar = false;
@@ -415,7 +416,7 @@ int build_groups(b2g_sac* h) {
         if (h->use_planes) {
           uint16_t* const* ip = l == 0 ? h->xp[n == 2 ? 1 : 0] : (l == 1 ? h->h1p[n] : h->h2p[n]);
           uint16_t* const* op = l == 0 ? h->h1p[n] : (l == 1 ? h->h2p[n] : h->h3p[n]);
-          d.flags |= GG_PLANES | GG_B_RVEC | ((l == 0 && (c.Ci & 1)) ? GG_A_ALIGN4 : 0);
+          d.flags |= GG_PLANES | GG_B_RVEC | ((l == 0 && (c.Ci & 1)) ? GG_A_ALIGN4 : 0) | ((l == 0 && h->a_rowlanes) ? GG_A_ROWLANES : 0);
           d.A_hi = ip[0]; d.A_lo = ip[1];
           d.B_hi = h->wp[n][l][2]; d.B_lo = h->wp[n][l][3];
           d.bR_p = wT_r[l]; d.bN_p = wT_n[l];
@@ -608,7 +609,7 @@ int build_groups(b2g_sac* h) {
                         GG_COLSUM | GG_EPI_ATOMIC, split_for((M + 63) / 64, R, 74));
         w.colsum = h->g(nn(n, "/cnn1/b"));
         if (h->wgrad_planes) {
-          w.flags = (w.flags & ~GG_COLSUM) | GG_PLANES | GG_MN_MAJOR | ((Ci & 1) ? GG_A_ALIGN4 : 0);
+          w.flags = (w.flags & ~GG_COLSUM) | GG_PLANES | GG_MN_MAJOR | ((Ci & 1) ? GG_A_ALIGN4 : 0) | (h->a_rowlanes ? GG_A_ROWLANES : 0);
           w.A_hi = h->xp[0][0]; w.A_lo = h->xp[0][1]; w.B_hi = h->dZ1p[n][0]; w.B_lo = h->dZ1p[n][1];
         }
         g.host.push_back(w);
@@ -1189,6 +1190,7 @@ int b2g_sac_create(const b2g_sac_cfg* cfg, b2g_sac** out) {
   DA(h->z0[0], 5 * B * h->H);                      // one block: zeroed with a single memset per step
   for (int q = 1; q < 5; ++q) h->z0[q] = h->z0[0] + (size_t)q * B * h->H;
   { const char* e = getenv("B2G_FC0_SPLIT"); h->fc0_split = !(e && atoi(e) == 0); }
+  { const char* e = getenv("B2G_ROWLANES"); h->a_rowlanes = !(e && atoi(e) == 0); }
   for (int q = 0; q < 4; ++q) { DA(h->a0[q], B * h->H); DA(h->dz1[q], B * h->H); }
   DA(h->dz0_pi, B * h->H); DA(h->dz0_v3, B * 3 * h->H);
   DA(h->per_sample, 7 * B); DA(h->pi_out, B * h->A); DA(h->eps, B * h->A + 4); DA(h->rew_n, B); DA(h->done_n, B);

@@ -91,6 +91,38 @@ __global__ void __launch_bounds__(WARPS * 32) tail_kernel(TailArgs t) {
       const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&Wk1[w * H * LD + (i >> 6) * LD + (i & 63)]);
       asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(k1s[w] + i) : "memory");
     }
+  // Every small parameter the per-sample chain touches (fc0/fc1 biases, output layers, the action rows of the qf fc0
+  // kernels) is staged too: read from global they are ~30 dependent L2 round trips per sample, and a warp owns exactly
+  // one sample, so those round trips were most of this kernel's duration.
+  float* sp = red + ((MET_COUNT + 1 + 3) & ~3);
+  auto stage = [&](float* dst, const float* src, int n) {
+    for (int i = tid; i < n; i += blockDim.x) {
+      const uint32_t d32 = (uint32_t)__cvta_generic_to_shared(dst + i);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d32), "l"(src + i) : "memory");
+    }
+  };
+  const HeadW* hw[S_NW] = {&t.pi, &t.vf, &t.q1, &t.q2, &t.vt};
+  float* s_b0[S_NW]; float* s_b1[S_NW];
+  for (int w = 0; w < S_NW; ++w) {
+    s_b0[w] = sp + w * 2 * H; s_b1[w] = s_b0[w] + H;
+    stage(s_b0[w], hw[w]->b0, H); stage(s_b1[w], hw[w]->b1, H);
+  }
+  float* s_pi_ko = sp + S_NW * 2 * H;
+  float* s_ksig = s_pi_ko + H * A;
+  float* s_pi_bo = s_ksig + H * A;
+  float* s_bsig = s_pi_bo + A;
+  float* s_vko[4];                                  // vf, q1, q2, vt output layers: ko[64] then bo
+  s_vko[0] = s_bsig + A;
+  for (int w = 1; w < 4; ++w) s_vko[w] = s_vko[w - 1] + H + 1;
+  float* s_q1act = s_vko[3] + H + 1;                // action rows of the qf fc0 kernels [A][64]
+  float* s_q2act = s_q1act + A * H;
+  stage(s_pi_ko, t.pi.ko, H * A); stage(s_ksig, t.ksig, H * A); stage(s_pi_bo, t.pi.bo, A); stage(s_bsig, t.bsig, A);
+  {
+    const HeadW* vh[4] = {&t.vf, &t.q1, &t.q2, &t.vt};
+    for (int w = 0; w < 4; ++w) { stage(s_vko[w], vh[w]->ko, H); stage(s_vko[w] + H, vh[w]->bo, 1); }
+  }
+  stage(s_q1act, t.q1.k0 + (size_t)t.feat_dim * H, A * H);
+  stage(s_q2act, t.q2.k0 + (size_t)t.feat_dim * H, A * H);
   for (int i = tid; i < n_acc + MET_COUNT + 1; i += blockDim.x) acc[i] = 0.f;
   asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
@@ -108,21 +140,31 @@ __global__ void __launch_bounds__(WARPS * 32) tail_kernel(TailArgs t) {
   const float alpha = expf(log_alpha);
 
   for (int b = blockIdx.x * WARPS + warp; b < t.B; b += gridDim.x * WARPS) {
+    // every per-sample global read, issued as one batch
+    const V2 zpi = ld2(t.z0_pi + b * H, lane), zvf = ld2(t.z0_vf + b * H, lane), zvt = ld2(t.z0_vt + b * H, lane);
+    const V2 z0q1 = ld2(t.z0_q1 + b * H, lane), z0q2 = ld2(t.z0_q2 + b * H, lane);
+    const float rew_r = t.rew[b], done_r = t.done[b];
+    float eps_r[AMAX], act_r[AMAX];
+#pragma unroll
+    for (int a = 0; a < AMAX; ++a) {
+      eps_r[a] = a < A ? t.eps[b * A + a] : 0.f;
+      act_r[a] = a < A ? t.act[(size_t)b * t.act_stride + a] : 0.f;
+    }
     // ------------------------------------------------------------------ actor forward
-    const V2 a0_pi = relu2(V2{t.z0_pi[b * H + lane] + t.pi.b0[lane], t.z0_pi[b * H + lane + 32] + t.pi.b0[lane + 32]});
+    const V2 a0_pi = relu2(V2{zpi.lo + s_b0[S_PI][lane], zpi.hi + s_b0[S_PI][lane + 32]});
     st2(t.a0_pi + b * H, lane, a0_pi);
-    const V2 g = relu2(fwd64(Wk1 + S_PI * H * LD, t.pi.b1, a0_pi, lane));
+    const V2 g = relu2(fwd64(Wk1 + S_PI * H * LD, s_b1[S_PI], a0_pi, lane));
     float mu[AMAX], ls_raw[AMAX], ls[AMAX], sd[AMAX], pi[AMAX], tt[AMAX], epsn[AMAX], actv[AMAX];
     float logp = 0.f, ent = 0.f;
 #pragma unroll
     for (int a = 0; a < AMAX; ++a) {
       if (a < A) {
-        mu[a] = warp_sum(g.lo * t.pi.ko[lane * A + a] + g.hi * t.pi.ko[(lane + 32) * A + a]) + t.pi.bo[a];
-        ls_raw[a] = warp_sum(g.lo * t.ksig[lane * A + a] + g.hi * t.ksig[(lane + 32) * A + a]) + t.bsig[a];
+        mu[a] = warp_sum(g.lo * s_pi_ko[lane * A + a] + g.hi * s_pi_ko[(lane + 32) * A + a]) + s_pi_bo[a];
+        ls_raw[a] = warp_sum(g.lo * s_ksig[lane * A + a] + g.hi * s_ksig[(lane + 32) * A + a]) + s_bsig[a];
         ls[a] = fminf(fmaxf(ls_raw[a], LS_MIN), LS_MAX);
         sd[a] = expf(ls[a]);
-        epsn[a] = t.eps[b * A + a];
-        actv[a] = t.act[(size_t)b * t.act_stride + a];
+        epsn[a] = eps_r[a];
+        actv[a] = act_r[a];
         const float u = mu[a] + epsn[a] * sd[a];
         tt[a] = (u - mu[a]) / (sd[a] + EPSF);
         pi[a] = tanhf(u);
@@ -131,39 +173,38 @@ __global__ void __launch_bounds__(WARPS * 32) tail_kernel(TailArgs t) {
       }
     }
     // ------------------------------------------------------------------ critics forward
-    const V2 a0_vf = relu2(V2{t.z0_vf[b * H + lane] + t.vf.b0[lane], t.z0_vf[b * H + lane + 32] + t.vf.b0[lane + 32]});
-    const V2 a1_vf = relu2(fwd64(Wk1 + S_VF * H * LD, t.vf.b1, a0_vf, lane));
-    const float v = out1(t.vf.ko, t.vf.bo, a1_vf, lane);
-    const V2 a0_vt = relu2(V2{t.z0_vt[b * H + lane] + t.vt.b0[lane], t.z0_vt[b * H + lane + 32] + t.vt.b0[lane + 32]});
-    const V2 a1_vt = relu2(fwd64(Wk1 + S_VT * H * LD, t.vt.b1, a0_vt, lane));
-    const float v_targ = out1(t.vt.ko, t.vt.bo, a1_vt, lane);
+    const V2 a0_vf = relu2(V2{zvf.lo + s_b0[S_VF][lane], zvf.hi + s_b0[S_VF][lane + 32]});
+    const V2 a1_vf = relu2(fwd64(Wk1 + S_VF * H * LD, s_b1[S_VF], a0_vf, lane));
+    const float v = out1(s_vko[0], s_vko[0] + H, a1_vf, lane);
+    const V2 a0_vt = relu2(V2{zvt.lo + s_b0[S_VT][lane], zvt.hi + s_b0[S_VT][lane + 32]});
+    const V2 a1_vt = relu2(fwd64(Wk1 + S_VT * H * LD, s_b1[S_VT], a0_vt, lane));
+    const float v_targ = out1(s_vko[3], s_vko[3] + H, a1_vt, lane);
 
-    V2 z0q1 = ld2(t.z0_q1 + b * H, lane), z0q2 = ld2(t.z0_q2 + b * H, lane);
     V2 z0q1p = z0q1, z0q2p = z0q2;   // fc0 pre-activation at pi: linear in the action columns
 #pragma unroll
     for (int a = 0; a < AMAX; ++a) {
       if (a < A) {
         const float dlt = pi[a] - actv[a];
-        const float* r1 = t.q1.k0 + (size_t)(t.feat_dim + a) * H;
-        const float* r2 = t.q2.k0 + (size_t)(t.feat_dim + a) * H;
+        const float* r1 = s_q1act + a * H;
+        const float* r2 = s_q2act + a * H;
         z0q1p.lo = fmaf(dlt, r1[lane], z0q1p.lo); z0q1p.hi = fmaf(dlt, r1[lane + 32], z0q1p.hi);
         z0q2p.lo = fmaf(dlt, r2[lane], z0q2p.lo); z0q2p.hi = fmaf(dlt, r2[lane + 32], z0q2p.hi);
       }
     }
-    const V2 b0q1 = ld2(t.q1.b0, lane), b0q2 = ld2(t.q2.b0, lane);
+    const V2 b0q1 = ld2(s_b0[S_Q1], lane), b0q2 = ld2(s_b0[S_Q2], lane);
     const V2 a0_q1 = relu2(V2{z0q1.lo + b0q1.lo, z0q1.hi + b0q1.hi});
     const V2 a0_q2 = relu2(V2{z0q2.lo + b0q2.lo, z0q2.hi + b0q2.hi});
     const V2 a0_q1p = relu2(V2{z0q1p.lo + b0q1.lo, z0q1p.hi + b0q1.hi});
     const V2 a0_q2p = relu2(V2{z0q2p.lo + b0q2.lo, z0q2p.hi + b0q2.hi});
-    const V2 a1_q1 = relu2(fwd64(Wk1 + S_Q1 * H * LD, t.q1.b1, a0_q1, lane));
-    const V2 a1_q2 = relu2(fwd64(Wk1 + S_Q2 * H * LD, t.q2.b1, a0_q2, lane));
-    const V2 a1_q1p = relu2(fwd64(Wk1 + S_Q1 * H * LD, t.q1.b1, a0_q1p, lane));
-    const V2 a1_q2p = relu2(fwd64(Wk1 + S_Q2 * H * LD, t.q2.b1, a0_q2p, lane));
-    const float q1 = out1(t.q1.ko, t.q1.bo, a1_q1, lane), q2 = out1(t.q2.ko, t.q2.bo, a1_q2, lane);
-    const float q1p = out1(t.q1.ko, t.q1.bo, a1_q1p, lane), q2p = out1(t.q2.ko, t.q2.bo, a1_q2p, lane);
+    const V2 a1_q1 = relu2(fwd64(Wk1 + S_Q1 * H * LD, s_b1[S_Q1], a0_q1, lane));
+    const V2 a1_q2 = relu2(fwd64(Wk1 + S_Q2 * H * LD, s_b1[S_Q2], a0_q2, lane));
+    const V2 a1_q1p = relu2(fwd64(Wk1 + S_Q1 * H * LD, s_b1[S_Q1], a0_q1p, lane));
+    const V2 a1_q2p = relu2(fwd64(Wk1 + S_Q2 * H * LD, s_b1[S_Q2], a0_q2p, lane));
+    const float q1 = out1(s_vko[1], s_vko[1] + H, a1_q1, lane), q2 = out1(s_vko[2], s_vko[2] + H, a1_q2, lane);
+    const float q1p = out1(s_vko[1], s_vko[1] + H, a1_q1p, lane), q2p = out1(s_vko[2], s_vko[2] + H, a1_q2p, lane);
 
     // ------------------------------------------------------------------ losses + seeds
-    const float q_backup = t.rew[b] + (1.f - t.done[b]) * t.gamma * v_targ;
+    const float q_backup = rew_r + (1.f - done_r) * t.gamma * v_targ;
     const float v_backup = fminf(q1p, q2p) - alpha * logp;
     const float e1 = q1 - q_backup, e2 = q2 - q_backup, ev = v - v_backup;
     if (lane == 0) {
@@ -192,13 +233,13 @@ __global__ void __launch_bounds__(WARPS * 32) tail_kernel(TailArgs t) {
     }
 
     // ------------------------------------------------------------------ value heads backward
-    auto value_head_bwd = [&](float dout, const HeadW& w, const float* Ws, V2 a0, V2 a1, float* accv, float* dz1_out,
+    auto value_head_bwd = [&](float dout, const float* wko, const float* Ws, V2 a0, V2 a1, float* accv, float* dz1_out,
                               float* dz0_out) {
       // output layer grads
       atomicAdd(&accv[lane], a1.lo * dout);
       atomicAdd(&accv[lane + 32], a1.hi * dout);
       if (lane == 0) atomicAdd(&accv[H], dout);
-      V2 dz1{a1.lo > 0.f ? dout * w.ko[lane] : 0.f, a1.hi > 0.f ? dout * w.ko[lane + 32] : 0.f};
+      V2 dz1{a1.lo > 0.f ? dout * wko[lane] : 0.f, a1.hi > 0.f ? dout * wko[lane + 32] : 0.f};
       st2(dz1_out, lane, dz1);
       V2 da0 = bwd64(Ws, dz1, lane);
       V2 dz0{a0.lo > 0.f ? da0.lo : 0.f, a0.hi > 0.f ? da0.hi : 0.f};
@@ -207,22 +248,22 @@ __global__ void __launch_bounds__(WARPS * 32) tail_kernel(TailArgs t) {
     st2(t.a0_vf + b * H, lane, a0_vf);
     st2(t.a0_q1 + b * H, lane, a0_q1);
     st2(t.a0_q2 + b * H, lane, a0_q2);
-    value_head_bwd(ev * invB, t.vf, Wk1 + S_VF * H * LD, a0_vf, a1_vf, a_vf, t.dz1_vf + b * H, t.dz0_v3 + (size_t)b * 3 * H);
-    value_head_bwd(e1 * invB, t.q1, Wk1 + S_Q1 * H * LD, a0_q1, a1_q1, a_q1, t.dz1_q1 + b * H, t.dz0_v3 + (size_t)b * 3 * H + H);
-    value_head_bwd(e2 * invB, t.q2, Wk1 + S_Q2 * H * LD, a0_q2, a1_q2, a_q2, t.dz1_q2 + b * H, t.dz0_v3 + (size_t)b * 3 * H + 2 * H);
+    value_head_bwd(ev * invB, s_vko[0], Wk1 + S_VF * H * LD, a0_vf, a1_vf, a_vf, t.dz1_vf + b * H, t.dz0_v3 + (size_t)b * 3 * H);
+    value_head_bwd(e1 * invB, s_vko[1], Wk1 + S_Q1 * H * LD, a0_q1, a1_q1, a_q1, t.dz1_q1 + b * H, t.dz0_v3 + (size_t)b * 3 * H + H);
+    value_head_bwd(e2 * invB, s_vko[2], Wk1 + S_Q2 * H * LD, a0_q2, a1_q2, a_q2, t.dz1_q2 + b * H, t.dz0_v3 + (size_t)b * 3 * H + 2 * H);
 
     // ------------------------------------------------------------------ policy backward
     // d(-Q1(s,pi))/d pi through qf1 with its weights held constant
     float dpi[AMAX];
     {
       const float dout = -invB;
-      V2 dz1{a1_q1p.lo > 0.f ? dout * t.q1.ko[lane] : 0.f, a1_q1p.hi > 0.f ? dout * t.q1.ko[lane + 32] : 0.f};
+      V2 dz1{a1_q1p.lo > 0.f ? dout * s_vko[1][lane] : 0.f, a1_q1p.hi > 0.f ? dout * s_vko[1][lane + 32] : 0.f};
       V2 da0 = bwd64(Wk1 + S_Q1 * H * LD, dz1, lane);
       V2 dz0{a0_q1p.lo > 0.f ? da0.lo : 0.f, a0_q1p.hi > 0.f ? da0.hi : 0.f};
 #pragma unroll
       for (int a = 0; a < AMAX; ++a) {
         if (a < A) {
-          const float* r1 = t.q1.k0 + (size_t)(t.feat_dim + a) * H;
+          const float* r1 = s_q1act + a * H;
           dpi[a] = warp_sum(dz0.lo * r1[lane] + dz0.hi * r1[lane + 32]);
         }
       }
@@ -243,8 +284,8 @@ __global__ void __launch_bounds__(WARPS * 32) tail_kernel(TailArgs t) {
         atomicAdd(&a_ksig[lane * A + a], g.lo * dls[a]);
         atomicAdd(&a_ksig[(lane + 32) * A + a], g.hi * dls[a]);
         if (lane == 0) { atomicAdd(&a_bmu[a], dmu[a]); atomicAdd(&a_bsig[a], dls[a]); }
-        dg.lo += dmu[a] * t.pi.ko[lane * A + a] + dls[a] * t.ksig[lane * A + a];
-        dg.hi += dmu[a] * t.pi.ko[(lane + 32) * A + a] + dls[a] * t.ksig[(lane + 32) * A + a];
+        dg.lo += dmu[a] * s_pi_ko[lane * A + a] + dls[a] * s_ksig[lane * A + a];
+        dg.hi += dmu[a] * s_pi_ko[(lane + 32) * A + a] + dls[a] * s_ksig[(lane + 32) * A + a];
       }
     }
     {
@@ -310,7 +351,8 @@ namespace {
 }  // namespace
 
 static size_t tail_smem(int A) {
-  return sizeof(float) * (S_NW * H * LD + 2 * H * A + 2 * A + 3 * (H + 1) + MET_COUNT + 1 + 8);
+  return sizeof(float) * (S_NW * H * LD + 2 * H * A + 2 * A + 3 * (H + 1) + MET_COUNT + 1 + 8 +
+                          /* staged small parameters */ (S_NW * 2 * H + 2 * H * A + 2 * A + 4 * (H + 1) + 2 * A * H + 8));
 }
 
 void tail_launch(const TailArgs& a, cudaStream_t s) {
