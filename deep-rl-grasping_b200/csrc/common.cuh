@@ -88,13 +88,18 @@ struct GemmGroup {          // one grouped launch
   double flops = 0;
   bool tc = false;          // run on the tcgen05 engine
   bool tc_eligible = false; // large dense contraction (convs, cnn_fc1)
+  int* dev_ranges = nullptr; // tcgen05 engine: contiguous tile range per CTA (gg_tc_ranges)
+  int ranges_grid = 0;
 };
 
 // engines (gg_simt.cu / gg_tc.cu)
 void gg_simt_launch(const GemmDesc* dev_descs, int ndesc, int total_tiles, cudaStream_t s);
 constexpr int GG_SIMT_BM = 64, GG_SIMT_BN = 64, GG_SIMT_BK = 16;
 // tcgen05 engine: 128 x 64 output tile, 64-wide r-chunks; x3 != 0 -> BF16 hi/lo split (3 MMAs)
-cudaError_t gg_tc_launch(const GemmDesc* host_descs, int ndesc, int total_tiles, int mode_flags, int x3, int num_sms, cudaStream_t s);
+cudaError_t gg_tc_launch(const GemmDesc* host_descs, int ndesc, int total_tiles, int mode_flags, int x3, int num_sms, cudaStream_t s,
+                         const int* dev_ranges = nullptr, int ranges_grid = 0);
+// host side of the contiguous tile schedule: cost-balanced range boundaries [grid + 1] for a finalized group
+std::vector<int> gg_tc_ranges(const GemmDesc* host_descs, int ndesc, int total_tiles, int grid);
 constexpr int GG_TC_MAX_DESCS = 16;
 int gg_tc_smem_bytes();
 extern long long* g_tc_trace;   // bring-up hook (gg_tc.cu)

@@ -19,6 +19,9 @@
 // TMEM: 2 x (128 lanes x 64 fp32 columns).  Shared memory: 4 x 48 KiB ring.
 #include <cuda_bf16.h>
 
+#include <algorithm>
+#include <vector>
+
 #include "common.cuh"
 
 namespace b2g {
@@ -47,6 +50,7 @@ struct DescPack {
   int n;
   int total_tiles;
   long long* trace;   // bring-up: per-tile clock64 stamps of CTA 0 (nullptr in production)
+  const int* ranges;  // [grid + 1] contiguous, cost-balanced tile range per CTA (nullptr: round-robin over the grid)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -209,6 +213,12 @@ __global__ void __launch_bounds__(Roles<planes>::NTHREADS, 1) gg_tc_kernel(const
   const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
   pdl_trigger();      // the next kernel on the stream may begin its own prologue now
   pdl_wait();         // everything above overlapped the predecessor; its results are visible from here on
+  // Tile schedule.  With host-built ranges every CTA owns a CONTIGUOUS run of tiles whose summed cost (r-chunks + a
+  // fixed per-tile term) is balanced: consecutive tiles then share their problem and column block, so the per-problem
+  // state (pinned descriptor fields, staged column tables and their barrier pair) is refreshed a few times per CTA
+  // instead of once per tile, and neighbouring rows stay in the same SM's L1/L2 slice.
+  int t_begin = blockIdx.x, t_end = pk.total_tiles, t_step = gridDim.x;
+  if (pk.ranges) { t_begin = pk.ranges[blockIdx.x]; t_end = pk.ranges[blockIdx.x + 1]; t_step = 1; }
 
   if (planes && warp < MMA_WARP) {
     // =========================================================================== producers (BF16 planes, cp.async)
@@ -221,10 +231,10 @@ __global__ void __launch_bounds__(Roles<planes>::NTHREADS, 1) gg_tc_kernel(const
     // overlap the copies of tile i (the ring keeps running across tile boundaries)
     // qa / ca: this thread's A row group and 16-byte column group.  Default: 8 lanes span one row's 128 bytes
     // (dense rows: one line per row).  GG_A_ROWLANES: 8 lanes span 8 consecutive rows of one column group.
-    struct TState { TileInfo ti; int a_off[4]; bool a_ok[4]; int b_off[2]; bool b_ok[2]; int ta, tb; int qa, ca; bool valid; };
+    struct TState { TileInfo ti; int a_off[4]; bool a_ok[4]; int b_off[2]; bool b_ok[2]; int ta[4], tb[4]; int qa, ca; bool valid; };
     auto fetch = [&](int tile) {
       TState t;
-      t.valid = tile < pk.total_tiles;
+      t.valid = tile < t_end;
       if (!t.valid) return t;
       t.ti = tile_info(pk, tile);
       const GemmDesc& d = pk.d[t.ti.p];
@@ -245,21 +255,28 @@ __global__ void __launch_bounds__(Roles<planes>::NTHREADS, 1) gg_tc_kernel(const
         t.b_ok[i] = nB < d.N;
         t.b_off[i] = t.b_ok[i] ? (d.bN_p ? d.bN_p : d.bN)[nB] : 0;
       }
-      t.ta = t.tb = 0;
-      if (t.ti.nchunks > 0) {
-        t.ta = d.aR[t.ti.r_begin + t.ca * 8];
-        t.tb = (d.bR_p ? d.bR_p : d.bR)[t.ti.r_begin + c8 * 8];
+      // r-offset table entries of the first four r-chunks (the ring depth): short tiles (dgrad: 4 chunks) never wait
+      // for a table round trip inside the chunk loop; longer ones keep loading four chunks ahead
+      const int* tA = d.aR;
+      const int* tB = d.bR_p ? d.bR_p : d.bR;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        t.ta[k] = t.tb[k] = 0;
+        if (k < t.ti.nchunks) {
+          t.ta[k] = tA[t.ti.r_begin + k * TK + t.ca * 8];
+          t.tb[k] = tB[t.ti.r_begin + k * TK + c8 * 8];
+        }
       }
       return t;
     };
-    TState cur = fetch(blockIdx.x);
+    TState cur = fetch(t_begin);
     int tcount = 0;
     int pin_p = -1, pflags = 0;
     const uint16_t* pA_hi = nullptr; const uint16_t* pA_lo = nullptr; const uint16_t* pB_hi = nullptr; const uint16_t* pB_lo = nullptr;
     const int* tabA = nullptr; const int* tabB_k = nullptr; const int* tabB_mn = nullptr;
-    for (int tile = blockIdx.x; tile < pk.total_tiles; tile += gridDim.x, ++tcount) {
+    for (int tile = t_begin; tile < t_end; tile += t_step, ++tcount) {
       if (pk.trace && blockIdx.x == 0 && tid == 0 && tcount < 64) pk.trace[tcount * 8 + 0] = clock64();
-      const TState nxt = fetch(tile + gridDim.x);
+      const TState nxt = fetch(tile + t_step);
       const TileInfo ti = cur.ti;
       if (ti.p != pin_p) {
         const GemmDesc& dd = pk.d[ti.p];
@@ -325,8 +342,10 @@ __global__ void __launch_bounds__(Roles<planes>::NTHREADS, 1) gg_tc_kernel(const
       } else if (ti.nchunks > 0) {
         const bool align4 = pflags & GG_A_ALIGN4;
         const int* const tabB = tabB_k;
-        int ta = cur.ta, tb = cur.tb;
+        int ta0 = cur.ta[0], ta1 = cur.ta[1], ta2 = cur.ta[2], ta3 = cur.ta[3];
+        int tb0 = cur.tb[0], tb1 = cur.tb[1], tb2 = cur.tb[2], tb3 = cur.tb[3];
         for (int ch = 0; ch < ti.nchunks; ++ch, ++gc) {
+          const int ta = ta0, tb = tb0;
           const int s = gc % STAGES;
           const uint32_t sA_hi = ring + s * STAGE_BYTES, sA_lo = sA_hi + A_BYTES;
           const uint32_t sB_hi = sA_lo + A_BYTES, sB_lo = sB_hi + B_BYTES;
@@ -359,7 +378,8 @@ __global__ void __launch_bounds__(Roles<planes>::NTHREADS, 1) gg_tc_kernel(const
             if (x3) cp_async16(sB_lo + o, pB_lo + e, nb);
           }
           cp_async_arrive_noinc(smem_u32(&bar_full[s]));
-          if (ch + 1 < ti.nchunks) { ta = tabA[r0a + TK]; tb = tabB[r0 + TK]; }
+          ta0 = ta1; ta1 = ta2; ta2 = ta3; tb0 = tb1; tb1 = tb2; tb2 = tb3;
+          if (ch + 4 < ti.nchunks) { ta3 = tabA[r0a + 4 * TK]; tb3 = tabB[r0 + 4 * TK]; }
         }
       }
       if (pk.trace && blockIdx.x == 0 && tid == 0 && tcount < 64) pk.trace[tcount * 8 + 1] = clock64();
@@ -377,7 +397,7 @@ __global__ void __launch_bounds__(Roles<planes>::NTHREADS, 1) gg_tc_kernel(const
     const bool b_thread = b_rvec ? true : (qb >= 0 && qb < TN / 4);
     uint32_t gc = 0;                    // ring chunk counter, continuous across tiles
 
-    for (int tile = blockIdx.x; tile < pk.total_tiles; tile += gridDim.x) {
+    for (int tile = t_begin; tile < t_end; tile += t_step) {
       const TileInfo ti = tile_info(pk, tile);
       if (ti.nchunks == 0) continue;
       const GemmDesc& d = pk.d[ti.p];
@@ -551,7 +571,7 @@ __global__ void __launch_bounds__(Roles<planes>::NTHREADS, 1) gg_tc_kernel(const
     // =========================================================================== MMA issuer
     if (lane == 0) {
       uint32_t gc = 0, it = 0;
-      for (int tile = blockIdx.x; tile < pk.total_tiles; tile += gridDim.x) {
+      for (int tile = t_begin; tile < t_end; tile += t_step) {
         const TileInfo ti = tile_info(pk, tile);
         if (ti.nchunks == 0) continue;
         const uint32_t buf = it & 1;
@@ -607,39 +627,57 @@ __global__ void __launch_bounds__(Roles<planes>::NTHREADS, 1) gg_tc_kernel(const
     const uint32_t stg = ring + STAGES * STAGE_BYTES + (uint32_t)ew * (32 * EPI_COLS * 4);
     uint32_t it = 0;
     int staged_p = -1, staged_n0 = -1;             // which (problem, column block) the staged tables belong to
-    // row-side offsets are fetched one tile ahead (their round trip overlaps the current tile's work)
-    auto row_fetch = [&](int tile, int& cm_o, int& km_o, bool& ok_o) {
-      cm_o = km_o = 0; ok_o = false;
-      if (tile >= pk.total_tiles) return;
-      const TileInfo t2 = tile_info(pk, tile);
-      if (t2.nchunks == 0) return;
-      const GemmDesc& d2 = pk.d[t2.p];
-      const int m2 = t2.m0 + lq * 32 + lane;
-      ok_o = m2 < d2.M;
-      cm_o = ok_o ? d2.cM[m2] : 0;
-      km_o = (ok_o && (d2.flags & GG_EPI_MASK)) ? (d2.kM ? d2.kM[m2] : cm_o) : 0;
+    // Everything a tile's epilogue needs from global memory besides the mask -- tile coordinates, this lane's row
+    // offsets (cM / kM), this thread's column-table entry (cN / kN / bias) -- is fetched ONE TILE AHEAD and only
+    // consumed after the current tile's work, so none of those round trips sits on the per-tile critical path.
+    // No arithmetic touches a freshly loaded value inside prefetch() (a dependent instruction would stall there).
+    struct ENext { TileInfo ti; int cm, km; bool ok, km_same, valid; int t_cn, t_kn; float t_bias; bool kn_same; };
+    auto prefetch = [&](int tile) {
+      ENext e;
+      e.valid = tile < t_end;
+      e.cm = e.km = 0; e.ok = false; e.km_same = true; e.t_cn = e.t_kn = 0; e.t_bias = 0.f; e.kn_same = true;
+      if (!e.valid) return e;
+      e.ti = tile_info(pk, tile);
+      if (e.ti.nchunks == 0) return e;
+      const GemmDesc& d2 = pk.d[e.ti.p];
+      const int fl = d2.flags;
+      const int m2 = e.ti.m0 + lq * 32 + lane;
+      e.ok = m2 < d2.M;
+      if (e.ok) e.cm = d2.cM[m2];
+      const int* kMp = d2.kM;
+      e.km_same = !((fl & GG_EPI_MASK) && kMp);
+      if (e.ok && !e.km_same) e.km = kMp[m2];
+      if (et < TN) {
+        const int n = e.ti.n0 + et;
+        if (n < d2.N) {
+          e.t_cn = d2.cN[n];
+          const int* kNp = d2.kN;
+          e.kn_same = kNp == nullptr;
+          if (kNp) e.t_kn = kNp[n];
+        }
+      } else if (et < 2 * TN) {
+        const int n = e.ti.n0 + et - TN;
+        if ((fl & GG_EPI_BIAS_RELU) && n < d2.N) e.t_bias = d2.bias[n];
+      }
+      return e;
     };
-    int cm_n, km_n; bool ok_n;
-    row_fetch(blockIdx.x, cm_n, km_n, ok_n);
-    for (int tile = blockIdx.x; tile < pk.total_tiles; tile += gridDim.x) {
-      const TileInfo ti = tile_info(pk, tile);
-      const int cm = cm_n, km = km_n;
-      const bool m_ok = ok_n;
-      row_fetch(tile + gridDim.x, cm_n, km_n, ok_n);
+    ENext nxt = prefetch(t_begin);
+    for (int tile = t_begin; tile < t_end; tile += t_step) {
+      const ENext cur = nxt;
+      nxt = prefetch(tile + t_step);
+      const TileInfo ti = cur.ti;
       if (ti.nchunks == 0) continue;
+      const int cm = cur.cm, km = cur.km_same ? cur.cm : cur.km;
+      const bool m_ok = cur.ok;
       const GemmDesc& d = pk.d[ti.p];
       const uint32_t buf = it & 1;
       if (ti.p != staged_p || ti.n0 != staged_n0) {   // block-uniform: every epilogue warp walks the same tiles
         asm volatile("bar.sync 2, %0;" ::"n"(NEPI));  // previous readers of the staged tables are done
         if (et < TN) {
-          const int n = ti.n0 + et;
-          const bool ok = n < d.N;
-          const int cn = ok ? d.cN[n] : 0;
-          s_cn[et] = cn;
-          s_kn[et] = ok ? (d.kN ? d.kN[n] : cn) : 0;
+          s_cn[et] = cur.t_cn;
+          s_kn[et] = cur.kn_same ? cur.t_cn : cur.t_kn;
         } else if (et < 2 * TN) {
-          const int n = ti.n0 + et - TN;
-          s_bias[et - TN] = ((d.flags & GG_EPI_BIAS_RELU) && n < d.N) ? d.bias[n] : 0.f;
+          s_bias[et - TN] = cur.t_bias;
         }
         asm volatile("bar.sync 2, %0;" ::"n"(NEPI));
         staged_p = ti.p; staged_n0 = ti.n0;
@@ -655,11 +693,28 @@ __global__ void __launch_bounds__(Roles<planes>::NTHREADS, 1) gg_tc_kernel(const
       const int col0 = (ew >> 2) * ecols;            // first accumulator column of this warp
       const int lpr_log = ecols == 16 ? 2 : (EPI_COLS == 64 ? 4 : 3), LPR = 1 << lpr_log, RPI = 32 >> lpr_log;
       const bool tr = pk.trace && blockIdx.x == 0 && ew == 0 && lane == 0 && it < 64;
+      const bool fastp = (dflags & GG_CN_AFFINE4) && (ti.n0 + ti.un <= dN);
+      const int ncols_w = max(0, min(ecols, ti.un - col0));        // warp-uniform, multiple of 16
+      // ReLU-mask values of the first store batch: their addresses depend only on the tables, so the loads are issued
+      // before the accumulator is even waited for and have landed by the time phase B needs them
+      float4 mk0[4];
+      const int pc = lane & (LPR - 1), psub = lane >> lpr_log;
+      const bool pact = pc < (ncols_w >> 2);
+      const bool early_mask = planes && fastp && (dflags & GG_EPI_MASK) && ncols_w > 0 && !dbg_nostore;   // (register budget: planes kernel only)
+      {
+        const int kn = (early_mask && pact) ? s_kn[col0 + 4 * pc] : 0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int row = RPI * u + psub;
+          const int km_r = __shfl_sync(0xffffffffu, km, row & 31);
+          const bool ok_r = __shfl_sync(0xffffffffu, (int)m_ok, row & 31) != 0;
+          mk0[u] = make_float4(1, 1, 1, 1);
+          if (early_mask && pact && ok_r && row < 32) mk0[u] = ldg4(dmask + km_r + kn);
+        }
+      }
       mbar_wait(smem_u32(&bar_acc_full[buf]), (it >> 1) & 1);
       tc_fence_after();
       if (tr) pk.trace[it * 8 + 4] = clock64();
-      const bool fastp = (dflags & GG_CN_AFFINE4) && (ti.n0 + ti.un <= dN);
-      const int ncols_w = max(0, min(ecols, ti.un - col0));        // warp-uniform, multiple of 16
 #pragma unroll 1
       for (int cb = col0; cb < col0 + ncols_w; cb += 16) {
         uint32_t v[16];
@@ -731,7 +786,7 @@ __global__ void __launch_bounds__(Roles<planes>::NTHREADS, 1) gg_tc_kernel(const
             if (okr[u]) {
               const uint32_t a = stg + (uint32_t)row * (EPI_COLS * 4) + (uint32_t)((c ^ (row & 7)) << 4);
               asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(o[u].x), "=f"(o[u].y), "=f"(o[u].z), "=f"(o[u].w) : "r"(a));
-              if (dflags & GG_EPI_MASK) mk[u] = ldg4(dmask + km_r + kn);
+              if (dflags & GG_EPI_MASK) mk[u] = (planes && rr0 == 0) ? mk0[u] : ldg4(dmask + km_r + kn);
             }
           }
 #pragma unroll
@@ -784,12 +839,44 @@ cudaError_t launch_mode(const DescPack& pk, int x3, int num_sms, cudaStream_t s)
 
 int gg_tc_smem_bytes() { return SMEM_BYTES; }
 
+// Cost-balanced contiguous tile ranges (mirrors tile_info: tiles of a problem are split-major).  Tile cost = its r-chunk
+// count + a fixed term for the per-tile handshakes and the epilogue.
+std::vector<int> gg_tc_ranges(const GemmDesc* descs, int ndesc, int total_tiles, int grid) {
+  std::vector<float> cost((size_t)total_tiles, 0.f);
+  const float fixed = 3.0f;
+  for (int p = 0; p < ndesc; ++p) {
+    const GemmDesc& d = descs[p];
+    const int per = d.tiles_m * d.tiles_n;
+    const int chunk_r = (((d.R + d.splitR - 1) / d.splitR) + TK - 1) / TK * TK;
+    for (int t = 0; t < d.tile_count; ++t) {
+      const int split = t / per;
+      const int rb = split * chunk_r, re = std::min(d.R, rb + chunk_r);
+      const int nch = re > rb ? (re - rb + TK - 1) / TK : 0;
+      cost[(size_t)d.tile_start + t] = nch > 0 ? nch + fixed : 0.05f;
+    }
+  }
+  double total = 0;
+  for (float c : cost) total += c;
+  std::vector<int> r((size_t)grid + 1, total_tiles);
+  r[0] = 0;
+  double acc = 0;
+  int t = 0;
+  for (int c = 1; c < grid; ++c) {
+    const double target = total * c / grid;
+    // CTA c-1 takes tiles while its share is not exceeded; it gets at least one, and one is left for every later CTA
+    while (t < total_tiles - (grid - c) && (t < r[c - 1] + 1 || acc + 0.5 * cost[t] <= target)) acc += cost[t++];
+    r[c] = t;
+  }
+  r[grid] = total_tiles;
+  return r;
+}
+
 // All problems of one launch share the operand-contiguity mode (flags & (GG_A_RVEC | GG_B_RVEC)).
 // host_descs: the group's descriptors (at most GG_TC_MAX_DESCS), passed as a __grid_constant__ pack.
 long long* g_tc_trace = nullptr;   // set by sac.cu for one traced launch
 
 cudaError_t gg_tc_launch(const GemmDesc* host_descs, int ndesc, int total_tiles, int mode_flags, int x3, int num_sms,
-                         cudaStream_t s) {
+                         cudaStream_t s, const int* dev_ranges, int ranges_grid) {
   if (total_tiles <= 0) return cudaSuccess;
   if (ndesc > GG_TC_MAX_DESCS) return cudaErrorInvalidValue;
   DescPack pk;
@@ -797,6 +884,8 @@ cudaError_t gg_tc_launch(const GemmDesc* host_descs, int ndesc, int total_tiles,
   pk.n = ndesc;
   pk.total_tiles = total_tiles;
   pk.trace = g_tc_trace;
+  const int grid = total_tiles < num_sms ? total_tiles : num_sms;
+  pk.ranges = (dev_ranges && ranges_grid == grid) ? dev_ranges : nullptr;   // built for exactly this grid size
   const bool ar = mode_flags & GG_A_RVEC, br = mode_flags & GG_B_RVEC;
   if (mode_flags & GG_PLANES) return launch_mode<true, true, true>(pk, x3, num_sms, s);
   if (ar && br) return launch_mode<true, true, false>(pk, x3, num_sms, s);

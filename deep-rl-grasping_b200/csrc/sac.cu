@@ -162,6 +162,8 @@ struct b2g_sac {
   cudaStream_t aux = nullptr;              // leaf work off the critical chain (zeroing, weight planes, leaf wgrads, bias sums)
   cudaEvent_t ev_aux[7]{};
   bool fork_leaves = false;
+  bool tc_ranges = false;                  // contiguous cost-balanced tile ranges per CTA: measured SLOWER than round-robin
+                                           // (split-R tiles of one output pile their atomics onto one CTA); B2G_TC_RANGES=1 enables
   bool a_rowlanes = true;                  // conv1 fwd gather with row-major lane order (B2G_ROWLANES=0 disables)
   bool fc0_split = true;                   // split-R heads_fc0 (needs z0 zeroed every step)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -327,6 +329,13 @@ int finalize_group(b2g_sac* h, GemmGroup& g) {
     g.flops += 2.0 * d.M * d.N * d.R;
   }
   g.total_tiles = start;
+  if (g.tc && h->tc_ranges && start > 0) {     // contiguous cost-balanced tile schedule of the tcgen05 engine
+    g.ranges_grid = std::min(start, h->num_sms);
+    const std::vector<int> rg = gg_tc_ranges(g.host.data(), (int)g.host.size(), start, g.ranges_grid);
+    if (int rc = dalloc(h, &g.dev_ranges, rg.size(), false)) return rc;
+    CK(cudaMemcpyAsync(g.dev_ranges, rg.data(), rg.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
   if (int rc = dalloc(h, &g.dev, g.host.size(), false)) return rc;
   CK(cudaMemcpyAsync(g.dev, g.host.data(), g.host.size() * sizeof(GemmDesc), cudaMemcpyHostToDevice, h->stream));
   CK(cudaStreamSynchronize(h->stream));
@@ -886,7 +895,7 @@ int issue_step(b2g_sac* h, bool sampled, bool apply, bool want_per_sample, Prof*
       g_tc_trace = h->dbg_trace;
     }
     struct Reset { ~Reset() { g_tc_trace = nullptr; } } reset_;
-    if (g.tc) CK(gg_tc_launch(g.host.data(), (int)g.host.size(), g.total_tiles, g.host[0].flags, x3, h->num_sms - sm_reserve, s));
+    if (g.tc) CK(gg_tc_launch(g.host.data(), (int)g.host.size(), g.total_tiles, g.host[0].flags, x3, h->num_sms - sm_reserve, s, g.dev_ranges, g.ranges_grid));
     else gg_simt_launch(g.dev, (int)g.host.size(), g.total_tiles, s);
     ++n; mark(g.name.c_str());
     if (trace) {
@@ -1191,6 +1200,7 @@ int b2g_sac_create(const b2g_sac_cfg* cfg, b2g_sac** out) {
   for (int q = 1; q < 5; ++q) h->z0[q] = h->z0[0] + (size_t)q * B * h->H;
   { const char* e = getenv("B2G_FC0_SPLIT"); h->fc0_split = !(e && atoi(e) == 0); }
   { const char* e = getenv("B2G_ROWLANES"); h->a_rowlanes = !(e && atoi(e) == 0); }
+  { const char* e = getenv("B2G_TC_RANGES"); h->tc_ranges = e && atoi(e) != 0; }
   for (int q = 0; q < 4; ++q) { DA(h->a0[q], B * h->H); DA(h->dz1[q], B * h->H); }
   DA(h->dz0_pi, B * h->H); DA(h->dz0_v3, B * 3 * h->H);
   DA(h->per_sample, 7 * B); DA(h->pi_out, B * h->A); DA(h->eps, B * h->A + 4); DA(h->rew_n, B); DA(h->done_n, B);
@@ -1498,7 +1508,7 @@ int b2g_sac_act(b2g_sac* h, const float* obs, int n, int deterministic, float* a
     g.indices = nullptr;
     gather_launch(g, h->stream);
     for (auto& gr : h->act_groups) {
-      if (gr.tc) CK(gg_tc_launch(gr.host.data(), (int)gr.host.size(), gr.total_tiles, gr.host[0].flags, h->cfg.precision == B2G_PREC_BF16X3 ? 1 : 0, h->num_sms, h->stream));
+      if (gr.tc) CK(gg_tc_launch(gr.host.data(), (int)gr.host.size(), gr.total_tiles, gr.host[0].flags, h->cfg.precision == B2G_PREC_BF16X3 ? 1 : 0, h->num_sms, h->stream, gr.dev_ranges, gr.ranges_grid));
       else gg_simt_launch(gr.dev, (int)gr.host.size(), gr.total_tiles, h->stream);
     }
     b2g::act_launch(make_tail(h, false), chunk, deterministic, h->pi_out, h->stream);
