@@ -166,6 +166,8 @@ struct OptimArgs {
   float* metrics;                                    // MET_GN_* accumulators
   int apply;                                         // 0 = only grad norms
   long long* bump_counter;                           // rng step counter advanced once per step (nullptr: prep did it)
+  int r_lo[2], r_hi[2];                              // optional: update only arena ranges [r_lo, r_hi) (floats, multiples of 4);
+                                                     // all zero = the whole arena
 };
 void optim_launch(const OptimArgs& a, cudaStream_t s);
 

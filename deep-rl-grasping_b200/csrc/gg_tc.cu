@@ -693,6 +693,7 @@ __global__ void __launch_bounds__(Roles<planes>::NTHREADS, 1) gg_tc_kernel(const
       const int col0 = (ew >> 2) * ecols;            // first accumulator column of this warp
       const int lpr_log = ecols == 16 ? 2 : (EPI_COLS == 64 ? 4 : 3), LPR = 1 << lpr_log, RPI = 32 >> lpr_log;
       const bool tr = pk.trace && blockIdx.x == 0 && ew == 0 && lane == 0 && it < 64;
+      if (tr) pk.trace[it * 8 + 7] = clock64();
       const bool fastp = (dflags & GG_CN_AFFINE4) && (ti.n0 + ti.un <= dN);
       const int ncols_w = max(0, min(ecols, ti.un - col0));        // warp-uniform, multiple of 16
       // ReLU-mask values of the first store batch: their addresses depend only on the tables, so the loads are issued

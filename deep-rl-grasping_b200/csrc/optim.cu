@@ -67,7 +67,10 @@ __global__ void __launch_bounds__(256) optim_kernel(OptimArgs a) {
   const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
   const float lrt[3] = {(float)a.step_consts[0], (float)a.step_consts[1], (float)a.step_consts[2]};
   float ss[2] = {0.f, 0.f};
-  for (int i4 = blockIdx.x * blockDim.x + threadIdx.x; i4 < n_total4; i4 += gridDim.x * blockDim.x) {
+  const bool ranged = a.r_hi[0] > 0 || a.r_hi[1] > 0;
+  const int len0 = ranged ? (a.r_hi[0] - a.r_lo[0]) >> 2 : n_total4, len1 = ranged ? (a.r_hi[1] - a.r_lo[1]) >> 2 : 0;
+  for (int k4 = blockIdx.x * blockDim.x + threadIdx.x; k4 < len0 + len1; k4 += gridDim.x * blockDim.x) {
+    const int i4 = !ranged ? k4 : (k4 < len0 ? (a.r_lo[0] >> 2) + k4 : (a.r_lo[1] >> 2) + (k4 - len0));
     const int i = i4 << 2;
     const int grp = i < a.n_pi ? 0 : (i < a.n_pi + a.n_values ? 1 : 2);
     float4 g = reinterpret_cast<const float4*>(a.G)[i4];
@@ -197,7 +200,9 @@ void planes_launch(const PlaneJob* dev_jobs, int njobs, int total_tiles, cudaStr
 void prep_launch(const PrepArgs& a, cudaStream_t s) { prep_kernel<<<1, 256, 0, s>>>(a); }
 
 void optim_launch(const OptimArgs& a, cudaStream_t s) {
-  const int n4 = (a.n_pi + a.n_values + a.n_ent) >> 2;
+  int n4 = (a.n_pi + a.n_values + a.n_ent) >> 2;
+  if (a.r_hi[0] > 0 || a.r_hi[1] > 0) n4 = ((a.r_hi[0] - a.r_lo[0]) + (a.r_hi[1] - a.r_lo[1])) >> 2;
+  if (n4 <= 0) return;
   int grid = (n4 + 255) / 256;
   if (grid > 148 * 8) grid = 148 * 8;
   optim_kernel<<<grid, 256, 0, s>>>(a);

@@ -164,6 +164,7 @@ struct b2g_sac {
   bool fork_leaves = false;
   bool tc_ranges = false;                  // contiguous cost-balanced tile ranges per CTA: measured SLOWER than round-robin
                                            // (split-R tiles of one output pile their atomics onto one CTA); B2G_TC_RANGES=1 enables
+  bool early_opt = false;                  // early fc1/heads optimiser pass on the leaf branch: measured no gain (B2G_EARLY_OPT=1 enables)
   bool a_rowlanes = true;                  // conv1 fwd gather with row-major lane order (B2G_ROWLANES=0 disables)
   bool fc0_split = true;                   // split-R heads_fc0 (needs z0 zeroed every step)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -903,10 +904,10 @@ int issue_step(b2g_sac* h, bool sampled, bool apply, bool want_per_sample, Prof*
       CK(cudaStreamSynchronize(s));
       CK(cudaMemcpy(t.data(), h->dbg_trace, t.size() * sizeof(long long), cudaMemcpyDeviceToHost));
       const long long t0 = t[0];
-      fprintf(stderr, "trace %s (cycles since first stamp; per tile: prod_start prod_issued | mma_full mma_commit | epi_accfull epi_ld epi_stored)\n", g.name.c_str());
+      fprintf(stderr, "trace %s (cycles since first stamp; per tile: prod_start prod_issued | mma_full mma_commit | epi_tables epi_accfull epi_ld epi_stored)\n", g.name.c_str());
       for (int i = 0; i < 12 && t[i * 8]; ++i)
-        fprintf(stderr, "  tile %2d: %7lld %7lld | %7lld %7lld | %7lld %7lld %7lld\n", i, t[i * 8] - t0, t[i * 8 + 1] - t0, t[i * 8 + 2] - t0,
-                t[i * 8 + 3] - t0, t[i * 8 + 4] - t0, t[i * 8 + 5] - t0, t[i * 8 + 6] - t0);
+        fprintf(stderr, "  tile %2d: %7lld %7lld | %7lld %7lld | %7lld %7lld %7lld %7lld\n", i, t[i * 8] - t0, t[i * 8 + 1] - t0, t[i * 8 + 2] - t0,
+                t[i * 8 + 3] - t0, t[i * 8 + 7] - t0, t[i * 8 + 4] - t0, t[i * 8 + 5] - t0, t[i * 8 + 6] - t0);
     }
     return 0;
   };
@@ -919,9 +920,19 @@ int issue_step(b2g_sac* h, bool sampled, bool apply, bool want_per_sample, Prof*
   int last_fc1 = -1;
   for (size_t i = 0; i < h->bwd_groups.size(); ++i)
     if (h->bwd_groups[i].name.find("fc1") != std::string::npos || h->bwd_groups[i].name.find("heads") != std::string::npos) last_fc1 = (int)i;
+  auto make_optim = [&]() {
+    OptimArgs oa{};
+    oa.P = h->P; oa.Mo = h->Mo; oa.Vo = h->Vo; oa.G = h->G; oa.T = h->P + h->n_train;
+    oa.n_pi = (int)h->n_pi; oa.n_values = (int)h->n_values; oa.n_ent = (int)h->n_ent; oa.n_target = (int)h->n_target;
+    oa.step_consts = h->step_consts; oa.tau = h->cfg.tau; oa.grad_scale = 1.0f / (float)h->cfg.nranks;
+    oa.metrics = h->metrics; oa.apply = apply ? 1 : 0;
+    return oa;
+  };
   const bool overlap = h->overlap_ar && h->cnn && last_fc1 >= 0 && last_fc1 + 1 < (int)h->bwd_groups.size();
   const int64_t pi_fc1 = h->tensors[h->tindex.at("model/pi/" + std::string(h->cnn ? "cnn_fc1/w" : "fc0/kernel"))].off;
   const int64_t v_fc1 = h->tensors[h->tindex.at("model/values_fn/" + std::string(h->cnn ? "cnn_fc1/w" : "vf/fc0/kernel"))].off;
+  const bool early_opt = fork && h->early_opt && h->cfg.nranks == 1 && h->cnn && last_fc1 >= 0 && last_fc1 + 1 < (int)h->bwd_groups.size() &&
+                         (pi_fc1 & 3) == 0 && (v_fc1 & 3) == 0;
   auto nccl_ck = [&](int rc) -> int {
     if (rc != 0) return fail(B2G_ENCCL, std::string("nccl: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
     return 0;
@@ -940,9 +951,18 @@ int issue_step(b2g_sac* h, bool sampled, bool apply, bool want_per_sample, Prof*
     }
     if (int rc = run_group(h->bwd_groups[i], leaf ? ax : s)) return rc;
     if ((int)i == last_fc1) {
+      if (fork) { CK(cudaEventRecord(h->ev_aux[3], s)); CK(cudaStreamWaitEvent(ax, h->ev_aux[3], 0)); }
       if (planes_bias && h->n_colsum_early) {
-        if (fork) { CK(cudaEventRecord(h->ev_aux[3], s)); CK(cudaStreamWaitEvent(ax, h->ev_aux[3], 0)); }
         colsum_launch(h->d_colsum_early, h->n_colsum_early, h->colsum_early_ctas, ax); ++n; mark("bias_grads_fc1");
+      }
+      if (early_opt) {
+        // Single GPU: every gradient of [cnn_fc1 .. end] of both trainable blocks (84 % of the parameters) is final
+        // here, so their Adam / Polyak pass runs on the leaf branch underneath the conv backward; the closing
+        // optimiser launch only sweeps the conv kernels.
+        OptimArgs oe = make_optim();
+        oe.r_lo[0] = (int)pi_fc1; oe.r_hi[0] = (int)h->n_pi;
+        oe.r_lo[1] = (int)v_fc1; oe.r_hi[1] = (int)(h->n_pi + h->n_values + h->n_ent);
+        optim_launch(oe, ax); ++n;
       }
       if (overlap) {
         // early all-reduce on the side stream / second communicator, overlapping the conv backward
@@ -979,12 +999,12 @@ int issue_step(b2g_sac* h, bool sampled, bool apply, bool want_per_sample, Prof*
     CK(cudaMemcpyAsync(h->metrics, h->G + h->n_train, MET_GN_PI * sizeof(float), cudaMemcpyDeviceToDevice, s)); ++n;
     mark("allreduce");
   }
-  OptimArgs oa{};
-  oa.P = h->P; oa.Mo = h->Mo; oa.Vo = h->Vo; oa.G = h->G; oa.T = h->P + h->n_train;
-  oa.n_pi = (int)h->n_pi; oa.n_values = (int)h->n_values; oa.n_ent = (int)h->n_ent; oa.n_target = (int)h->n_target;
-  oa.step_consts = h->step_consts; oa.tau = h->cfg.tau; oa.grad_scale = 1.0f / (float)h->cfg.nranks;
-  oa.metrics = h->metrics; oa.apply = apply ? 1 : 0;
+  OptimArgs oa = make_optim();
   oa.bump_counter = (fork && sampled) ? h->counters + 4 : nullptr;
+  if (early_opt) {
+    oa.r_lo[0] = 0; oa.r_hi[0] = (int)pi_fc1;
+    oa.r_lo[1] = (int)h->n_pi; oa.r_hi[1] = (int)v_fc1;
+  }
   optim_launch(oa, s); ++n; mark("adam_polyak");
   if (h->use_planes && apply) {
     // with fork: refreshed on the aux branch at the head of the next step (the API entry points mark them stale)
@@ -1200,6 +1220,7 @@ int b2g_sac_create(const b2g_sac_cfg* cfg, b2g_sac** out) {
   for (int q = 1; q < 5; ++q) h->z0[q] = h->z0[0] + (size_t)q * B * h->H;
   { const char* e = getenv("B2G_FC0_SPLIT"); h->fc0_split = !(e && atoi(e) == 0); }
   { const char* e = getenv("B2G_ROWLANES"); h->a_rowlanes = !(e && atoi(e) == 0); }
+  { const char* e = getenv("B2G_EARLY_OPT"); h->early_opt = e && atoi(e) != 0; }
   { const char* e = getenv("B2G_TC_RANGES"); h->tc_ranges = e && atoi(e) != 0; }
   for (int q = 0; q < 4; ++q) { DA(h->a0[q], B * h->H); DA(h->dz1[q], B * h->H); }
   DA(h->dz0_pi, B * h->H); DA(h->dz0_v3, B * 3 * h->H);
