@@ -62,6 +62,55 @@ __device__ __forceinline__ V2 bwd64(const float* __restrict__ Ws, V2 dz, int lan
   }
   return o;
 }
+// N independent 64x64 mat-vecs advanced in lock step: same arithmetic (and order) per mat-vec as fwd64 / bwd64, but
+// the N dependent FMA chains and their shuffles / shared loads interleave, which is what a one-warp-per-sample kernel
+// needs -- its duration is the length of the dependency chain, not the instruction count.
+template <int N>
+__device__ __forceinline__ void fwd64xN(const float* const (&Ws)[N], const float* const (&bias)[N], const V2 (&a)[N], V2 (&o)[N], int lane) {
+#pragma unroll
+  for (int k = 0; k < N; ++k) o[k] = V2{bias[k][lane], bias[k][lane + 32]};
+#pragma unroll 4
+  for (int i = 0; i < 32; ++i) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const float ai = __shfl_sync(0xffffffffu, a[k].lo, i);
+      o[k].lo = fmaf(ai, Ws[k][i * LD + lane], o[k].lo);
+      o[k].hi = fmaf(ai, Ws[k][i * LD + lane + 32], o[k].hi);
+    }
+  }
+#pragma unroll 4
+  for (int i = 0; i < 32; ++i) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const float ai = __shfl_sync(0xffffffffu, a[k].hi, i);
+      o[k].lo = fmaf(ai, Ws[k][(i + 32) * LD + lane], o[k].lo);
+      o[k].hi = fmaf(ai, Ws[k][(i + 32) * LD + lane + 32], o[k].hi);
+    }
+  }
+}
+template <int N>
+__device__ __forceinline__ void bwd64xN(const float* const (&Ws)[N], const V2 (&dz)[N], V2 (&o)[N], int lane) {
+#pragma unroll
+  for (int k = 0; k < N; ++k) o[k] = V2{0.f, 0.f};
+#pragma unroll 4
+  for (int j = 0; j < 32; ++j) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const float dj = __shfl_sync(0xffffffffu, dz[k].lo, j);
+      o[k].lo = fmaf(dj, Ws[k][lane * LD + j], o[k].lo);
+      o[k].hi = fmaf(dj, Ws[k][(lane + 32) * LD + j], o[k].hi);
+    }
+  }
+#pragma unroll 4
+  for (int j = 0; j < 32; ++j) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const float dj = __shfl_sync(0xffffffffu, dz[k].hi, j);
+      o[k].lo = fmaf(dj, Ws[k][lane * LD + j + 32], o[k].lo);
+      o[k].hi = fmaf(dj, Ws[k][(lane + 32) * LD + j + 32], o[k].hi);
+    }
+  }
+}
 __device__ __forceinline__ V2 ld2(const float* p, int lane) { return V2{p[lane], p[lane + 32]}; }
 __device__ __forceinline__ void st2(float* p, int lane, V2 v) { p[lane] = v.lo; p[lane + 32] = v.hi; }
 // scalar head output: sum_i a[i]*ko[i] + bo
@@ -174,12 +223,7 @@ __global__ void __launch_bounds__(WARPS * 32) tail_kernel(TailArgs t) {
     }
     // ------------------------------------------------------------------ critics forward
     const V2 a0_vf = relu2(V2{zvf.lo + s_b0[S_VF][lane], zvf.hi + s_b0[S_VF][lane + 32]});
-    const V2 a1_vf = relu2(fwd64(Wk1 + S_VF * H * LD, s_b1[S_VF], a0_vf, lane));
-    const float v = out1(s_vko[0], s_vko[0] + H, a1_vf, lane);
     const V2 a0_vt = relu2(V2{zvt.lo + s_b0[S_VT][lane], zvt.hi + s_b0[S_VT][lane + 32]});
-    const V2 a1_vt = relu2(fwd64(Wk1 + S_VT * H * LD, s_b1[S_VT], a0_vt, lane));
-    const float v_targ = out1(s_vko[3], s_vko[3] + H, a1_vt, lane);
-
     V2 z0q1p = z0q1, z0q2p = z0q2;   // fc0 pre-activation at pi: linear in the action columns
 #pragma unroll
     for (int a = 0; a < AMAX; ++a) {
@@ -196,10 +240,19 @@ __global__ void __launch_bounds__(WARPS * 32) tail_kernel(TailArgs t) {
     const V2 a0_q2 = relu2(V2{z0q2.lo + b0q2.lo, z0q2.hi + b0q2.hi});
     const V2 a0_q1p = relu2(V2{z0q1p.lo + b0q1.lo, z0q1p.hi + b0q1.hi});
     const V2 a0_q2p = relu2(V2{z0q2p.lo + b0q2.lo, z0q2p.hi + b0q2.hi});
-    const V2 a1_q1 = relu2(fwd64(Wk1 + S_Q1 * H * LD, s_b1[S_Q1], a0_q1, lane));
-    const V2 a1_q2 = relu2(fwd64(Wk1 + S_Q2 * H * LD, s_b1[S_Q2], a0_q2, lane));
-    const V2 a1_q1p = relu2(fwd64(Wk1 + S_Q1 * H * LD, s_b1[S_Q1], a0_q1p, lane));
-    const V2 a1_q2p = relu2(fwd64(Wk1 + S_Q2 * H * LD, s_b1[S_Q2], a0_q2p, lane));
+    V2 a1_vf, a1_vt, a1_q1, a1_q2, a1_q1p, a1_q2p;
+    {   // six independent fc1 layers, interleaved
+      const float* const Wn[6] = {Wk1 + S_VF * H * LD, Wk1 + S_VT * H * LD, Wk1 + S_Q1 * H * LD, Wk1 + S_Q2 * H * LD,
+                                  Wk1 + S_Q1 * H * LD, Wk1 + S_Q2 * H * LD};
+      const float* const bn[6] = {s_b1[S_VF], s_b1[S_VT], s_b1[S_Q1], s_b1[S_Q2], s_b1[S_Q1], s_b1[S_Q2]};
+      const V2 an[6] = {a0_vf, a0_vt, a0_q1, a0_q2, a0_q1p, a0_q2p};
+      V2 on[6];
+      fwd64xN<6>(Wn, bn, an, on, lane);
+      a1_vf = relu2(on[0]); a1_vt = relu2(on[1]); a1_q1 = relu2(on[2]); a1_q2 = relu2(on[3]);
+      a1_q1p = relu2(on[4]); a1_q2p = relu2(on[5]);
+    }
+    const float v = out1(s_vko[0], s_vko[0] + H, a1_vf, lane);
+    const float v_targ = out1(s_vko[3], s_vko[3] + H, a1_vt, lane);
     const float q1 = out1(s_vko[1], s_vko[1] + H, a1_q1, lane), q2 = out1(s_vko[2], s_vko[2] + H, a1_q2, lane);
     const float q1p = out1(s_vko[1], s_vko[1] + H, a1_q1p, lane), q2p = out1(s_vko[2], s_vko[2] + H, a1_q2p, lane);
 
@@ -232,42 +285,50 @@ __global__ void __launch_bounds__(WARPS * 32) tail_kernel(TailArgs t) {
       t.pi_out[b * A + lane] = pv;
     }
 
-    // ------------------------------------------------------------------ value heads backward
-    auto value_head_bwd = [&](float dout, const float* wko, const float* Ws, V2 a0, V2 a1, float* accv, float* dz1_out,
-                              float* dz0_out) {
-      // output layer grads
-      atomicAdd(&accv[lane], a1.lo * dout);
-      atomicAdd(&accv[lane + 32], a1.hi * dout);
-      if (lane == 0) atomicAdd(&accv[H], dout);
-      V2 dz1{a1.lo > 0.f ? dout * wko[lane] : 0.f, a1.hi > 0.f ? dout * wko[lane + 32] : 0.f};
-      st2(dz1_out, lane, dz1);
-      V2 da0 = bwd64(Ws, dz1, lane);
-      V2 dz0{a0.lo > 0.f ? da0.lo : 0.f, a0.hi > 0.f ? da0.hi : 0.f};
-      st2(dz0_out, lane, dz0);
-    };
+    // ------------------------------------------------------------------ value heads + d(-Q1(s,pi))/d pi backward
     st2(t.a0_vf + b * H, lane, a0_vf);
     st2(t.a0_q1 + b * H, lane, a0_q1);
     st2(t.a0_q2 + b * H, lane, a0_q2);
-    value_head_bwd(ev * invB, s_vko[0], Wk1 + S_VF * H * LD, a0_vf, a1_vf, a_vf, t.dz1_vf + b * H, t.dz0_v3 + (size_t)b * 3 * H);
-    value_head_bwd(e1 * invB, s_vko[1], Wk1 + S_Q1 * H * LD, a0_q1, a1_q1, a_q1, t.dz1_q1 + b * H, t.dz0_v3 + (size_t)b * 3 * H + H);
-    value_head_bwd(e2 * invB, s_vko[2], Wk1 + S_Q2 * H * LD, a0_q2, a1_q2, a_q2, t.dz1_q2 + b * H, t.dz0_v3 + (size_t)b * 3 * H + 2 * H);
-
-    // ------------------------------------------------------------------ policy backward
-    // d(-Q1(s,pi))/d pi through qf1 with its weights held constant
     float dpi[AMAX];
     {
-      const float dout = -invB;
-      V2 dz1{a1_q1p.lo > 0.f ? dout * s_vko[1][lane] : 0.f, a1_q1p.hi > 0.f ? dout * s_vko[1][lane + 32] : 0.f};
-      V2 da0 = bwd64(Wk1 + S_Q1 * H * LD, dz1, lane);
-      V2 dz0{a0_q1p.lo > 0.f ? da0.lo : 0.f, a0_q1p.hi > 0.f ? da0.hi : 0.f};
+      // output-layer gradients and the fc1 backward seeds of the three value heads, plus the qf1-at-pi path of the policy
+      // loss (its weights held constant); the four fc1 transposed mat-vecs are independent and run interleaved
+      const float douts[3] = {ev * invB, e1 * invB, e2 * invB};
+      const V2 a1s[3] = {a1_vf, a1_q1, a1_q2};
+      float* const accs[3] = {a_vf, a_q1, a_q2};
+      float* const dz1o[3] = {t.dz1_vf + b * H, t.dz1_q1 + b * H, t.dz1_q2 + b * H};
+      V2 dzn[4];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        atomicAdd(&accs[k][lane], a1s[k].lo * douts[k]);
+        atomicAdd(&accs[k][lane + 32], a1s[k].hi * douts[k]);
+        if (lane == 0) atomicAdd(&accs[k][H], douts[k]);
+        dzn[k] = V2{a1s[k].lo > 0.f ? douts[k] * s_vko[k][lane] : 0.f, a1s[k].hi > 0.f ? douts[k] * s_vko[k][lane + 32] : 0.f};
+        st2(dz1o[k], lane, dzn[k]);
+      }
+      {
+        const float dout = -invB;
+        dzn[3] = V2{a1_q1p.lo > 0.f ? dout * s_vko[1][lane] : 0.f, a1_q1p.hi > 0.f ? dout * s_vko[1][lane + 32] : 0.f};
+      }
+      const float* const Wn[4] = {Wk1 + S_VF * H * LD, Wk1 + S_Q1 * H * LD, Wk1 + S_Q2 * H * LD, Wk1 + S_Q1 * H * LD};
+      V2 dan[4];
+      bwd64xN<4>(Wn, dzn, dan, lane);
+      const V2 a0s[3] = {a0_vf, a0_q1, a0_q2};
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const V2 dz0{a0s[k].lo > 0.f ? dan[k].lo : 0.f, a0s[k].hi > 0.f ? dan[k].hi : 0.f};
+        st2(t.dz0_v3 + (size_t)b * 3 * H + k * H, lane, dz0);
+      }
+      const V2 dz0p{a0_q1p.lo > 0.f ? dan[3].lo : 0.f, a0_q1p.hi > 0.f ? dan[3].hi : 0.f};
 #pragma unroll
       for (int a = 0; a < AMAX; ++a) {
         if (a < A) {
           const float* r1 = s_q1act + a * H;
-          dpi[a] = warp_sum(dz0.lo * r1[lane] + dz0.hi * r1[lane + 32]);
+          dpi[a] = warp_sum(dz0p.lo * r1[lane] + dz0p.hi * r1[lane + 32]);
         }
       }
     }
+    // ------------------------------------------------------------------ policy backward
     float dmu[AMAX], dls[AMAX];
     V2 dg{0.f, 0.f};
 #pragma unroll
