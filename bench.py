@@ -281,7 +281,7 @@ def main():
         if os.path.exists(tpath):          # dram read+write per gg_tc_kernel launch from the committed ncu --set full capture
             traffic = json.load(open(tpath)).get("gg_tc_kernel_dram_bytes_per_launch")
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                    "traffic": traffic, "traffic_unit": "bytes per gg_tc_kernel launch (ncu dram read+write, profiles/ncu_gg_tc_r1_planes.md)", "kernel": "gg_tc_kernel (tcgen05 gather-GEMM, cp.async-fed BF16 hi/lo planes: convs, cnn_fc1 and head fc0 layers, fwd/wgrad/dgrad; 14 launches per step)" if prec else "gg_simt_kernel (fp32 FFMA engine)",
+                    "traffic": traffic, "traffic_unit": "bytes per gg_tc_kernel launch (ncu dram read+write averaged over the step's tensor-engine launches, profiles/ncu_launches_r1.csv)", "kernel": "gg_tc_kernel (tcgen05 gather-GEMM, cp.async-fed BF16 hi/lo planes: convs, cnn_fc1 and head fc0 layers, fwd/wgrad/dgrad; 11 launches per step)" if prec else "gg_simt_kernel (fp32 FFMA engine)",
                     "peak_source": peak_src, "launch_ms": gemm_ms, "launches": len(gemm_groups),
                     "step_share": gemm_ms / sum(prof.values()), "per_group_ms": {k: round(v, 4) for k, v in prof.items()},
                     "whole_step_frac": value / world * flops / 1e12 / peak_tf}
