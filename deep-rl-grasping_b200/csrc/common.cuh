@@ -78,6 +78,7 @@ struct GemmDesc {
   int tiles_m, tiles_n;
   int tile_start;   // first flattened CTA index of this problem inside a grouped launch
   int tile_count;
+  int col_id;       // tcgen05 engine: identity of (cN, kN, bias, N); equal ids share the staged column tables
 };
 
 struct GemmGroup {          // one grouped launch

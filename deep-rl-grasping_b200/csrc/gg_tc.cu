@@ -626,21 +626,26 @@ __global__ void __launch_bounds__(Roles<planes>::NTHREADS, 1) gg_tc_kernel(const
     float* dC = nullptr; uint16_t* dChi = nullptr; uint16_t* dClo = nullptr; const float* dmask = nullptr;
     const uint32_t stg = ring + STAGES * STAGE_BYTES + (uint32_t)ew * (32 * EPI_COLS * 4);
     uint32_t it = 0;
-    int staged_p = -1, staged_n0 = -1;             // which (problem, column block) the staged tables belong to
+    int staged_n0 = -1, st_col = -2;               // which (column tables, column block) the staged copies belong to
     // Everything a tile's epilogue needs from global memory besides the mask -- tile coordinates, this lane's row
     // offsets (cM / kM), this thread's column-table entry (cN / kN / bias) -- is fetched ONE TILE AHEAD and only
     // consumed after the current tile's work, so none of those round trips sits on the per-tile critical path.
     // No arithmetic touches a freshly loaded value inside prefetch() (a dependent instruction would stall there).
-    struct ENext { TileInfo ti; int cm, km; bool ok, km_same, valid; int t_cn, t_kn; float t_bias; bool kn_same; };
+    struct ENext { TileInfo ti; int cm, km; bool ok, km_same, valid; int t_cn, t_kn; float t_bias; bool kn_same; int col_id; };
     auto prefetch = [&](int tile) {
       ENext e;
       e.valid = tile < t_end;
       e.cm = e.km = 0; e.ok = false; e.km_same = true; e.t_cn = e.t_kn = 0; e.t_bias = 0.f; e.kn_same = true;
+      e.col_id = -1;
       if (!e.valid) return e;
       e.ti = tile_info(pk, tile);
       if (e.ti.nchunks == 0) return e;
       const GemmDesc& d2 = pk.d[e.ti.p];
       const int fl = d2.flags;
+      // identity of the column tables (host-assigned: same cN / kN / bias / N -> same id): problems that share them
+      // (the parity-class dgrads of a layer, both nets) do not re-stage -- and so skip the named-barrier pair -- when a
+      // CTA's consecutive tiles hop between them
+      e.col_id = d2.col_id;
       const int m2 = e.ti.m0 + lq * 32 + lane;
       e.ok = m2 < d2.M;
       if (e.ok) e.cm = d2.cM[m2];
@@ -671,7 +676,7 @@ __global__ void __launch_bounds__(Roles<planes>::NTHREADS, 1) gg_tc_kernel(const
       const bool m_ok = cur.ok;
       const GemmDesc& d = pk.d[ti.p];
       const uint32_t buf = it & 1;
-      if (ti.p != staged_p || ti.n0 != staged_n0) {   // block-uniform: every epilogue warp walks the same tiles
+      if (cur.col_id != st_col || ti.n0 != staged_n0) {   // block-uniform: every epilogue warp walks the same tiles
         asm volatile("bar.sync 2, %0;" ::"n"(NEPI));  // previous readers of the staged tables are done
         if (et < TN) {
           s_cn[et] = cur.t_cn;
@@ -680,7 +685,7 @@ __global__ void __launch_bounds__(Roles<planes>::NTHREADS, 1) gg_tc_kernel(const
           s_bias[et - TN] = cur.t_bias;
         }
         asm volatile("bar.sync 2, %0;" ::"n"(NEPI));
-        staged_p = ti.p; staged_n0 = ti.n0;
+        st_col = cur.col_id; staged_n0 = ti.n0;
       }
       if (ti.p != pinned_p) {      // register copies of everything the store loops need from the descriptor
         dflags = pin(d.flags); dN = pin(d.N);

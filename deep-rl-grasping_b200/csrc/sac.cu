@@ -19,6 +19,7 @@
 
 #include <algorithm>
 #include <map>
+#include <tuple>
 #include <string>
 #include <vector>
 
@@ -162,6 +163,7 @@ struct b2g_sac {
   cudaStream_t aux = nullptr;              // leaf work off the critical chain (zeroing, weight planes, leaf wgrads, bias sums)
   cudaEvent_t ev_aux[7]{};
   bool fork_leaves = false;
+  std::map<std::tuple<const void*, const void*, const void*, int>, int> col_ids;
   bool tc_ranges = false;                  // contiguous cost-balanced tile ranges per CTA: measured SLOWER than round-robin
                                            // (split-R tiles of one output pile their atomics onto one CTA); B2G_TC_RANGES=1 enables
   bool early_opt = false;                  // early fc1/heads optimiser pass on the leaf branch: measured no gain (B2G_EARLY_OPT=1 enables)
@@ -323,6 +325,13 @@ int finalize_group(b2g_sac* h, GemmGroup& g) {
       int sp = std::max(1, (g.tc ? 148 : 148) / std::max(1, tiles));
       sp = std::min(sp, std::max(1, d.R / (2 * bk)));
       d.splitR = sp;
+    }
+    {   // column-table identity (gg_tc.cu epilogue): descriptors with the same tables never trigger a re-stage
+      const auto key = std::make_tuple((const void*)d.cN, (const void*)d.kN,
+                                       (const void*)((d.flags & GG_EPI_BIAS_RELU) ? d.bias : nullptr), d.N);
+      auto it = h->col_ids.find(key);
+      if (it == h->col_ids.end()) it = h->col_ids.emplace(key, (int)h->col_ids.size()).first;
+      d.col_id = it->second;
     }
     d.tile_start = start;
     d.tile_count = d.tiles_m * d.tiles_n * d.splitR;
