@@ -270,7 +270,7 @@ def main():
     for _ in range(3):              # every rank: the step contains the all-reduce
         prof = L.profile_step(lr=LR)
     if rank == 0:
-        gemm_groups = {k: v for k, v in prof.items() if k.startswith("conv") or k.startswith("fc1_") or k.startswith("heads_fc0")
+        gemm_groups = {k: v for k, v in prof.items() if k.startswith("conv") or k.startswith("cnn_") or k.startswith("fc1_") or k.startswith("heads_fc0")
                        or k in ("heads_wgrad", "heads_dgrad")}
         gemm_ms = sum(gemm_groups.values())
         peak_tf, peak_hbm, peak_src = peaks()

@@ -51,6 +51,7 @@ struct DescPack {
   int total_tiles;
   long long* trace;   // bring-up: per-tile clock64 stamps of CTA 0 (nullptr in production)
   const int* ranges;  // [grid + 1] contiguous, cost-balanced tile range per CTA (nullptr: round-robin over the grid)
+  unsigned* sync_ctr; // fused multi-layer launch: epilogue warps that finished a tile (zeroed before the launch; nullptr: none)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -272,6 +273,27 @@ __global__ void __launch_bounds__(Roles<planes>::NTHREADS, 1) gg_tc_kernel(const
     TState cur = fetch(t_begin);
     int tcount = 0;
     int pin_p = -1, pflags = 0;
+    // Fused multi-layer launch: a problem of layer L may read its operands only after every tile of the layers before it
+    // has been stored.  Tiles are numbered layer by layer and every CTA walks its tiles in increasing order, so "all
+    // tiles below need_done are complete" is a count: epilogue warps bump one counter per finished tile, producers of a
+    // later layer wait for need_done * (epilogue warps) -- a grid barrier without leaving the kernel.  No cycle is
+    // possible (a tile only ever waits for lower-numbered tiles, all CTAs are co-resident: grid <= #SMs, 1 CTA / SM).
+    unsigned seen_done = 0, pneed = 0;
+    auto layer_wait = [&]() {
+      if (pneed > seen_done) {
+        if (lane == 0) {
+          unsigned v = 0, spins = 0;
+          while (true) {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(pk.sync_ctr) : "memory");
+            if (v >= pneed) break;
+            __nanosleep(40);
+            if (++spins > (1u << 22)) asm volatile("trap;");   // a lost signal must fail loudly, not hang the GPU
+          }
+          seen_done = v;
+        }
+        seen_done = __shfl_sync(0xffffffffu, seen_done, 0);
+      }
+    };
     const uint16_t* pA_hi = nullptr; const uint16_t* pA_lo = nullptr; const uint16_t* pB_hi = nullptr; const uint16_t* pB_lo = nullptr;
     const int* tabA = nullptr; const int* tabB_k = nullptr; const int* tabB_mn = nullptr;
     for (int tile = t_begin; tile < t_end; tile += t_step, ++tcount) {
@@ -283,8 +305,10 @@ __global__ void __launch_bounds__(Roles<planes>::NTHREADS, 1) gg_tc_kernel(const
         pflags = pin(dd.flags);
         pA_hi = pin(dd.A_hi); pA_lo = pin(dd.A_lo); pB_hi = pin(dd.B_hi); pB_lo = pin(dd.B_lo);
         tabA = pin(dd.aR); tabB_mn = pin(dd.bR); tabB_k = pin(dd.bR_p ? dd.bR_p : dd.bR);
+        pneed = pk.sync_ctr ? (unsigned)dd.need_done * (unsigned)(NEPI / 32) : 0u;
         pin_p = ti.p;
       }
+      if (ti.nchunks > 0) layer_wait();
       if (ti.nchunks > 0 && (pflags & GG_MN_MAJOR)) {
         // ---- wgrad: D[k, n] = sum_m act[m -> k] * dZ[m, n]; both operands are contiguous along their M / N
         // index for a fixed reduction index m, so tiles are MN-major: row (r = m) x 16-byte groups along k / n.
@@ -671,7 +695,10 @@ __global__ void __launch_bounds__(Roles<planes>::NTHREADS, 1) gg_tc_kernel(const
       const ENext cur = nxt;
       nxt = prefetch(tile + t_step);
       const TileInfo ti = cur.ti;
-      if (ti.nchunks == 0) continue;
+      if (ti.nchunks == 0) {
+        if (pk.sync_ctr && lane == 0) atomicAdd(pk.sync_ctr, 1u);   // empty split-R slices still count as finished tiles
+        continue;
+      }
       const int cm = cur.cm, km = cur.km_same ? cur.cm : cur.km;
       const bool m_ok = cur.ok;
       const GemmDesc& d = pk.d[ti.p];
@@ -818,6 +845,11 @@ __global__ void __launch_bounds__(Roles<planes>::NTHREADS, 1) gg_tc_kernel(const
         }
         __syncwarp();      // staging rows are reused by the next tile
       }
+      if (pk.sync_ctr) {          // this warp's stores of the tile are visible device-wide before the tile counts as done
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) atomicAdd(pk.sync_ctr, 1u);
+      }
       if (tr) pk.trace[it * 8 + 6] = clock64();
       ++it;
     }
@@ -882,7 +914,7 @@ std::vector<int> gg_tc_ranges(const GemmDesc* descs, int ndesc, int total_tiles,
 long long* g_tc_trace = nullptr;   // set by sac.cu for one traced launch
 
 cudaError_t gg_tc_launch(const GemmDesc* host_descs, int ndesc, int total_tiles, int mode_flags, int x3, int num_sms,
-                         cudaStream_t s, const int* dev_ranges, int ranges_grid) {
+                         cudaStream_t s, const int* dev_ranges, int ranges_grid, unsigned* sync_ctr) {
   if (total_tiles <= 0) return cudaSuccess;
   if (ndesc > GG_TC_MAX_DESCS) return cudaErrorInvalidValue;
   DescPack pk;
@@ -892,6 +924,8 @@ cudaError_t gg_tc_launch(const GemmDesc* host_descs, int ndesc, int total_tiles,
   pk.trace = g_tc_trace;
   const int grid = total_tiles < num_sms ? total_tiles : num_sms;
   pk.ranges = (dev_ranges && ranges_grid == grid) ? dev_ranges : nullptr;   // built for exactly this grid size
+  pk.sync_ctr = sync_ctr;
+  if (sync_ctr && (!(mode_flags & GG_PLANES) || grid > num_sms)) return cudaErrorInvalidValue;   // layer sync: planes kernel, co-resident grid
   const bool ar = mode_flags & GG_A_RVEC, br = mode_flags & GG_B_RVEC;
   if (mode_flags & GG_PLANES) return launch_mode<true, true, true>(pk, x3, num_sms, s);
   if (ar && br) return launch_mode<true, true, false>(pk, x3, num_sms, s);

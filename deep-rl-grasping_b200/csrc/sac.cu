@@ -167,6 +167,8 @@ struct b2g_sac {
   bool tc_ranges = false;                  // contiguous cost-balanced tile ranges per CTA: measured SLOWER than round-robin
                                            // (split-R tiles of one output pile their atomics onto one CTA); B2G_TC_RANGES=1 enables
   bool early_opt = false;                  // early fc1/heads optimiser pass on the leaf branch: measured no gain (B2G_EARLY_OPT=1 enables)
+  bool fuse_fwd = false;                   // B2G_FUSE_FWD=1: the CNN forward chain as one layer-synchronised launch
+  unsigned* sync_ctr = nullptr;            // its completion counter (zeroed every step)
   bool a_rowlanes = true;                  // conv1 fwd gather with row-major lane order (B2G_ROWLANES=0 disables)
   bool fc0_split = true;                   // split-R heads_fc0 (needs z0 zeroed every step)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -339,7 +341,12 @@ int finalize_group(b2g_sac* h, GemmGroup& g) {
     g.flops += 2.0 * d.M * d.N * d.R;
   }
   g.total_tiles = start;
-  if (g.tc && h->tc_ranges && start > 0) {     // contiguous cost-balanced tile schedule of the tcgen05 engine
+  if (g.layer_sync) {       // a layer's problems wait for every tile of the layers before it
+    std::map<int, int> first;
+    for (auto& d : g.host) { auto it = first.find(d.layer); if (it == first.end() || d.tile_start < it->second) first[d.layer] = d.tile_start; }
+    for (auto& d : g.host) d.need_done = d.layer > 0 ? first[d.layer] : 0;
+  }
+  if (g.tc && h->tc_ranges && start > 0 && !g.layer_sync) {     // contiguous cost-balanced tile schedule of the tcgen05 engine
     g.ranges_grid = std::min(start, h->num_sms);
     const std::vector<int> rg = gg_tc_ranges(g.host.data(), (int)g.host.size(), start, g.ranges_grid);
     if (int rc = dalloc(h, &g.dev_ranges, rg.size(), false)) return rc;
@@ -766,7 +773,29 @@ int build_groups(b2g_sac* h) {
       g.tc = s == "all" || (s != "none" && ("," + s + ",").find("," + g.name + ",") != std::string::npos);
     }
   };
-  for (auto& g : h->fwd_groups) { pick(g); if (int rc = finalize_group(h, g)) return rc; }
+  for (auto& g : h->fwd_groups) pick(g);
+  // Fused forward chain: conv1 -> conv2 -> conv3 -> fc1 of all three nets as ONE persistent launch with in-kernel layer
+  // barriers (gg_tc.cu: need_done / sync_ctr) instead of four launches.
+  if (h->fuse_fwd && h->cnn && h->use_planes && h->fwd_groups.size() >= 4) {
+    bool ok = true;
+    size_t ndesc = 0;
+    for (int l = 0; l < 4; ++l) {
+      ok = ok && h->fwd_groups[l].tc;
+      for (auto& d : h->fwd_groups[l].host) ok = ok && (d.flags & GG_PLANES);
+      ndesc += h->fwd_groups[l].host.size();
+    }
+    if (ok && ndesc <= (size_t)GG_TC_MAX_DESCS) {
+      GemmGroup m;
+      m.name = "cnn_fwd";
+      m.tc = m.tc_eligible = true;
+      m.layer_sync = true;
+      for (int l = 0; l < 4; ++l)
+        for (auto d : h->fwd_groups[l].host) { d.layer = l; m.host.push_back(d); }
+      h->fwd_groups.erase(h->fwd_groups.begin(), h->fwd_groups.begin() + 4);
+      h->fwd_groups.insert(h->fwd_groups.begin(), m);
+    }
+  }
+  for (auto& g : h->fwd_groups) { if (int rc = finalize_group(h, g)) return rc; }
   for (auto& g : h->bwd_groups) { pick(g); if (int rc = finalize_group(h, g)) return rc; }
   for (auto& g : h->act_groups) { pick(g); if (int rc = finalize_group(h, g)) return rc; }
   return 0;
@@ -879,6 +908,7 @@ int issue_step(b2g_sac* h, bool sampled, bool apply, bool want_per_sample, Prof*
     CK(cudaStreamWaitEvent(ax, h->ev_aux[0], 0));
     if (h->use_planes) { planes_launch(h->d_jobs, h->n_jobs, h->job_tiles, ax); ++n; }
     if (h->fc0_split) { CK(cudaMemsetAsync(h->z0[0], 0, (size_t)5 * h->B * h->H * sizeof(float), ax)); ++n; }
+    if (h->fuse_fwd) { CK(cudaMemsetAsync(h->sync_ctr, 0, 32 * sizeof(unsigned), ax)); ++n; }
     CK(cudaEventRecord(h->ev_aux[1], ax));
     prep_launch(pa, ax); ++n;
     CK(cudaMemsetAsync(h->G, 0, (size_t)(h->n_train + MET_COUNT) * sizeof(float), ax)); ++n;
@@ -892,6 +922,7 @@ int issue_step(b2g_sac* h, bool sampled, bool apply, bool want_per_sample, Prof*
   else {
     CK(cudaMemsetAsync(h->G, 0, (size_t)(h->n_train + MET_COUNT) * sizeof(float), s)); ++n;
     if (h->fc0_split) { CK(cudaMemsetAsync(h->z0[0], 0, (size_t)5 * h->B * h->H * sizeof(float), s)); ++n; }
+    if (h->fuse_fwd) { CK(cudaMemsetAsync(h->sync_ctr, 0, 32 * sizeof(unsigned), s)); ++n; }
     mark("zero_grads");
   }
   int x3 = h->cfg.precision == B2G_PREC_BF16X3 ? 1 : 0;
@@ -905,7 +936,8 @@ int issue_step(b2g_sac* h, bool sampled, bool apply, bool want_per_sample, Prof*
       g_tc_trace = h->dbg_trace;
     }
     struct Reset { ~Reset() { g_tc_trace = nullptr; } } reset_;
-    if (g.tc) CK(gg_tc_launch(g.host.data(), (int)g.host.size(), g.total_tiles, g.host[0].flags, x3, h->num_sms - sm_reserve, s, g.dev_ranges, g.ranges_grid));
+    if (g.tc) CK(gg_tc_launch(g.host.data(), (int)g.host.size(), g.total_tiles, g.host[0].flags, x3, h->num_sms - sm_reserve, s, g.dev_ranges, g.ranges_grid,
+                              g.layer_sync ? h->sync_ctr : nullptr));
     else gg_simt_launch(g.dev, (int)g.host.size(), g.total_tiles, s);
     ++n; mark(g.name.c_str());
     if (trace) {
@@ -1229,6 +1261,8 @@ int b2g_sac_create(const b2g_sac_cfg* cfg, b2g_sac** out) {
   for (int q = 1; q < 5; ++q) h->z0[q] = h->z0[0] + (size_t)q * B * h->H;
   { const char* e = getenv("B2G_FC0_SPLIT"); h->fc0_split = !(e && atoi(e) == 0); }
   { const char* e = getenv("B2G_ROWLANES"); h->a_rowlanes = !(e && atoi(e) == 0); }
+  { const char* e = getenv("B2G_FUSE_FWD"); h->fuse_fwd = e && atoi(e) != 0; }
+  DA(h->sync_ctr, 32);
   { const char* e = getenv("B2G_EARLY_OPT"); h->early_opt = e && atoi(e) != 0; }
   { const char* e = getenv("B2G_TC_RANGES"); h->tc_ranges = e && atoi(e) != 0; }
   for (int q = 0; q < 4; ++q) { DA(h->a0[q], B * h->H); DA(h->dz1[q], B * h->H); }
