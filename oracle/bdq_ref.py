@@ -16,7 +16,10 @@ shapes of the shipped zips (trained_models/BDQ_8pads, BDQ_33pads_big; SURVEY.md 
   loss    = mean_b w_b mean_d (Q_d(s, a_d) - y)^2 ;  trunk gradient rescaled by 1/(D+1) (paper, section 4)
   Adam (TF1 form), hard target copy every ``target_network_update_freq`` steps.
 Every detail not visible in the zips/configs (loss reduction, the 1/(D+1) rescale, no gradient clipping) is a
-choice documented here, not a pinned fact.
+choice documented here, not a pinned fact.  trained_models/BDQ_8pads/logs.full.csv (mean_loss, mean_td_errors per log
+interval) was examined as a possible pin: its early rows have mean_loss ~ 0.002 * mean_td_errors**2, below the Jensen
+bound td**2 / 9 of the paper's definitions, so the fork's logged quantities are not the ones restated here and the
+log cannot arbitrate.
 """
 from __future__ import annotations
 
