@@ -63,6 +63,8 @@ class SAC:
             raise NotImplementedError("target_update_interval must be 1 (every shipped zip)")
         if action_noise is not None:
             raise NotImplementedError("action_noise is not used by the reference (zip: action_noise None)")
+        if getattr(policy, "unsupported", None):
+            raise NotImplementedError(policy.unsupported)
         self.policy = policy
         self.policy_kwargs = dict(policy_kwargs or {})
         layers = list(self.policy_kwargs.get("layers", [64, 64]))

@@ -36,7 +36,12 @@ class RunningMeanStd:
         self.mean, self.var, self.count = new_mean, m_2 / tot, tot
 
 
-class DummyVecEnv:
+class VecEnv:
+    """Marker base class (``isinstance(env, VecEnv)`` in base_callbacks.py:50 and [SB2] evaluate_policy)."""
+    num_envs = 1
+
+
+class DummyVecEnv(VecEnv):
     """Sequential vectorised env: ``DummyVecEnv([lambda: env, ...])`` (train_stable_baselines.py:54)."""
 
     def __init__(self, env_fns: Sequence[Callable]):
@@ -81,7 +86,7 @@ class DummyVecEnv:
         return [getattr(e, name)(*a, **k) for e in self.envs]
 
 
-class VecNormalize:
+class VecNormalize(VecEnv):
     """[SB2] VecNormalize(venv, training=True, norm_obs=True, norm_reward=True, clip_obs=10.,
     clip_reward=10., gamma=0.99, epsilon=1e-8)."""
 
@@ -219,3 +224,15 @@ class VecNormalize:
         vn.obs_rms.mean, vn.obs_rms.var, vn.obs_rms.count = d["obs_mean"], d["obs_var"], d["obs_count"]
         vn.ret_rms.mean, vn.ret_rms.var, vn.ret_rms.count = np.float64(d["ret_mean"]), np.float64(d["ret_var"]), d["ret_count"]
         return vn
+
+
+def sync_envs_normalization(env, eval_env) -> None:
+    """[SB2] common/vec_env/__init__.py: copy the running statistics of every VecNormalize layer of ``env`` into the
+    matching layer of ``eval_env`` (base_callbacks.py:81 before each evaluation)."""
+    import copy
+    e, ev = env, eval_env
+    while e is not None and ev is not None:
+        if isinstance(e, VecNormalize) and isinstance(ev, VecNormalize):
+            ev.obs_rms = copy.deepcopy(e.obs_rms)
+            ev.ret_rms = copy.deepcopy(e.ret_rms)
+        e, ev = getattr(e, "venv", None), getattr(ev, "venv", None)
