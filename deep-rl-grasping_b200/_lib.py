@@ -17,14 +17,14 @@ B2G_PREC_FP32_SIMT, B2G_PREC_BF16X3, B2G_PREC_BF16 = 0, 1, 2
 SYMBOLS = [
     "b2g_last_error", "b2g_version", "b2g_nccl_unique_id", "b2g_sac_create", "b2g_sac_destroy", "b2g_sync",
     "b2g_param_count", "b2g_param_info", "b2g_get_param", "b2g_set_param", "b2g_get_grad", "b2g_get_adam",
-    "b2g_reset_optimizer", "b2g_replay_add", "b2g_replay_size", "b2g_set_norm_stats", "b2g_sac_step",
+    "b2g_reset_optimizer", "b2g_replay_add", "b2g_replay_size", "b2g_replay_get", "b2g_get_last_batch", "b2g_set_norm_stats", "b2g_sac_step",
     "b2g_sac_step_async", "b2g_sac_step_explicit", "b2g_sac_step_host_pipelined", "b2g_sac_pipeline_flush", "b2g_sac_act", "b2g_launches_per_step", "b2g_last_step_ms",
     "b2g_profile_step",
     "b2g_bdq_create", "b2g_bdq_destroy", "b2g_bdq_param_count", "b2g_bdq_param_info", "b2g_bdq_get_param", "b2g_bdq_set_param",
     "b2g_bdq_get_grad", "b2g_bdq_replay_add", "b2g_bdq_replay_size", "b2g_bdq_set_norm_stats", "b2g_bdq_step",
     "b2g_bdq_step_explicit", "b2g_bdq_act",
     "b2g_encoder_create", "b2g_encoder_destroy", "b2g_encoder_n_layers", "b2g_encoder_layer_shape", "b2g_encoder_set_weights",
-    "b2g_encoder_encode",
+    "b2g_encoder_encode", "b2g_debug_gemm",
 ]
 
 ENC_MAX_LAYERS = 8
@@ -105,6 +105,8 @@ def load():
     lib.b2g_replay_add.argtypes = [vp, fp, fp, fp, fp, fp, C.c_int64]
     lib.b2g_replay_size.argtypes = [vp]
     lib.b2g_replay_size.restype = C.c_int64
+    lib.b2g_replay_get.argtypes = [vp, C.c_int64, fp, fp, fp, fp, fp]
+    lib.b2g_get_last_batch.argtypes = [vp, C.POINTER(C.c_int32), fp, fp, fp]
     lib.b2g_set_norm_stats.argtypes = [vp, dp, dp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int]
     lib.b2g_sac_step.argtypes = [vp, C.c_int, C.c_float, C.POINTER(SacMetrics)]
     lib.b2g_sac_step_async.argtypes = [vp, C.c_int, C.c_float]
@@ -135,6 +137,7 @@ def load():
     lib.b2g_encoder_layer_shape.argtypes = [vp, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     lib.b2g_encoder_set_weights.argtypes = [vp, C.c_int, fp, C.c_size_t, fp, C.c_size_t]
     lib.b2g_encoder_encode.argtypes = [vp, fp, C.c_int, fp]
+    lib.b2g_debug_gemm.argtypes = [C.c_int, C.c_int, C.c_int, fp, fp, fp, C.c_int, C.c_int]
     _lib = lib
     return lib
 

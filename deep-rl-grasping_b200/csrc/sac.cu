@@ -1418,6 +1418,32 @@ int b2g_replay_add(b2g_sac* h, const float* obs, const float* act, const float* 
 
 int64_t b2g_replay_size(const b2g_sac* h) { return h ? h->r_size : 0; }
 
+int b2g_replay_get(b2g_sac* h, int64_t slot, float* obs, float* act, float* rew, float* next_obs, float* done) {
+  if (!h) return fail(B2G_EINVAL, "NULL handle");
+  if (slot < 0 || slot >= h->r_size) return fail(B2G_EINVAL, "replay slot out of range");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaStreamSynchronize(h->stream));
+  const size_t E = h->E, A = h->A;
+  if (obs) CK(cudaMemcpy(obs, h->r_obs + slot * E, E * sizeof(float), cudaMemcpyDeviceToHost));
+  if (next_obs) CK(cudaMemcpy(next_obs, h->r_next + slot * E, E * sizeof(float), cudaMemcpyDeviceToHost));
+  if (act) CK(cudaMemcpy(act, h->r_act + slot * A, A * sizeof(float), cudaMemcpyDeviceToHost));
+  if (rew) CK(cudaMemcpy(rew, h->r_rew + slot, sizeof(float), cudaMemcpyDeviceToHost));
+  if (done) CK(cudaMemcpy(done, h->r_done + slot, sizeof(float), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int b2g_get_last_batch(b2g_sac* h, int32_t* indices, float* eps, float* per_sample, float* pi_out) {
+  if (!h) return fail(B2G_EINVAL, "NULL handle");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaStreamSynchronize(h->stream));
+  const size_t B = h->B, A = h->A;
+  if (indices) CK(cudaMemcpy(indices, h->indices, B * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  if (eps) CK(cudaMemcpy(eps, h->eps, B * A * sizeof(float), cudaMemcpyDeviceToHost));
+  if (per_sample) CK(cudaMemcpy(per_sample, h->per_sample, 7 * B * sizeof(float), cudaMemcpyDeviceToHost));
+  if (pi_out) CK(cudaMemcpy(pi_out, h->pi_out, B * A * sizeof(float), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
 int b2g_set_norm_stats(b2g_sac* h, const double* obs_mean, const double* obs_var, double ret_var, double clip_obs, double clip_rew,
                        double eps, int norm_obs, int norm_reward) {
   if (!h) return fail(B2G_EINVAL, "NULL handle");
@@ -1442,7 +1468,7 @@ static int ensure_graph(b2g_sac* h) {
   cudaGraph_t graph = nullptr;
   CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
   int n = 0;
-  int rc = issue_step(h, true, true, false, nullptr, &n);
+  int rc = issue_step(h, true, true, true, nullptr, &n);
   cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
   if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
   if (e != cudaSuccess) return fail(B2G_ECUDA, std::string("graph capture failed: ") + cudaGetErrorString(e));
@@ -1463,7 +1489,7 @@ int b2g_sac_step_async(b2g_sac* h, int n_steps, float lr) {
   CK(cudaEventRecord(h->ev0, h->stream));
   for (int i = 0; i < n_steps; ++i) {
     if (h->use_graph) CK(cudaGraphLaunch(h->graph_exec, h->stream));
-    else if (int rc = issue_step(h, true, true, false, nullptr, &h->launches)) return rc;
+    else if (int rc = issue_step(h, true, true, true, nullptr, &h->launches)) return rc;
   }
   CK(cudaEventRecord(h->ev1, h->stream));
   return 0;

@@ -141,6 +141,25 @@ class Learner:
     def replay_size(self) -> int:
         return int(self.lib.b2g_replay_size(self.h))
 
+    def replay_get(self, slot: int) -> dict:
+        """One stored (raw) transition, like ``ReplayBuffer.storage[slot]``."""
+        obs, nxt = np.empty(self.obs_shape, np.float32), np.empty(self.obs_shape, np.float32)
+        act, rew, done = np.empty(self.n_act, np.float32), np.empty(1, np.float32), np.empty(1, np.float32)
+        _lib.check(self.lib.b2g_replay_get(self.h, int(slot), _fp(obs.reshape(-1)), _fp(act), _fp(rew), _fp(nxt.reshape(-1)), _fp(done)))
+        return dict(obs=obs, act=act, rew=float(rew[0]), next_obs=nxt, done=float(done[0]))
+
+    def last_batch(self) -> dict:
+        """Replay slots, policy noise and per-sample outputs of the LAST gradient step (graph path included)."""
+        B = self.batch_size
+        idx = np.empty(B, np.int32)
+        eps, ps, pi = np.empty((B, self.n_act), np.float32), np.empty((7, B), np.float32), np.empty((B, self.n_act), np.float32)
+        _lib.check(self.lib.b2g_get_last_batch(self.h, idx.ctypes.data_as(C.POINTER(C.c_int32)), _fp(eps.reshape(-1)),
+                                               _fp(ps.reshape(-1)), _fp(pi.reshape(-1))))
+        out = dict(indices=idx, eps=eps, pi=pi)
+        for i, k in enumerate(("q1", "q2", "v", "logp", "v_targ", "q1_pi", "q2_pi")):
+            out[k] = ps[i].copy()
+        return out
+
     def set_norm_stats(self, obs_mean=None, obs_var=None, ret_var=1.0, clip_obs=10.0, clip_reward=10.0, epsilon=1e-8,
                        norm_obs=True, norm_reward=True):
         dp = C.POINTER(C.c_double)

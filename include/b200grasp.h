@@ -93,6 +93,14 @@ int b2g_reset_optimizer(b2g_sac* h);   /* zero Adam moments and step counters (f
 int b2g_replay_add(b2g_sac* h, const float* obs, const float* act, const float* rew, const float* next_obs,
                    const float* done, int64_t n);
 int64_t b2g_replay_size(const b2g_sac* h);
+/* ReplayBuffer.storage[slot] ([SB2] common/buffers.py): one stored (raw) transition back to the host; any output may be
+ * NULL.  slot in [0, b2g_replay_size). */
+int b2g_replay_get(b2g_sac* h, int64_t slot, float* obs, float* act, float* rew, float* next_obs, float* done);
+/* What the LAST gradient step (any entry point, the CUDA-graph path included) drew and produced: the replay slots
+ * indices[batch] (sampled steps only), the policy noise eps[batch, n_act], the per-sample rows q1,q2,v,logp,v_targ,
+ * q1_pi,q2_pi (7 x [batch]) and the squashed actions pi[batch, n_act].  Any pointer may be NULL.  This is what lets a
+ * test replay the very batch of a sampled step in the oracle. */
+int b2g_get_last_batch(b2g_sac* h, int32_t* indices, float* eps, float* per_sample, float* pi_out);
 int b2g_set_norm_stats(b2g_sac* h, const double* obs_mean, const double* obs_var, double ret_var, double clip_obs,
                        double clip_rew, double eps, int norm_obs, int norm_reward);
 
@@ -211,6 +219,13 @@ int b2g_encoder_set_weights(b2g_encoder* h, int layer, const float* kernel, size
                             size_t bias_numel);
 /* imgs: host [n, height, width, channels] fp32 -> out: host [n, encoding_dim]; B2G_ESTATE until every layer is loaded */
 int b2g_encoder_encode(b2g_encoder* h, const float* imgs, int n, float* out);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Bring-up hook (not on the product path): C[M,N] = A[M,K] * B[N,K]^T through the tcgen05 engine; host pointers,
+ * K a multiple of 8; x3 != 0 -> BF16 hi/lo split (3 MMAs); split_k > 1 -> that many partial accumulators summed
+ * with fp32 atomics.  tools/tc_accum_probe.py uses it to measure the accumulation behaviour of the tensor core.
+ * ------------------------------------------------------------------------------------------------------------ */
+int b2g_debug_gemm(int M, int N, int K, const float* A, const float* B, float* C, int x3, int split_k);
 
 #ifdef __cplusplus
 }
