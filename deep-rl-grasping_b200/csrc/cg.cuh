@@ -1,0 +1,91 @@
+// TMA-fed tcgen05 contraction engine ("cg"): declarations shared by cg.cu (kernel) and sac.cu (problem builders).
+//
+// Every dense contraction of the step is a list of 128-row output tiles; the operands of a tile are fetched, K-chunk by
+// K-chunk, by cp.async.bulk.tensor (TMA) boxes over BF16 plane tensors straight into 128B-swizzled shared-memory UMMA
+// tiles.  Convolutions need no im2col buffer: their patches / shifted windows / zero borders are expressed as tensor-map
+// VIEWS (overlapping strides, element strides, out-of-bound zero fill) of the NHWC activation planes, so one elected
+// thread feeds the whole ring (tools/tma_probe.cu checks each view behaviour on the device).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b2g {
+
+constexpr int CG_MAX_LOADS = 4;     // TMA boxes per K-chunk and plane (A atoms + B atoms)
+constexpr int CG_MAX_PROBLEMS = 12; // problems per grouped launch (the whole list travels as a __grid_constant__ kernel parameter)
+constexpr int CG_MAX_STAGES = 8;
+constexpr int CG_MAX_PLANES = 3;
+
+enum CgEpiKind : int {
+  CG_EPI_ACT = 0,     // relu(acc + bias[n]) -> BF16 planes (activations; optional fp32 copy)
+  CG_EPI_RAW = 1,     // acc -> fp32 (fc0 pre-activations)
+  CG_EPI_DGRAD = 2,   // acc * (mask[row, n] > 0) -> BF16 planes (gradient maps)
+  CG_EPI_WGRAD = 3,   // acc -> fp32 weight gradient, plain store or atomic accumulation (split-K)
+};
+
+struct CgLoad {
+  int map;            // index of the plane-0 tensor map in the map table; plane p uses map + p
+  int rank;           // tensor-map rank (2..5)
+  int smem_off;       // byte offset of the box inside one plane block of a stage
+  int c0[5];          // box start coordinates: c0 + tm*d_tm + tn*d_tn + c1*d_c1 + c2*d_c2 (+ tm_tab)
+  int d_tm[5], d_tn[5], d_c1[5], d_c2[5];
+};
+
+struct CgProblem {
+  // ---- tile grid: tile -> (split, tm, tn); K-chunk c = c1 * n2 + c2
+  int tile_start, tiles_m, tiles_n, splits;
+  int chunks, n2;
+  // ---- operand fetch
+  int nloads, planes;
+  int plane_bytes;            // bytes of one plane block (A region + B region) inside a stage
+  int tx_bytes;               // bytes all boxes of one stage deliver (planes x sum of box bytes)
+  CgLoad ld[CG_MAX_LOADS];
+  const int* tm_tab;          // optional [tiles_m][CG_MAX_LOADS][2]: extra offsets of coordinates 1 and 2 per (tm, load)
+  // ---- MMA
+  int mn_major;               // 0: K-major A and B (rows = M|N, 128 B of K); 1: MN-major (rows = K, 128 B of M|N)
+  int ksteps;                 // UMMA K = 16 steps per chunk
+  int a_off, b_off;           // region offsets inside a plane block
+  int a_kstep, b_kstep;       // descriptor start-address advance per k-step (bytes)
+  int a_lbo, b_lbo;           // MN-major: byte stride between 64-element atoms along M|N
+  int umma_n;                 // tile width (multiple of 16, <= 256)
+  int nprod;                  // products per k-step: 1 (hi*hi), 3 (+hi*lo, lo*hi), 6 (+mid terms of the 3-plane split)
+  // ---- epilogue
+  int epi;
+  int rows_tile;              // real rows of a full tile (<= 128)
+  int lim_rows;               // tm * rows_tile + r < lim_rows
+  int d0, d1;                 // r -> i0 = r % d0, i1 = (r / d0) % d1, i2 = r / (d0 * d1)
+  long long o_tm; int o0, o1, o2; long long o_base;    // output element offset of (tm, r)
+  long long m_tm; int m0, m1, m2; long long m_base;    // mask element offset of (tm, r)
+  int n_valid;                // columns < n_valid are stored (N of the problem)
+  int grp_stride;             // element distance between consecutive 32-column groups of the output (32 = contiguous)
+  int out_planes;             // planes written by ACT / DGRAD
+  uint16_t* out_p[CG_MAX_PLANES];
+  float* out_f;               // fp32 output (RAW / WGRAD; optional extra copy for ACT), same offsets, ld = o0-based
+  long long f_tm; int f0;     // fp32 copy: offset = tm * f_tm + r * f0 + col   (ACT extra copy only; 0 = none)
+  const float* bias;          // [N]
+  int bias_grp;               // element distance between the bias blocks of consecutive 32-column groups (32 = contiguous)
+  long long f_grp;            // same for the fp32 copy
+  const uint16_t* mask;       // hi plane of the forward activation (DGRAD)
+  int atomic;                 // WGRAD: 1 = red.add (split-K or shared output), 0 = store
+  float scale;                // WGRAD: multiply before accumulation (1 = none)
+};
+
+struct CgGroup {               // one launch
+  CgProblem host[CG_MAX_PROBLEMS];
+  int n = 0;
+  int total_tiles = 0;
+  int slot_bytes = 0, nstages = 0;
+  const char* name = "";
+  double flops = 0;
+};
+
+// encodes a BF16 tiled tensor map (SWIZZLE_128B, zero OOB fill); dims/box innermost first, strides in BYTES for dims 1..rank-1
+int cg_encode_map(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                  const uint32_t* elem_strides);
+// finalises tile_start / total_tiles / ring geometry of a group (host side)
+int cg_finalize(CgGroup& g, int smem_budget);
+cudaError_t cg_launch(const CgGroup& g, const CUtensorMap* dev_maps, int num_sms, cudaStream_t s, bool pdl, int debug_flags);
+int cg_smem_limit();
+
+}  // namespace b2g

@@ -130,6 +130,7 @@ struct TailArgs {
   int grad_scale_B;            // divide means by this batch size (local batch)
   // fc0 pre-activations (no bias) [B,H] each
   const float* z0_pi; const float* z0_vf; const float* z0_q1; const float* z0_q2; const float* z0_vt;
+  int z0v_ld;                  // row stride of z0_vf / z0_q1 / z0_q2 (H, or 3H when the three heads share one [B,3H] block)
   HeadW pi, vf, q1, q2, vt;
   const float* ksig; const float* bsig;      // pi: dense_1 (log_std) kernel/bias; pi.ko/bo = dense (mu)
   HeadG g_pi, g_vf, g_q1, g_q2;
@@ -143,6 +144,7 @@ struct TailArgs {
   float* dz1_pi; float* dz1_vf; float* dz1_q1; float* dz1_q2; // [B,H]
   float* dz0_pi;                               // [B,H]
   float* dz0_v3;                               // [B,3H] = vf | q1 | q2
+  uint16_t* dz0_pi_p[2]; uint16_t* dz0_v3_p[2];  // optional BF16 hi / lo planes of the same (engine v2 operands)
   float* per_sample;                           // 7 x [B]: q1,q2,v,logp,v_targ,q1_pi,q2_pi
   float* pi_out;                               // [B,A]
   float* metrics;                              // accumulators (see MET_* in sac.cu)

@@ -25,6 +25,7 @@
 
 #include "../../include/b200grasp.h"
 #include "common.cuh"
+#include "sac_internal.cuh"
 
 using namespace b2g;
 
@@ -38,7 +39,8 @@ bool pdl_enabled() {
 
 thread_local std::string g_b2g_err;     // shared with bdq.cu
 #define g_err g_b2g_err
-static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+int b2g_fail(int code, const std::string& msg) { g_b2g_err = msg; return code; }
+static int fail(int code, const std::string& msg) { return b2g_fail(code, msg); }
 #define CK(call)                                                                                  \
   do {                                                                                            \
     cudaError_t e_ = (call);                                                                      \
@@ -87,106 +89,8 @@ int load_nccl(const char* path) {
   return 0;
 }
 
-struct Tensor {
-  std::string name;
-  int ndim;
-  int64_t shape[4];
-  int64_t numel;
-  int64_t off;    // float offset inside P
-  int group;      // 0 pi, 1 values, 2 ent, 3 target
-};
-
 int64_t pad32(int64_t n) { return (n + 31) / 32 * 32; }
 }  // namespace
-
-struct b2g_sac {
-  b2g_sac_cfg cfg{};
-  bool cnn = false;
-  int num_sms = 148;
-  int B = 0, A = 0, H = 0, E = 0, Cimg = 0, feat_dim = 0, FS = 0;
-  int Hi = 0, Wi = 0, H1 = 0, W1 = 0, H2 = 0, W2 = 0, H3 = 0, W3 = 0;
-  std::vector<Tensor> tensors;
-  std::map<std::string, int> tindex;
-  int64_t n_pi = 0, n_values = 0, n_ent = 0, n_target = 0, n_train = 0, n_all = 0;
-  float *P = nullptr, *Mo = nullptr, *Vo = nullptr, *G = nullptr;   // G has MET_COUNT extra floats (metrics ride the all-reduce)
-  float* metrics = nullptr;
-  cudaStream_t stream = nullptr;
-  std::vector<void*> allocs;
-  // replay
-  float *r_obs = nullptr, *r_next = nullptr, *r_act = nullptr, *r_rew = nullptr, *r_done = nullptr;
-  int64_t r_size = 0, r_pos = 0;
-  // normalisation
-  double *d_mean = nullptr, *d_istd = nullptr, *d_normc = nullptr;   // normc: ret_istd, clip_obs, clip_rew, norm_obs, norm_rew
-  double ret_istd = 1.0, clip_obs = 10.0, clip_rew = 10.0;
-  int norm_obs = 0, norm_rew = 0;
-  // batch buffers
-  float *x_obs = nullptr, *x_next = nullptr;
-  float *h1[3]{}, *h2[3]{}, *h3[3]{}, *F[3]{};
-  float *dZ4[2]{}, *dZ3p[2]{}, *dZ2p[2]{}, *dZ1[2]{};
-  float *z0[5]{}, *a0[4]{}, *dz1[4]{}, *dz0_pi = nullptr, *dz0_v3 = nullptr;
-  // BF16 hi/lo planes ([..][0] = hi, [..][1] = lo) of the tensors that feed forward / dgrad contractions
-  bool use_planes = false;
-  uint16_t *xp[2][2]{}, *h1p[3][2]{}, *h2p[3][2]{}, *h3p[3][2]{};
-  uint16_t *dZ4p[2][2]{}, *dZ3pp[2][2]{}, *dZ2pp[2][2]{}, *dZ1p[2][2]{};
-  bool wgrad_planes = false;
-  ColsumJob* d_colsum = nullptr;
-  int n_colsum = 0, colsum_ctas = 0;
-  uint16_t* wp[3][4][4]{};          // [net][cnn1,cnn2,cnn3,fc1][hi, lo, hiT, loT]
-  PlaneJob* d_jobs = nullptr;
-  int n_jobs = 0, job_tiles = 0;
-  bool planes_dirty = true;
-  long long* dbg_trace = nullptr;
-  std::map<const int*, std::vector<int>> host_tabs;   // host copies of the offset tables (contract checks at build time)
-  float *per_sample = nullptr, *pi_out = nullptr, *eps = nullptr, *rew_n = nullptr, *done_n = nullptr;
-  int* indices = nullptr;
-  float *s_obs = nullptr, *s_next = nullptr, *s_act = nullptr, *s_rew = nullptr, *s_done = nullptr;  // staged explicit batch
-  // pipelined host-batch path: the big obs / next_obs copies ping-pong on a copy stream
-  float *ps_obs[2]{}, *ps_next[2]{};
-  cudaStream_t cstream = nullptr;
-  cudaEvent_t ev_h2d[2]{}, ev_consumed[2]{}, ev_met[2]{};
-  float* pm_met[2]{};            // pinned: MET_COUNT floats + [log_alpha, grad log_alpha]
-  long long* pm_cnt[2]{};        // pinned counters
-  long long pipe_k = 0;
-  bool pipe_pending = false;
-  cudaEvent_t record_after_gather = nullptr;
-  long long* counters = nullptr;
-  double* step_consts = nullptr;
-  float* d_lr = nullptr;
-  float cur_lr = -1.f;
-  // launches
-  std::vector<GemmGroup> fwd_groups, bwd_groups, act_groups;
-  cudaGraphExec_t graph_exec = nullptr;
-  bool use_graph = true;
-  void* nccl_comm = nullptr;
-  void* nccl_comm2 = nullptr;          // second communicator: early all-reduce on the side stream
-  cudaStream_t side = nullptr;
-  cudaStream_t aux = nullptr;              // leaf work off the critical chain (zeroing, weight planes, leaf wgrads, bias sums)
-  cudaEvent_t ev_aux[7]{};
-  bool fork_leaves = false;
-  std::map<std::tuple<const void*, const void*, const void*, int>, int> col_ids;
-  bool tc_ranges = false;                  // contiguous cost-balanced tile ranges per CTA: measured SLOWER than round-robin
-                                           // (split-R tiles of one output pile their atomics onto one CTA); B2G_TC_RANGES=1 enables
-  bool early_opt = false;                  // early fc1/heads optimiser pass on the leaf branch: measured no gain (B2G_EARLY_OPT=1 enables)
-  bool fuse_fwd = false;                   // B2G_FUSE_FWD=1: the CNN forward chain as one layer-synchronised launch
-  unsigned* sync_ctr = nullptr;            // its completion counter (zeroed every step)
-  bool a_rowlanes = true;                  // conv1 fwd gather with row-major lane order (B2G_ROWLANES=0 disables)
-  bool fc0_split = true;                   // split-R heads_fc0 (needs z0 zeroed every step)
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  bool overlap_ar = false;
-  int ar_sms = 16;
-  ColsumJob* d_colsum_early = nullptr;
-  int n_colsum_early = 0, colsum_early_ctas = 0;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  float last_ms = 0.f;
-  int launches = 0;
-  std::vector<std::string> prof_names;
-  b2g_sac_metrics* h_metrics_pinned = nullptr;
-  float* h_met = nullptr;        // pinned MET_COUNT floats
-  long long* h_cnt = nullptr;    // pinned counters
-
-  float* p(const std::string& n) { return P + tensors[tindex.at(n)].off; }
-  float* g(const std::string& n) { return G + tensors[tindex.at(n)].off; }
-};
 
 namespace {
 
@@ -825,6 +729,10 @@ TailArgs make_tail(b2g_sac* h, bool want_per_sample) {
   t.gamma = h->cfg.gamma; t.target_entropy = h->cfg.target_entropy;
   t.grad_scale_B = h->B;
   t.z0_pi = h->z0[0]; t.z0_vf = h->z0[1]; t.z0_q1 = h->z0[2]; t.z0_q2 = h->z0[3]; t.z0_vt = h->z0[4];
+  t.z0v_ld = h->H;
+  if (h->v2.on && !h->v2_skip) {     // engine v2 writes the three value heads' fc0 outputs as one [B, 3H] block
+    t.z0_vf = h->v2.z0v; t.z0_q1 = h->v2.z0v + h->H; t.z0_q2 = h->v2.z0v + 2 * h->H; t.z0v_ld = 3 * h->H;
+  }
   t.pi = head_w(h, "model/pi", "dense");
   t.vf = head_w(h, "model/values_fn/vf", "vf");
   t.q1 = head_w(h, "model/values_fn/qf1", "qf1");
@@ -842,6 +750,7 @@ TailArgs make_tail(b2g_sac* h, bool want_per_sample) {
   t.a0_pi = h->a0[0]; t.a0_vf = h->a0[1]; t.a0_q1 = h->a0[2]; t.a0_q2 = h->a0[3];
   t.dz1_pi = h->dz1[0]; t.dz1_vf = h->dz1[1]; t.dz1_q1 = h->dz1[2]; t.dz1_q2 = h->dz1[3];
   t.dz0_pi = h->dz0_pi; t.dz0_v3 = h->dz0_v3;
+  if (h->v2.bwd) { for (int k = 0; k < 2; ++k) { t.dz0_pi_p[k] = h->v2.dz0pi[k]; t.dz0_v3_p[k] = h->v2.dz0v[k]; } }
   t.per_sample = want_per_sample ? h->per_sample : nullptr;
   t.pi_out = want_per_sample ? h->pi_out : nullptr;
   t.metrics = h->metrics;
@@ -906,7 +815,8 @@ int issue_step(b2g_sac* h, bool sampled, bool apply, bool want_per_sample, Prof*
     if (sampled) { ga.indices = nullptr; ga.rng_counters = h->counters; ga.seed = pa.seed; ga.indices_out = h->indices; }
     CK(cudaEventRecord(h->ev_aux[0], s));
     CK(cudaStreamWaitEvent(ax, h->ev_aux[0], 0));
-    if (h->use_planes) { planes_launch(h->d_jobs, h->n_jobs, h->job_tiles, ax); ++n; }
+    if (h->use_planes && !h->v2.bwd) { planes_launch(h->d_jobs, h->n_jobs, h->job_tiles, ax); ++n; }
+    if (h->v2.on) { if (int rc = v2_planes(h, ax)) return rc; ++n; }
     if (h->fc0_split) { CK(cudaMemsetAsync(h->z0[0], 0, (size_t)5 * h->B * h->H * sizeof(float), ax)); ++n; }
     if (h->fuse_fwd) { CK(cudaMemsetAsync(h->sync_ctr, 0, 32 * sizeof(unsigned), ax)); ++n; }
     CK(cudaEventRecord(h->ev_aux[1], ax));
@@ -916,7 +826,11 @@ int issue_step(b2g_sac* h, bool sampled, bool apply, bool want_per_sample, Prof*
   } else {
     prep_launch(pa, s); ++n; mark("prep");
   }
-  gather_launch(ga, s); ++n; mark("gather_normalize");
+  if (h->v2.on) {
+    if (!fork) { if (int rc = v2_planes(h, s)) return rc; ++n; mark("weight_planes_v2"); }
+    if (int rc = v2_gather(h, ga, s)) return rc;
+  } else gather_launch(ga, s);
+  ++n; mark("gather_normalize");
   if (h->record_after_gather) CK(cudaEventRecord(h->record_after_gather, s));   // staged batch consumed
   if (fork) CK(cudaStreamWaitEvent(s, h->ev_aux[1], 0));
   else {
@@ -952,7 +866,11 @@ int issue_step(b2g_sac* h, bool sampled, bool apply, bool want_per_sample, Prof*
     }
     return 0;
   };
-  for (auto& g : h->fwd_groups) if (int rc = run_group(g, s)) return rc;
+  if (h->v2.on) {
+    for (auto& g : h->v2.fwd) { if (int rc = v2_launch(h, g, s)) return rc; ++n; mark(g.name); }
+  } else {
+    for (auto& g : h->fwd_groups) if (int rc = run_group(g, s)) return rc;
+  }
   if (fork) CK(cudaStreamWaitEvent(s, h->ev_aux[6], 0));
   tail_launch(make_tail(h, want_per_sample), s); ++n; mark("heads_tail");
   const bool planes_bias = h->wgrad_planes && h->cfg.precision != B2G_PREC_FP32_SIMT;
@@ -969,15 +887,33 @@ int issue_step(b2g_sac* h, bool sampled, bool apply, bool want_per_sample, Prof*
     oa.metrics = h->metrics; oa.apply = apply ? 1 : 0;
     return oa;
   };
-  const bool overlap = h->overlap_ar && h->cnn && last_fc1 >= 0 && last_fc1 + 1 < (int)h->bwd_groups.size();
+  const bool overlap = !h->v2.bwd && h->overlap_ar && h->cnn && last_fc1 >= 0 && last_fc1 + 1 < (int)h->bwd_groups.size();
   const int64_t pi_fc1 = h->tensors[h->tindex.at("model/pi/" + std::string(h->cnn ? "cnn_fc1/w" : "fc0/kernel"))].off;
   const int64_t v_fc1 = h->tensors[h->tindex.at("model/values_fn/" + std::string(h->cnn ? "cnn_fc1/w" : "vf/fc0/kernel"))].off;
-  const bool early_opt = fork && h->early_opt && h->cfg.nranks == 1 && h->cnn && last_fc1 >= 0 && last_fc1 + 1 < (int)h->bwd_groups.size() &&
+  const bool early_opt = !h->v2.bwd && fork && h->early_opt && h->cfg.nranks == 1 && h->cnn && last_fc1 >= 0 && last_fc1 + 1 < (int)h->bwd_groups.size() &&
                          (pi_fc1 & 3) == 0 && (v_fc1 & 3) == 0;
   auto nccl_ck = [&](int rc) -> int {
     if (rc != 0) return fail(B2G_ENCCL, std::string("nccl: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
     return 0;
   };
+  if (h->v2.bwd) {
+    // backward chain on engine v2; the small head wgrads (fc0 / fc1 kernels and biases: fp32 operands, register-staged) stay
+    // on the v1 engine and, like the bias column sums, run on the leaf branch
+    for (auto& g : h->bwd_groups) {
+      if (g.name != "heads_wgrad") continue;
+      if (fork) { CK(cudaEventRecord(h->ev_aux[2], s)); CK(cudaStreamWaitEvent(ax, h->ev_aux[2], 0)); }
+      if (int rc = run_group(g, fork ? ax : s)) return rc;
+    }
+    for (auto& g : h->v2.bwd_groups) {
+      if (int rc = v2_launch(h, g, s)) return rc;
+      ++n; mark(g.name);
+      if (std::string(g.name) == "conv2_dgrad") {          // every gradient map exists: bias sums overlap the conv wgrads
+        if (fork) { CK(cudaEventRecord(h->ev_aux[4], s)); CK(cudaStreamWaitEvent(ax, h->ev_aux[4], 0)); }
+        if (int rc = v2_colsum(h, fork ? ax : s)) return rc;
+        ++n; if (!fork) mark("bias_grads");
+      }
+    }
+  } else
   for (size_t i = 0; i < h->bwd_groups.size(); ++i) {
     const bool leaf = fork && h->bwd_groups[i].name == "heads_wgrad";
     if (fork && planes_bias && i + 1 == h->bwd_groups.size()) {
@@ -1020,7 +956,7 @@ int issue_step(b2g_sac* h, bool sampled, bool apply, bool want_per_sample, Prof*
       }
     }
   }
-  if (planes_bias && !fork) { colsum_launch(h->d_colsum, h->n_colsum, h->colsum_ctas, s); ++n; mark("bias_grads"); }
+  if (planes_bias && !fork && !h->v2.bwd) { colsum_launch(h->d_colsum, h->n_colsum, h->colsum_ctas, s); ++n; mark("bias_grads"); }
   if (fork) { CK(cudaEventRecord(h->ev_aux[5], ax)); CK(cudaStreamWaitEvent(s, h->ev_aux[5], 0)); }
   if (h->cfg.nranks > 1) {
     if (overlap) {
@@ -1047,7 +983,7 @@ int issue_step(b2g_sac* h, bool sampled, bool apply, bool want_per_sample, Prof*
     oa.r_lo[1] = (int)h->n_pi; oa.r_hi[1] = (int)v_fc1;
   }
   optim_launch(oa, s); ++n; mark("adam_polyak");
-  if (h->use_planes && apply) {
+  if (h->use_planes && apply && !h->v2.bwd) {
     // with fork: refreshed on the aux branch at the head of the next step (the API entry points mark them stale)
     if (!fork) { planes_launch(h->d_jobs, h->n_jobs, h->job_tiles, s); ++n; mark("weight_planes"); }
   }
@@ -1059,7 +995,7 @@ int issue_step(b2g_sac* h, bool sampled, bool apply, bool want_per_sample, Prof*
 // BF16 planes of the CNN weights follow every optimiser step inside the step itself; after a host upload
 // (b2g_set_param) they are refreshed here, outside any graph.
 void refresh_planes(b2g_sac* h, bool for_step = false) {
-  if (for_step && h->fork_leaves) {     // the step refreshes the planes itself and leaves them one update behind
+  if (for_step && (h->fork_leaves || h->v2.bwd)) {     // the step refreshes the planes itself and leaves them one update behind
     h->planes_dirty = true;
     return;
   }
@@ -1232,6 +1168,13 @@ int b2g_sac_create(const b2g_sac_cfg* cfg, b2g_sac** out) {
     }
   }
   h->use_planes = h->cnn && cfg->precision != B2G_PREC_FP32_SIMT;
+  {   // engine v2 (TMA-fed, cg.cu) drives the forward chain of the parity mode; B2G_ENGINE=v1 keeps the round-1 engine
+    const char* en = getenv("B2G_ENGINE");
+    h->v2.on = h->cnn && cfg->precision == B2G_PREC_BF16X3 && !(en && en[0] == 'v' && en[1] == '1') && h->Hi == 64 && h->Wi == 64;
+    if (const char* dbg = getenv("B2G_CG_DEBUG")) h->v2.dbg = atoi(dbg);
+    { const char* eb = getenv("B2G_ENGINE_BWD"); h->v2.bwd = h->v2.on && !(eb && eb[0] == 'v' && eb[1] == '1'); }
+    if (h->v2.on && (rc = v2_alloc(h))) return bail(rc);
+  }
   if (const char* pl = getenv("B2G_TC_PLANES")) if (pl[0] == '0') h->use_planes = false;
   h->wgrad_planes = h->use_planes;
   if (const char* pl = getenv("B2G_TC_WGRAD_PLANES")) h->wgrad_planes = h->use_planes && pl[0] != '0';
@@ -1240,6 +1183,10 @@ int b2g_sac_create(const b2g_sac_cfg* cfg, b2g_sac** out) {
     for (int k = 0; k < 2; ++k) { DA(h->xp[0][k], nx); DA(h->xp[1][k], nx); }
     for (int n = 0; n < 3; ++n)
       for (int k = 0; k < 2; ++k) {
+        if (h->v2.on) {      // planes 0 / 1 of the v2 activations ARE the hi / lo planes the v1 backward reads
+          h->h1p[n][k] = h->v2.H1[n][k]; h->h2p[n][k] = h->v2.H2[n][k]; h->h3p[n][k] = h->v2.H3[n][k];
+          continue;
+        }
         DA(h->h1p[n][k], (size_t)B * h->H1 * h->W1 * 32); DA(h->h2p[n][k], (size_t)B * h->H2 * h->W2 * 64); DA(h->h3p[n][k], (size_t)B * 1024);
       }
     for (int n = 0; n < 2; ++n)
@@ -1259,7 +1206,7 @@ int b2g_sac_create(const b2g_sac_cfg* cfg, b2g_sac** out) {
   for (int n = 0; n < 3; ++n) DA(h->F[n], (size_t)B * h->FS);
   DA(h->z0[0], 5 * B * h->H);                      // one block: zeroed with a single memset per step
   for (int q = 1; q < 5; ++q) h->z0[q] = h->z0[0] + (size_t)q * B * h->H;
-  { const char* e = getenv("B2G_FC0_SPLIT"); h->fc0_split = !(e && atoi(e) == 0); }
+  { const char* e = getenv("B2G_FC0_SPLIT"); h->fc0_split = !(e && atoi(e) == 0) && !h->v2.on; }
   { const char* e = getenv("B2G_ROWLANES"); h->a_rowlanes = !(e && atoi(e) == 0); }
   { const char* e = getenv("B2G_FUSE_FWD"); h->fuse_fwd = e && atoi(e) != 0; }
   DA(h->sync_ctr, 32);
@@ -1300,6 +1247,7 @@ int b2g_sac_create(const b2g_sac_cfg* cfg, b2g_sac** out) {
       return bail(fail(B2G_ECUDA, "init copy failed"));
   }
   if ((rc = build_groups(h))) return bail(rc);
+  if (h->v2.on && (rc = v2_create(h))) return bail(rc);
   if (cfg->nranks > 1) {
     if (!cfg->nccl_id) return bail(fail(B2G_EINVAL, "nranks > 1 needs nccl_id"));
     if ((rc = load_nccl(cfg->nccl_lib))) return bail(rc);

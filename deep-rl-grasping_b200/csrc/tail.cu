@@ -12,6 +12,8 @@
 // reduced in shared memory and added to the gradient arena here.
 #include <math.h>
 
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace b2g {
@@ -113,6 +115,13 @@ __device__ __forceinline__ void bwd64xN(const float* const (&Ws)[N], const V2 (&
 }
 __device__ __forceinline__ V2 ld2(const float* p, int lane) { return V2{p[lane], p[lane + 32]}; }
 __device__ __forceinline__ void st2(float* p, int lane, V2 v) { p[lane] = v.lo; p[lane + 32] = v.hi; }
+// BF16 hi / lo planes of a 64-wide row (x = hi + lo to ~2^-17)
+__device__ __forceinline__ void st2_planes(uint16_t* hi, uint16_t* lo, int lane, V2 v) {
+  const __nv_bfloat16 h0 = __float2bfloat16_rn(v.lo), h1 = __float2bfloat16_rn(v.hi);
+  hi[lane] = __bfloat16_as_ushort(h0); hi[lane + 32] = __bfloat16_as_ushort(h1);
+  lo[lane] = __bfloat16_as_ushort(__float2bfloat16_rn(v.lo - __bfloat162float(h0)));
+  lo[lane + 32] = __bfloat16_as_ushort(__float2bfloat16_rn(v.hi - __bfloat162float(h1)));
+}
 // scalar head output: sum_i a[i]*ko[i] + bo
 __device__ __forceinline__ float out1(const float* __restrict__ ko, const float* __restrict__ bo, V2 a, int lane) {
   return warp_sum(a.lo * ko[lane] + a.hi * ko[lane + 32]) + bo[0];
@@ -190,8 +199,8 @@ __global__ void __launch_bounds__(WARPS * 32) tail_kernel(TailArgs t) {
 
   for (int b = blockIdx.x * WARPS + warp; b < t.B; b += gridDim.x * WARPS) {
     // every per-sample global read, issued as one batch
-    const V2 zpi = ld2(t.z0_pi + b * H, lane), zvf = ld2(t.z0_vf + b * H, lane), zvt = ld2(t.z0_vt + b * H, lane);
-    const V2 z0q1 = ld2(t.z0_q1 + b * H, lane), z0q2 = ld2(t.z0_q2 + b * H, lane);
+    const V2 zpi = ld2(t.z0_pi + b * H, lane), zvf = ld2(t.z0_vf + (size_t)b * t.z0v_ld, lane), zvt = ld2(t.z0_vt + b * H, lane);
+    const V2 z0q1 = ld2(t.z0_q1 + (size_t)b * t.z0v_ld, lane), z0q2 = ld2(t.z0_q2 + (size_t)b * t.z0v_ld, lane);
     const float rew_r = t.rew[b], done_r = t.done[b];
     float eps_r[AMAX], act_r[AMAX];
 #pragma unroll
@@ -318,6 +327,7 @@ __global__ void __launch_bounds__(WARPS * 32) tail_kernel(TailArgs t) {
       for (int k = 0; k < 3; ++k) {
         const V2 dz0{a0s[k].lo > 0.f ? dan[k].lo : 0.f, a0s[k].hi > 0.f ? dan[k].hi : 0.f};
         st2(t.dz0_v3 + (size_t)b * 3 * H + k * H, lane, dz0);
+        if (t.dz0_v3_p[0]) st2_planes(t.dz0_v3_p[0] + (size_t)b * 3 * H + k * H, t.dz0_v3_p[1] + (size_t)b * 3 * H + k * H, lane, dz0);
       }
       const V2 dz0p{a0_q1p.lo > 0.f ? dan[3].lo : 0.f, a0_q1p.hi > 0.f ? dan[3].hi : 0.f};
 #pragma unroll
@@ -355,6 +365,7 @@ __global__ void __launch_bounds__(WARPS * 32) tail_kernel(TailArgs t) {
       V2 da0 = bwd64(Wk1 + S_PI * H * LD, dz1, lane);
       V2 dz0{a0_pi.lo > 0.f ? da0.lo : 0.f, a0_pi.hi > 0.f ? da0.hi : 0.f};
       st2(t.dz0_pi + b * H, lane, dz0);
+      if (t.dz0_pi_p[0]) st2_planes(t.dz0_pi_p[0] + (size_t)b * H, t.dz0_pi_p[1] + (size_t)b * H, lane, dz0);
     }
     // a1 (= g etc.) needed by the fc1 wgrad contractions: store over a0? no -- fc1 wgrad uses a0 (its input)
   }

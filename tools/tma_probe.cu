@@ -123,7 +123,8 @@ static int run_load(const CUtensorMap& m, const CUtensorMap* dmap, int use_globa
 // value stored at element index i of a probe buffer: a bf16 bit pattern that is unique for i < 2^15 and never 0 / 0xCDCD
 static inline uint16_t val(size_t i) { return (uint16_t)(0x4000 + (i & 0x3FFF)); }
 
-int main() {
+int main(int argc, char** argv) {
+  const int only = argc > 1 ? atoi(argv[1]) : 0;   // 0 = the cases the engine relies on (1-3, 5, 6); 4, 7, 8, 9 = exploratory, one per process
   CK(cudaSetDevice(0));
   CK(cudaFree(0));
   cudaDriverEntryPointQueryResult q;
@@ -139,7 +140,7 @@ int main() {
   std::vector<uint16_t> got;
   auto sw_off = [](int r, int ch) { return r * 128 + ((ch ^ (r & 7)) << 4); };   // bytes
 
-  {   // ---- case 1: 2-D [rows=256][cols=512] bf16, box {64, 128}, SW128
+  if (only == 0 || only == 1) {   // ---- case 1: 2-D [rows=256][cols=512] bf16, box {64, 128}, SW128
     printf("case 1: 2-D tile, SWIZZLE_128B\n");
     CUtensorMap m;
     const uint64_t dims[2] = {512, 256}, str[1] = {512 * 2};
@@ -158,7 +159,7 @@ int main() {
       if (!flag || bad) ++fails;
     }
   }
-  {   // ---- case 2: h1 [B=8][15][15][32] bf16 viewed as {64 (two pixels x 32 ch), 14 (x), 15 (y), B}; strides {64 B, 15*64 B, 225*64 B}
+  if (only == 0 || only == 2) {   // ---- case 2: h1 [B=8][15][15][32] bf16 viewed as {64 (two pixels x 32 ch), 14 (x), 15 (y), B}; strides {64 B, 15*64 B, 225*64 B}
     printf("case 2: 4-D overlapping-stride view, element strides {1,2,2,1} (conv2 implicit im2col)\n");
     CUtensorMap m;
     const uint64_t dims[4] = {64, 14, 15, 8}, str[3] = {64, 15 * 64, 225 * 64};
@@ -184,7 +185,7 @@ int main() {
       }
     }
   }
-  {   // ---- case 3: dZ3 [B=8][4][4][64]; box {64, 6, 6, 3} starting at (0, -kx, -ky, b0): zero fill outside, batch overrun at the end
+  if (only == 0 || only == 3) {   // ---- case 3: dZ3 [B=8][4][4][64]; box {64, 6, 6, 3} starting at (0, -kx, -ky, b0): zero fill outside, batch overrun at the end
     printf("case 3: negative coordinates / OOB zero fill (conv3 dgrad view)\n");
     CUtensorMap m;
     const uint64_t dims[4] = {64, 4, 4, 8}, str[3] = {128, 4 * 128, 16 * 128};
@@ -211,7 +212,7 @@ int main() {
       }
     }
   }
-  {   // ---- case 4: image [B=4][64][64] (1 channel), patch view {8 kx, 8 ky, 8 j (pairs of output pixels: 16 B), 15 oy (4 rows), B}
+  if (only == 4) {   // ---- case 4: image [B=4][64][64] (1 channel), patch view {8 kx, 8 ky, 8 j (pairs of output pixels: 16 B), 15 oy (4 rows), B}
     printf("case 4: 5-D view of a 1-channel image (conv1: 8x8 patches, stride 4, even output columns)\n");
     CUtensorMap m;
     const uint64_t dims[5] = {8, 8, 8, 15, 4}, str[4] = {64 * 2, 8 * 2, 4 * 64 * 2, 4096 * 2};
@@ -239,7 +240,7 @@ int main() {
       if (!flag || bad) ++fails;
     }
   }
-  {   // ---- case 5: map in global memory
+  if (only == 0 || only == 5) {   // ---- case 5: map in global memory
     printf("case 5: tensor map resident in global memory\n");
     CUtensorMap m, *dm;
     const uint64_t dims[2] = {512, 256}, str[1] = {512 * 2};
@@ -258,7 +259,7 @@ int main() {
       if (!flag || bad) ++fails;
     }
   }
-  {   // ---- case 6: TMA store of a swizzled 32-row tile into a [256][512] tensor, partly out of range (rows clipped)
+  if (only == 0 || only == 6) {   // ---- case 6: TMA store of a swizzled 32-row tile into a [256][512] tensor, partly out of range (rows clipped)
     printf("case 6: TMA store (shared -> global), rows beyond the tensor are clipped\n");
     uint16_t* o;
     CK(cudaMalloc(&o, 256 * 512 * 2));
@@ -283,6 +284,58 @@ int main() {
         }
       printf("  mismatches=%d (outside the box / clipped rows: %d)\n", bad, outside);
       if (bad) ++fails;
+    }
+  }
+  if (only == 7) {   // ---- case 7: 3-D view with NON-MONOTONIC strides {kx 2 B, ky 128 B, j 16 B} (rank 3)
+    printf("case 7: 3-D non-monotonic strides\n");
+    CUtensorMap m;
+    const uint64_t dims[3] = {8, 8, 8}, str[2] = {128, 16};
+    const uint32_t box[3] = {8, 8, 8}, es[3] = {1, 1, 1};
+    if (!make_map(&m, d, 3, dims, str, box, es, CU_TENSOR_MAP_SWIZZLE_128B)) ++fails;
+    else {
+      CUtensorMap* dm; CK(cudaMalloc(&dm, sizeof(m))); CK(cudaMemcpy(dm, &m, sizeof(m), cudaMemcpyHostToDevice));
+      const int c[5] = {0, 0, 0, 0, 0};
+      // rank-3 loads go through the 4-D path of the probe kernel with a unit 4th coordinate: not available -> use rank 2 fallback? no: issue as 5-D is wrong.
+      printf("  (encode ok)\n");
+    }
+  }
+  if (only == 8) {   // ---- case 8: 5-D view, plain contiguous (monotonic) strides
+    printf("case 8: 5-D contiguous tensor\n");
+    CUtensorMap m;
+    const uint64_t dims[5] = {64, 4, 4, 4, 4}, str[4] = {128, 512, 2048, 8192};
+    const uint32_t box[5] = {64, 2, 2, 2, 2}, es[5] = {1, 1, 1, 1, 1};
+    if (!make_map(&m, d, 5, dims, str, box, es, CU_TENSOR_MAP_SWIZZLE_128B)) ++fails;
+    else {
+      const int c[5] = {0, 1, 1, 1, 1};
+      const int flag = run_load(m, nullptr, 0, 5, c, 16 * 128, got);
+      int bad = 0, r = 0;
+      for (int i4 = 0; i4 < 2; ++i4) for (int i3 = 0; i3 < 2; ++i3) for (int i2 = 0; i2 < 2; ++i2) for (int i1 = 0; i1 < 2; ++i1, ++r)
+        for (int e = 0; e < 64; ++e) {
+          const size_t gi = (size_t)(1 + i4) * 4096 + (1 + i3) * 1024 + (1 + i2) * 256 + (1 + i1) * 64 + e;
+          if (got[(sw_off(r, e / 8)) / 2 + (e % 8)] != val(gi)) ++bad;
+        }
+      printf("  completed=%d mismatches=%d\n", flag, bad);
+      if (!flag || bad) ++fails;
+    }
+  }
+  if (only == 9) {   // ---- case 9: conv1 through a space-to-depth image [b][16][16][16] : {32 = 2 px x 16, 2 dy (512 B), 15 ox (32 B), 15 oy (512 B), b}
+    printf("case 9: 5-D space-to-depth conv1 view (non-monotonic, repeated strides)\n");
+    CUtensorMap m;
+    const uint64_t dims[5] = {32, 2, 15, 15, 4}, str[4] = {512, 32, 512, 8192};
+    const uint32_t box[5] = {32, 2, 15, 8, 1}, es[5] = {1, 1, 1, 1, 1};
+    if (!make_map(&m, d, 5, dims, str, box, es, CU_TENSOR_MAP_SWIZZLE_128B)) ++fails;
+    else {
+      const int c[5] = {0, 0, 0, 0, 1};
+      const int rows = 120;
+      const int flag = run_load(m, nullptr, 0, 5, c, rows * 128, got);
+      int bad = 0;
+      for (int oy = 0; oy < 8; ++oy) for (int ox = 0; ox < 15; ++ox) for (int dy = 0; dy < 2; ++dy) for (int e = 0; e < 32; ++e) {
+        const int r = oy * 15 + ox, ee = dy * 32 + e;
+        const size_t gi = (size_t)4096 + (size_t)(oy + dy) * 256 + ox * 16 + e;
+        if (got[(sw_off(r, ee / 8)) / 2 + (ee % 8)] != val(gi)) ++bad;
+      }
+      printf("  completed=%d mismatches=%d\n", flag, bad);
+      if (!flag || bad) ++fails;
     }
   }
   printf("tma_probe: %s (%d failing cases)\n", fails ? "FAIL" : "ALL OK", fails);
