@@ -59,6 +59,9 @@ struct CgProblem {
   long long m_tm; int m0, m1, m2; long long m_base;    // mask element offset of (tm, r)
   int n_valid;                // columns < n_valid are stored (N of the problem)
   int grp_stride;             // element distance between consecutive 32-column groups of the output (32 = contiguous)
+  int grp_tab;                // 1: per-group output / mask offsets and row limits come from the tables below (conv2 dgrad: one
+                              //    accumulator column group per output-parity class)
+  int grp_off[8], grp_moff[8], grp_lim0[8], grp_lim1[8];
   int out_planes;             // planes written by ACT / DGRAD
   uint16_t* out_p[CG_MAX_PLANES];
   float* out_f;               // fp32 output (RAW / WGRAD; optional extra copy for ACT), same offsets, ld = o0-based

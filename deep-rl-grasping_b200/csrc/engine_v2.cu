@@ -56,6 +56,39 @@ __global__ void __launch_bounds__(256) gather2_kernel(Gather2Args a) {
   const float scale = g.scale;
   uint16_t* s0 = sm_planes; uint16_t* s1 = s0 + npx; uint16_t* s2 = s1 + npx;
   uint16_t* xh = a.xp[which][0]; uint16_t* xl = a.xp[which][1];
+  auto put_feature = [&](float yy) {                         // direct feature -> column 512 of the feature rows
+    uint16_t p0, p1, p2;
+    split3(yy, p0, p1, p2);
+    const size_t fo = (size_t)b * g.FS + g.feat_col, po = (size_t)b * a.KF + g.feat_col;
+    if (which) { g.F_t[fo] = yy; a.fp[2][0][po] = p0; a.fp[2][1][po] = p1; a.fp[2][2][po] = p2; }
+    else {
+      g.F_pi[fo] = yy; g.F_v[fo] = yy;
+      a.fp[0][0][po] = p0; a.fp[0][1][po] = p1; a.fp[0][2][po] = p2;
+      a.fp[1][0][po] = p0; a.fp[1][1][po] = p1; a.fp[1][2][po] = p2;
+    }
+  };
+  if (Cfull == 2) {
+    // depth configuration: a 16-byte group is {pixel, actuator, pixel, actuator}; the float64 chain runs on the two image
+    // values only (the actuator plane is read at pixel [0,0] alone), no run-time div/mod, packed 4-byte plane stores
+    for (int e4 = tid; e4 < (E >> 2); e4 += blockDim.x) {
+      const float4 v = *reinterpret_cast<const float4*>(src + 4 * e4);
+      float y0 = v.x, y1 = v.z;
+      if (norm_obs) {
+        const double2 m0 = *reinterpret_cast<const double2*>(g.mean + 4 * e4), m1 = *reinterpret_cast<const double2*>(g.mean + 4 * e4 + 2);
+        const double2 i0 = *reinterpret_cast<const double2*>(g.var + 4 * e4), i1 = *reinterpret_cast<const double2*>(g.var + 4 * e4 + 2);
+        y0 = (float)fmin(fmax(((double)y0 - m0.x) * i0.x, -clip_obs), clip_obs);
+        y1 = (float)fmin(fmax(((double)y1 - m1.x) * i1.x, -clip_obs), clip_obs);
+        if (e4 == 0) put_feature((float)fmin(fmax(((double)v.y - m0.y) * i0.y, -clip_obs), clip_obs) / scale);
+      } else if (e4 == 0) put_feature(v.y / scale);
+      y0 = y0 / scale; y1 = y1 / scale;
+      uint16_t a0, a1, a2, b0, b1, b2;
+      split3(y0, a0, a1, a2);
+      split3(y1, b0, b1, b2);
+      const uint32_t w0 = (uint32_t)a0 | ((uint32_t)b0 << 16), w1 = (uint32_t)a1 | ((uint32_t)b1 << 16), w2 = (uint32_t)a2 | ((uint32_t)b2 << 16);
+      reinterpret_cast<uint32_t*>(s0)[e4] = w0; reinterpret_cast<uint32_t*>(s1)[e4] = w1; reinterpret_cast<uint32_t*>(s2)[e4] = w2;
+      if (xh) { reinterpret_cast<uint32_t*>(xh + (size_t)b * npx)[e4] = w0; reinterpret_cast<uint32_t*>(xl + (size_t)b * npx)[e4] = w1; }
+    }
+  } else
   for (int e4 = tid; e4 < (E >> 2); e4 += blockDim.x) {
     const float4 v = *reinterpret_cast<const float4*>(src + 4 * e4);
     float y[4] = {v.x, v.y, v.z, v.w};
@@ -67,37 +100,31 @@ __global__ void __launch_bounds__(256) gather2_kernel(Gather2Args a) {
       float yy = y[j];
       if (norm_obs) yy = (float)fmin(fmax(((double)yy - g.mean[e]) * g.var[e], -clip_obs), clip_obs);
       yy = yy / scale;
-      uint16_t p0, p1, p2;
-      split3(yy, p0, p1, p2);
       if (c < Ci) {
+        uint16_t p0, p1, p2;
+        split3(yy, p0, p1, p2);
         const int o = pix * Ci + c;
         s0[o] = p0; s1[o] = p1; s2[o] = p2;
         if (xh) { xh[(size_t)b * npx + o] = p0; xl[(size_t)b * npx + o] = p1; }
-      } else {                                                // direct feature -> column 512 of the feature rows
-        const size_t fo = (size_t)b * g.FS + g.feat_col, po = (size_t)b * a.KF + g.feat_col;
-        if (which) { g.F_t[fo] = yy; a.fp[2][0][po] = p0; a.fp[2][1][po] = p1; a.fp[2][2][po] = p2; }
-        else {
-          g.F_pi[fo] = yy; g.F_v[fo] = yy;
-          a.fp[0][0][po] = p0; a.fp[0][1][po] = p1; a.fp[0][2][po] = p2;
-          a.fp[1][0][po] = p0; a.fp[1][1][po] = p1; a.fp[1][2][po] = p2;
-        }
-      }
+      } else put_feature(yy);
     }
   }
   __syncthreads();
   // patch rows: for output pixel (oy, ox) and kernel row ky the 8*Ci elements (kx, ci) are contiguous in the NHWC plane
   const int seg = 8 * Ci;                                     // elements per (patch, ky) run: 16 B (Ci = 1) .. 64 B (Ci = 4)
   const int K1 = 64 * Ci, nruns = a.OH * a.OW * 8;
-  for (int pl = 0; pl < 3; ++pl) {
-    const uint16_t* sp = sm_planes + pl * npx;
-    uint16_t* dst = a.a1[which][pl] + (size_t)b * a.OH * a.OW * K1;
-    for (int i = tid; i < nruns * (seg / 8); i += blockDim.x) {
-      const int part = i % (seg / 8), run = i / (seg / 8);    // 16-byte pieces of a run
-      const int ky = run & 7, patch = run >> 3;
-      const int oy = patch / a.OW, ox = patch - oy * a.OW;
-      const int so = ((4 * oy + ky) * g.W + 4 * ox) * Ci + 8 * part;       // 8-byte aligned at least
-      const uint2 lo = *reinterpret_cast<const uint2*>(sp + so), hi = *reinterpret_cast<const uint2*>(sp + so + 4);
-      *reinterpret_cast<uint4*>(dst + (size_t)patch * K1 + ky * seg + 8 * part) = make_uint4(lo.x, lo.y, hi.x, hi.y);
+  const size_t img = (size_t)b * a.OH * a.OW * K1;
+  for (int i = tid; i < nruns * (seg / 8); i += blockDim.x) {
+    const int part = i % (seg / 8), run = i / (seg / 8);      // 16-byte pieces of a run
+    const int ky = run & 7, patch = run >> 3;
+    const int oy = patch / a.OW, ox = patch - oy * a.OW;
+    const int so = ((4 * oy + ky) * g.W + 4 * ox) * Ci + 8 * part;         // 8-byte aligned at least
+    const size_t go = img + (size_t)patch * K1 + ky * seg + 8 * part;
+#pragma unroll
+    for (int pl = 0; pl < 3; ++pl) {
+      const uint16_t* sp = sm_planes + pl * npx + so;
+      const uint2 lo = *reinterpret_cast<const uint2*>(sp), hi = *reinterpret_cast<const uint2*>(sp + 4);
+      *reinterpret_cast<uint4*>(a.a1[which][pl] + go) = make_uint4(lo.x, lo.y, hi.x, hi.y);
     }
   }
   if (which == 0 && g.act) {
@@ -494,6 +521,7 @@ int v2_create(b2g_sac* h) {
       P.tiles_m = (B + 127) / 128; P.tiles_n = Nn / 64;
       P.epi = CG_EPI_RAW; P.rows_tile = 128; P.lim_rows = B;
       P.o_tm = (long long)128 * Nn; P.o0 = Nn; P.n_valid = Nn;
+      P.splits = P.chunks; P.atomic = 1;      // one K-chunk per CTA, fp32 red.add into the zeroed z0 block (10 serial 9-chunk tiles otherwise)
       P.out_f = z0out[n];
       g.host[g.n++] = P;
     }
@@ -608,31 +636,42 @@ int v2_create(b2g_sac* h) {
       }
       if (int rc = push_group(h, v.bwd_groups, g, "conv3_bwd")) return rc;
     }
-    // ---- conv2 dgrad: the four output-parity classes of the stride-2 convolution, both nets (8 problems)
+    // ---- conv2 dgrad: the four output-parity classes of the stride-2 convolution share their A operand (the gradient map
+    // shifted by (-jy, -jx), zero-filled outside), so ONE tile computes all four: B = [W(py,px)] stacked along N
+    // (4 x 32 input channels = 128 accumulator columns, two boxes of 64 rows), one 32-column group per class, each with
+    // its own output offset and row limits (classes with 7 rows / columns mask the 8th).
     {
       CgGroup g;
-      for (int py = 0; py < 2; ++py)
-        for (int px = 0; px < 2; ++px) {
-          const int ny = (15 - py + 1) / 2, nx = (15 - px + 1) / 2;
-          for (int n = 0; n < 2; ++n) {
-            const int mA = add_maps(v, v.dZ2[n], NB, 4, {64, 6, 6, (uint64_t)B}, {128, 768, 4608}, {64, (uint32_t)nx, (uint32_t)ny, 2});
-            const int mB = add_maps(v, v.W2n[n], NB, 2, {64, 512}, {128}, {64, 32});
-            if (mA < 0 || mB < 0) return b2g_fail(B2G_ECUDA, "engine v2: cuTensorMapEncodeTiled failed (conv2 dgrad)");
-            CgProblem P = kmajor(NB, 32, 4, 2, 2 * ny * nx);
-            P.nloads = 2;
-            P.ld[0] = mk_load(mA, 4, 0); P.ld[0].d_tm[3] = 2; P.ld[0].d_c1[2] = -1; P.ld[0].d_c2[1] = -1;
-            P.ld[1] = mk_load(mB, 2, P.b_off); P.ld[1].c0[1] = (py * 4 + px) * 32; P.ld[1].d_c1[1] = 256; P.ld[1].d_c2[1] = 64;
-            P.tiles_m = (B + 1) / 2;
-            P.epi = CG_EPI_DGRAD; P.rows_tile = 2 * ny * nx; P.lim_rows = B * ny * nx;
-            P.d0 = nx; P.d1 = ny;
-            P.o_tm = 2 * 225 * 64; P.o0 = 2 * 64; P.o1 = 2 * 15 * 64; P.o2 = 225 * 64; P.o_base = (py * 15 + px) * 64 + n * 32;
-            P.m_tm = 2 * 225 * 32; P.m0 = 2 * 32; P.m1 = 2 * 15 * 32; P.m2 = 225 * 32; P.m_base = (py * 15 + px) * 32;
-            P.n_valid = 32; P.out_planes = 2;
-            for (int p = 0; p < 2; ++p) P.out_p[p] = v.dZ1[p];
-            P.mask = v.H1[n][0];
-            g.host[g.n++] = P;
-          }
+      for (int n = 0; n < 2; ++n) {
+        const int mA = add_maps(v, v.dZ2[n], NB, 4, {64, 6, 6, (uint64_t)B}, {128, 768, 4608}, {64, 8, 8, 2});
+        const int mB = add_maps(v, v.W2n[n], NB, 2, {64, 512}, {128}, {64, 64});
+        if (mA < 0 || mB < 0) return b2g_fail(B2G_ECUDA, "engine v2: cuTensorMapEncodeTiled failed (conv2 dgrad)");
+        CgProblem P = kmajor(NB, 128, 4, 2, 128);
+        P.tx_bytes = NB * (128 * 128 + 2 * 64 * 128);
+        P.nloads = 3;
+        P.ld[0] = mk_load(mA, 4, 0); P.ld[0].d_tm[3] = 2; P.ld[0].d_c1[2] = -1; P.ld[0].d_c2[1] = -1;
+        // kernel positions (ky, kx) = (py + 2 jy, px + 2 jx): rows ((2 jy) * 4 + 2 jx) * 32 .. hold (py = 0; px = 0, 1), + 128 rows (py = 1)
+        for (int py = 0; py < 2; ++py) {
+          P.ld[1 + py] = mk_load(mB, 2, P.b_off + py * 64 * 128);
+          P.ld[1 + py].c0[1] = py * 128; P.ld[1 + py].d_c1[1] = 256; P.ld[1 + py].d_c2[1] = 64;
         }
+        P.tiles_m = (B + 1) / 2;
+        P.epi = CG_EPI_DGRAD; P.rows_tile = 128; P.lim_rows = B * 64;
+        P.d0 = 8; P.d1 = 8;
+        P.o_tm = 2 * 225 * 64; P.o0 = 2 * 64; P.o1 = 2 * 15 * 64; P.o2 = 225 * 64; P.o_base = n * 32;
+        P.m_tm = 2 * 225 * 32; P.m0 = 2 * 32; P.m1 = 2 * 15 * 32; P.m2 = 225 * 32; P.m_base = 0;
+        P.grp_tab = 1;
+        for (int py = 0; py < 2; ++py)
+          for (int px = 0; px < 2; ++px) {
+            const int gg = py * 2 + px;
+            P.grp_off[gg] = (py * 15 + px) * 64; P.grp_moff[gg] = (py * 15 + px) * 32;
+            P.grp_lim0[gg] = (15 - px + 1) / 2; P.grp_lim1[gg] = (15 - py + 1) / 2;
+          }
+        P.n_valid = 128; P.out_planes = 2;
+        for (int p = 0; p < 2; ++p) P.out_p[p] = v.dZ1[p];
+        P.mask = v.H1[n][0];
+        g.host[g.n++] = P;
+      }
       if (int rc = push_group(h, v.bwd_groups, g, "conv2_dgrad")) return rc;
     }
     // ---- conv2 + conv1 wgrad (MN-major, reduction over batch x pixels, split-K with fp32 red.add)
@@ -711,7 +750,7 @@ int v2_gather(b2g_sac* h, const GatherArgs& ga, cudaStream_t s) {
   a.g = ga;
   for (int w = 0; w < 2; ++w) {
     for (int p = 0; p < 3; ++p) a.a1[w][p] = v.A1[w][p];
-    a.xp[w][0] = h->xp[w][0]; a.xp[w][1] = h->xp[w][1];
+    a.xp[w][0] = v.bwd ? nullptr : h->xp[w][0]; a.xp[w][1] = v.bwd ? nullptr : h->xp[w][1];
   }
   for (int n = 0; n < 3; ++n) for (int p = 0; p < 3; ++p) a.fp[n][p] = v.F[n][p];
   a.KF = v.KF; a.Ci = h->Cimg; a.OH = h->H1; a.OW = h->W1;

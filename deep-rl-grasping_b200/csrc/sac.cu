@@ -817,7 +817,8 @@ int issue_step(b2g_sac* h, bool sampled, bool apply, bool want_per_sample, Prof*
     CK(cudaStreamWaitEvent(ax, h->ev_aux[0], 0));
     if (h->use_planes && !h->v2.bwd) { planes_launch(h->d_jobs, h->n_jobs, h->job_tiles, ax); ++n; }
     if (h->v2.on) { if (int rc = v2_planes(h, ax)) return rc; ++n; }
-    if (h->fc0_split) { CK(cudaMemsetAsync(h->z0[0], 0, (size_t)5 * h->B * h->H * sizeof(float), ax)); ++n; }
+    if (h->fc0_split || h->v2.on) { CK(cudaMemsetAsync(h->z0[0], 0, (size_t)5 * h->B * h->H * sizeof(float), ax)); ++n; }
+    if (h->v2.on) { CK(cudaMemsetAsync(h->v2.z0v, 0, (size_t)3 * h->B * h->H * sizeof(float), ax)); ++n; }
     if (h->fuse_fwd) { CK(cudaMemsetAsync(h->sync_ctr, 0, 32 * sizeof(unsigned), ax)); ++n; }
     CK(cudaEventRecord(h->ev_aux[1], ax));
     prep_launch(pa, ax); ++n;
@@ -835,7 +836,8 @@ int issue_step(b2g_sac* h, bool sampled, bool apply, bool want_per_sample, Prof*
   if (fork) CK(cudaStreamWaitEvent(s, h->ev_aux[1], 0));
   else {
     CK(cudaMemsetAsync(h->G, 0, (size_t)(h->n_train + MET_COUNT) * sizeof(float), s)); ++n;
-    if (h->fc0_split) { CK(cudaMemsetAsync(h->z0[0], 0, (size_t)5 * h->B * h->H * sizeof(float), s)); ++n; }
+    if (h->fc0_split || h->v2.on) { CK(cudaMemsetAsync(h->z0[0], 0, (size_t)5 * h->B * h->H * sizeof(float), s)); ++n; }
+    if (h->v2.on) { CK(cudaMemsetAsync(h->v2.z0v, 0, (size_t)3 * h->B * h->H * sizeof(float), s)); ++n; }
     if (h->fuse_fwd) { CK(cudaMemsetAsync(h->sync_ctr, 0, 32 * sizeof(unsigned), s)); ++n; }
     mark("zero_grads");
   }

@@ -386,6 +386,275 @@ __global__ void __launch_bounds__(WARPS * 32) tail_kernel(TailArgs t) {
   if (tid < MET_GN_PI) atomicAdd(t.metrics + tid, red[tid]);
 }
 
+
+// ================================================================================================
+// tail4: the same per-sample arithmetic as tail_kernel, with the sample's work split over FOUR warps
+// (actor | vf + target vf | qf1 | qf2) that exchange a handful of scalars through shared memory and three
+// named barriers.  A warp's duration is its dependency chain: 12 serial 64x64 mat-vecs became 4 (actor fc1 ->
+// qf1-at-pi fc1 -> qf1-at-pi fc1^T -> actor fc1^T), and 128 CTAs instead of 32 occupy the GPU.
+// Every expression is evaluated exactly as in tail_kernel (same order inside each mat-vec and reduction).
+// ================================================================================================
+__device__ __forceinline__ void bar_group(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+
+__global__ void __launch_bounds__(WARPS * 32) tail4_kernel(TailArgs t) {
+  extern __shared__ float smem[];
+  float* Wk1 = smem;
+  float* acc = Wk1 + S_NW * H * LD;
+  const int A = t.A;
+  const int n_acc = 2 * H * A + 2 * A + 3 * (H + 1);
+  float* red = acc + n_acc;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  pdl_trigger();
+  pdl_wait();
+  const float* k1s[S_NW] = {t.pi.k1, t.vf.k1, t.q1.k1, t.q2.k1, t.vt.k1};
+  for (int w = 0; w < S_NW; ++w)
+    for (int i = tid; i < H * H; i += blockDim.x) {
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&Wk1[w * H * LD + (i >> 6) * LD + (i & 63)]);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(k1s[w] + i) : "memory");
+    }
+  float* sp = red + ((MET_COUNT + 1 + 3) & ~3);
+  auto stage = [&](float* dst, const float* src, int n) {
+    for (int i = tid; i < n; i += blockDim.x) {
+      const uint32_t d32 = (uint32_t)__cvta_generic_to_shared(dst + i);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d32), "l"(src + i) : "memory");
+    }
+  };
+  const HeadW* hw[S_NW] = {&t.pi, &t.vf, &t.q1, &t.q2, &t.vt};
+  float* s_b0[S_NW]; float* s_b1[S_NW];
+  for (int w = 0; w < S_NW; ++w) {
+    s_b0[w] = sp + w * 2 * H; s_b1[w] = s_b0[w] + H;
+    stage(s_b0[w], hw[w]->b0, H); stage(s_b1[w], hw[w]->b1, H);
+  }
+  float* s_pi_ko = sp + S_NW * 2 * H;
+  float* s_ksig = s_pi_ko + H * A;
+  float* s_pi_bo = s_ksig + H * A;
+  float* s_bsig = s_pi_bo + A;
+  float* s_vko[4];
+  s_vko[0] = s_bsig + A;
+  for (int w = 1; w < 4; ++w) s_vko[w] = s_vko[w - 1] + H + 1;
+  float* s_q1act = s_vko[3] + H + 1;
+  float* s_q2act = s_q1act + A * H;
+  float* scratch = s_q2act + A * H;               // 2 sample groups x 32 floats
+  stage(s_pi_ko, t.pi.ko, H * A); stage(s_ksig, t.ksig, H * A); stage(s_pi_bo, t.pi.bo, A); stage(s_bsig, t.bsig, A);
+  {
+    const HeadW* vh[4] = {&t.vf, &t.q1, &t.q2, &t.vt};
+    for (int w = 0; w < 4; ++w) { stage(s_vko[w], vh[w]->ko, H); stage(s_vko[w] + H, vh[w]->bo, 1); }
+  }
+  stage(s_q1act, t.q1.k0 + (size_t)t.feat_dim * H, A * H);
+  stage(s_q2act, t.q2.k0 + (size_t)t.feat_dim * H, A * H);
+  for (int i = tid; i < n_acc + MET_COUNT + 1; i += blockDim.x) acc[i] = 0.f;
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncthreads();
+
+  float* a_kmu = acc;
+  float* a_ksig = a_kmu + H * A;
+  float* a_bmu = a_ksig + H * A;
+  float* a_bsig = a_bmu + A;
+  float* a_vf = a_bsig + A;
+  float* a_q1 = a_vf + H + 1;
+  float* a_q2 = a_q1 + H + 1;
+  const float invB = 1.0f / (float)t.grad_scale_B;
+  const float log_alpha = t.log_alpha[0];
+  const float alpha = expf(log_alpha);
+  const int sg = warp >> 2, role = warp & 3, barid = 1 + sg;
+  float* sc = scratch + sg * 32;          // [0..7] pi, [8] logp, [9] q1p, [10] q2p, [11] v_targ, [16..23] dpi
+
+  for (int b = blockIdx.x * 2 + sg; b < t.B; b += gridDim.x * 2) {
+    if (role == 0) {
+      // ------------------------------------------------------------------ actor
+      const V2 zpi = ld2(t.z0_pi + b * H, lane);
+      float eps_r[AMAX];
+#pragma unroll
+      for (int a = 0; a < AMAX; ++a) eps_r[a] = a < A ? t.eps[b * A + a] : 0.f;
+      const V2 a0_pi = relu2(V2{zpi.lo + s_b0[S_PI][lane], zpi.hi + s_b0[S_PI][lane + 32]});
+      st2(t.a0_pi + b * H, lane, a0_pi);
+      const V2 g = relu2(fwd64(Wk1 + S_PI * H * LD, s_b1[S_PI], a0_pi, lane));
+      float mu[AMAX], ls_raw[AMAX], ls[AMAX], sd[AMAX], pi[AMAX], tt[AMAX];
+      float logp = 0.f, ent = 0.f;
+#pragma unroll
+      for (int a = 0; a < AMAX; ++a) {
+        if (a < A) {
+          mu[a] = warp_sum(g.lo * s_pi_ko[lane * A + a] + g.hi * s_pi_ko[(lane + 32) * A + a]) + s_pi_bo[a];
+          ls_raw[a] = warp_sum(g.lo * s_ksig[lane * A + a] + g.hi * s_ksig[(lane + 32) * A + a]) + s_bsig[a];
+          ls[a] = fminf(fmaxf(ls_raw[a], LS_MIN), LS_MAX);
+          sd[a] = expf(ls[a]);
+          const float u = mu[a] + eps_r[a] * sd[a];
+          tt[a] = (u - mu[a]) / (sd[a] + EPSF);
+          pi[a] = tanhf(u);
+          logp += -0.5f * (tt[a] * tt[a] + 2.f * ls[a] + 1.8378770664093453f) - logf(1.f - pi[a] * pi[a] + EPSF);
+          ent += ls[a] + 1.4189385332046727f;
+          if (lane == a) sc[a] = pi[a];
+        }
+      }
+      if (lane == 0) sc[8] = logp;
+      bar_group(barid);                                    // A: pi, logp published
+      bar_group(barid);                                    // B: q1p, q2p, v_targ published
+      const float q1p = sc[9];
+      if (lane == 0) {
+        atomicAdd(&red[MET_POLICY_LOSS], (alpha * logp - q1p) * invB);
+        atomicAdd(&red[MET_ENT_COEF_LOSS], -log_alpha * (logp + t.target_entropy) * invB);
+        atomicAdd(&red[MET_ENTROPY], ent * invB);
+        atomicAdd(&red[MET_MEAN_LOGP], logp * invB);
+        atomicAdd(&red[MET_COUNT], -(logp + t.target_entropy) * invB);
+        if (t.per_sample) t.per_sample[3 * t.B + b] = logp;
+      }
+      if (t.pi_out && lane < A) {
+        float pv = 0.f;
+#pragma unroll
+        for (int a = 0; a < AMAX; ++a) if (a == lane) pv = pi[a];
+        t.pi_out[b * A + lane] = pv;
+      }
+      bar_group(barid);                                    // C: dpi published
+      float dmu[AMAX], dls[AMAX];
+      V2 dg{0.f, 0.f};
+#pragma unroll
+      for (int a = 0; a < AMAX; ++a) {
+        if (a < A) {
+          const float dpi = sc[16 + a];
+          const float one_m = 1.f - pi[a] * pi[a];
+          const float du = (alpha * invB) * 2.f * pi[a] * one_m / (one_m + EPSF) + dpi * one_m;
+          dmu[a] = du;
+          const float spe = sd[a] + EPSF;
+          float d = du * eps_r[a] * sd[a] + (alpha * invB) * (-tt[a] * eps_r[a] * sd[a] * EPSF / (spe * spe) - 1.f);
+          dls[a] = (ls_raw[a] >= LS_MIN && ls_raw[a] <= LS_MAX) ? d : 0.f;
+          atomicAdd(&a_kmu[lane * A + a], g.lo * dmu[a]);
+          atomicAdd(&a_kmu[(lane + 32) * A + a], g.hi * dmu[a]);
+          atomicAdd(&a_ksig[lane * A + a], g.lo * dls[a]);
+          atomicAdd(&a_ksig[(lane + 32) * A + a], g.hi * dls[a]);
+          if (lane == 0) { atomicAdd(&a_bmu[a], dmu[a]); atomicAdd(&a_bsig[a], dls[a]); }
+          dg.lo += dmu[a] * s_pi_ko[lane * A + a] + dls[a] * s_ksig[lane * A + a];
+          dg.hi += dmu[a] * s_pi_ko[(lane + 32) * A + a] + dls[a] * s_ksig[(lane + 32) * A + a];
+        }
+      }
+      const V2 dz1{g.lo > 0.f ? dg.lo : 0.f, g.hi > 0.f ? dg.hi : 0.f};
+      st2(t.dz1_pi + b * H, lane, dz1);
+      const V2 da0 = bwd64(Wk1 + S_PI * H * LD, dz1, lane);
+      const V2 dz0{a0_pi.lo > 0.f ? da0.lo : 0.f, a0_pi.hi > 0.f ? da0.hi : 0.f};
+      st2(t.dz0_pi + b * H, lane, dz0);
+      if (t.dz0_pi_p[0]) st2_planes(t.dz0_pi_p[0] + (size_t)b * H, t.dz0_pi_p[1] + (size_t)b * H, lane, dz0);
+    } else if (role == 1) {
+      // ------------------------------------------------------------------ vf + target vf
+      const V2 zvf = ld2(t.z0_vf + (size_t)b * t.z0v_ld, lane), zvt = ld2(t.z0_vt + b * H, lane);
+      const V2 a0_vf = relu2(V2{zvf.lo + s_b0[S_VF][lane], zvf.hi + s_b0[S_VF][lane + 32]});
+      const V2 a0_vt = relu2(V2{zvt.lo + s_b0[S_VT][lane], zvt.hi + s_b0[S_VT][lane + 32]});
+      V2 a1_vf, a1_vt;
+      {
+        const float* const Wn[2] = {Wk1 + S_VF * H * LD, Wk1 + S_VT * H * LD};
+        const float* const bn[2] = {s_b1[S_VF], s_b1[S_VT]};
+        const V2 an[2] = {a0_vf, a0_vt};
+        V2 on[2];
+        fwd64xN<2>(Wn, bn, an, on, lane);
+        a1_vf = relu2(on[0]); a1_vt = relu2(on[1]);
+      }
+      const float v = out1(s_vko[0], s_vko[0] + H, a1_vf, lane);
+      const float v_targ = out1(s_vko[3], s_vko[3] + H, a1_vt, lane);
+      if (lane == 0) sc[11] = v_targ;
+      bar_group(barid);                                    // A
+      bar_group(barid);                                    // B
+      const float v_backup = fminf(sc[9], sc[10]) - alpha * sc[8];
+      const float ev = v - v_backup;
+      if (lane == 0) {
+        atomicAdd(&red[MET_VALUE_LOSS], 0.5f * ev * ev * invB);
+        atomicAdd(&red[MET_MEAN_V], v * invB);
+        if (t.per_sample) { t.per_sample[2 * t.B + b] = v; t.per_sample[4 * t.B + b] = v_targ; }
+      }
+      st2(t.a0_vf + b * H, lane, a0_vf);
+      const float dout = ev * invB;
+      atomicAdd(&a_vf[lane], a1_vf.lo * dout);
+      atomicAdd(&a_vf[lane + 32], a1_vf.hi * dout);
+      if (lane == 0) atomicAdd(&a_vf[H], dout);
+      const V2 dz1{a1_vf.lo > 0.f ? dout * s_vko[0][lane] : 0.f, a1_vf.hi > 0.f ? dout * s_vko[0][lane + 32] : 0.f};
+      st2(t.dz1_vf + b * H, lane, dz1);
+      const V2 da = bwd64(Wk1 + S_VF * H * LD, dz1, lane);
+      const V2 dz0{a0_vf.lo > 0.f ? da.lo : 0.f, a0_vf.hi > 0.f ? da.hi : 0.f};
+      st2(t.dz0_v3 + (size_t)b * 3 * H, lane, dz0);
+      if (t.dz0_v3_p[0]) st2_planes(t.dz0_v3_p[0] + (size_t)b * 3 * H, t.dz0_v3_p[1] + (size_t)b * 3 * H, lane, dz0);
+      bar_group(barid);                                    // C
+    } else {
+      // ------------------------------------------------------------------ qf1 (role 2) / qf2 (role 3)
+      const bool isq1 = role == 2;
+      const int SQ = isq1 ? S_Q1 : S_Q2;
+      const float* z0p = isq1 ? t.z0_q1 : t.z0_q2;
+      const float* sact = isq1 ? s_q1act : s_q2act;
+      const float* sko = isq1 ? s_vko[1] : s_vko[2];
+      float* aacc = isq1 ? a_q1 : a_q2;
+      const V2 z0q = ld2(z0p + (size_t)b * t.z0v_ld, lane);
+      const float rew_r = t.rew[b], done_r = t.done[b];
+      float act_r[AMAX];
+#pragma unroll
+      for (int a = 0; a < AMAX; ++a) act_r[a] = a < A ? t.act[(size_t)b * t.act_stride + a] : 0.f;
+      const V2 b0q = ld2(s_b0[SQ], lane);
+      const V2 a0_q = relu2(V2{z0q.lo + b0q.lo, z0q.hi + b0q.hi});
+      const V2 a1_q = relu2(fwd64(Wk1 + SQ * H * LD, s_b1[SQ], a0_q, lane));
+      const float q = out1(sko, sko + H, a1_q, lane);
+      bar_group(barid);                                    // A: pi available
+      V2 z0qp = z0q;
+#pragma unroll
+      for (int a = 0; a < AMAX; ++a) {
+        if (a < A) {
+          const float dlt = sc[a] - act_r[a];
+          const float* r1 = sact + a * H;
+          z0qp.lo = fmaf(dlt, r1[lane], z0qp.lo); z0qp.hi = fmaf(dlt, r1[lane + 32], z0qp.hi);
+        }
+      }
+      const V2 a0_qp = relu2(V2{z0qp.lo + b0q.lo, z0qp.hi + b0q.hi});
+      const V2 a1_qp = relu2(fwd64(Wk1 + SQ * H * LD, s_b1[SQ], a0_qp, lane));
+      const float qp = out1(sko, sko + H, a1_qp, lane);
+      if (lane == 0) sc[isq1 ? 9 : 10] = qp;
+      bar_group(barid);                                    // B
+      if (isq1) {
+        // d(-Q1(s, pi))/d pi first: the actor warp waits for it
+        const float dout = -invB;
+        const V2 dzp{a1_qp.lo > 0.f ? dout * sko[lane] : 0.f, a1_qp.hi > 0.f ? dout * sko[lane + 32] : 0.f};
+        const V2 dap = bwd64(Wk1 + SQ * H * LD, dzp, lane);
+        const V2 dz0p{a0_qp.lo > 0.f ? dap.lo : 0.f, a0_qp.hi > 0.f ? dap.hi : 0.f};
+#pragma unroll
+        for (int a = 0; a < AMAX; ++a) {
+          if (a < A) {
+            const float* r1 = sact + a * H;
+            const float d = warp_sum(dz0p.lo * r1[lane] + dz0p.hi * r1[lane + 32]);
+            if (lane == a) sc[16 + a] = d;
+          }
+        }
+      }
+      bar_group(barid);                                    // C
+      const float q_backup = rew_r + (1.f - done_r) * t.gamma * sc[11];
+      const float e = q - q_backup;
+      if (lane == 0) {
+        atomicAdd(&red[isq1 ? MET_QF1_LOSS : MET_QF2_LOSS], 0.5f * e * e * invB);
+        atomicAdd(&red[isq1 ? MET_MEAN_Q1 : MET_MEAN_Q2], q * invB);
+        if (t.per_sample) { t.per_sample[(isq1 ? 0 : 1) * t.B + b] = q; t.per_sample[(isq1 ? 5 : 6) * t.B + b] = qp; }
+      }
+      st2((isq1 ? t.a0_q1 : t.a0_q2) + b * H, lane, a0_q);
+      const float dout = e * invB;
+      atomicAdd(&aacc[lane], a1_q.lo * dout);
+      atomicAdd(&aacc[lane + 32], a1_q.hi * dout);
+      if (lane == 0) atomicAdd(&aacc[H], dout);
+      const V2 dz1{a1_q.lo > 0.f ? dout * sko[lane] : 0.f, a1_q.hi > 0.f ? dout * sko[lane + 32] : 0.f};
+      st2((isq1 ? t.dz1_q1 : t.dz1_q2) + b * H, lane, dz1);
+      const V2 da = bwd64(Wk1 + SQ * H * LD, dz1, lane);
+      const V2 dz0{a0_q.lo > 0.f ? da.lo : 0.f, a0_q.hi > 0.f ? da.hi : 0.f};
+      const size_t o = (size_t)b * 3 * H + (isq1 ? H : 2 * H);
+      st2(t.dz0_v3 + o, lane, dz0);
+      if (t.dz0_v3_p[0]) st2_planes(t.dz0_v3_p[0] + o, t.dz0_v3_p[1] + o, lane, dz0);
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < H * A; i += blockDim.x) {
+    atomicAdd(t.g_pi.ko + i, a_kmu[i]);
+    atomicAdd(t.g_ksig + i, a_ksig[i]);
+  }
+  if (tid < A) { atomicAdd(t.g_pi.bo + tid, a_bmu[tid]); atomicAdd(t.g_bsig + tid, a_bsig[tid]); }
+  if (tid < H) {
+    atomicAdd(t.g_vf.ko + tid, a_vf[tid]); atomicAdd(t.g_q1.ko + tid, a_q1[tid]); atomicAdd(t.g_q2.ko + tid, a_q2[tid]);
+  }
+  if (tid == 0) {
+    atomicAdd(t.g_vf.bo, a_vf[H]); atomicAdd(t.g_q1.bo, a_q1[H]); atomicAdd(t.g_q2.bo, a_q2[H]);
+    atomicAdd(t.g_log_alpha, red[MET_COUNT]);
+  }
+  if (tid < MET_GN_PI) atomicAdd(t.metrics + tid, red[tid]);
+}
+
 // ---- policy inference ([SB2] SACPolicy.step: deterministic_policy = tanh(mu), policy = tanh(mu + eps*std))
 __global__ void __launch_bounds__(WARPS * 32) act_kernel(TailArgs t, int n, int deterministic, float* act_out) {
   __shared__ float Wk1[H * LD];
@@ -424,7 +693,8 @@ namespace {
 
 static size_t tail_smem(int A) {
   return sizeof(float) * (S_NW * H * LD + 2 * H * A + 2 * A + 3 * (H + 1) + MET_COUNT + 1 + 8 +
-                          /* staged small parameters */ (S_NW * 2 * H + 2 * H * A + 2 * A + 4 * (H + 1) + 2 * A * H + 8));
+                          /* staged small parameters */ (S_NW * 2 * H + 2 * H * A + 2 * A + 4 * (H + 1) + 2 * A * H + 8) +
+                          /* tail4 scratch */ 64);
 }
 
 void tail_launch(const TailArgs& a, cudaStream_t s) {
@@ -432,10 +702,18 @@ void tail_launch(const TailArgs& a, cudaStream_t s) {
   const size_t smem = tail_smem(a.A);
   if (!attr_set) {
     cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem(AMAX));
+    cudaFuncSetAttribute(tail4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem(AMAX));
     attr_set = true;
   }
-  const int grid = (a.B + WARPS - 1) / WARPS;
-  launch_pdl(tail_kernel, dim3(grid), dim3(WARPS * 32), smem, s, pdl_enabled(), a);
+  static int v1 = -1;
+  if (v1 < 0) { const char* e = getenv("B2G_TAIL"); v1 = (e && e[0] == 'v' && e[1] == '1') ? 1 : 0; }
+  if (v1) {
+    const int grid = (a.B + WARPS - 1) / WARPS;
+    launch_pdl(tail_kernel, dim3(grid), dim3(WARPS * 32), smem, s, pdl_enabled(), a);
+  } else {
+    const int grid = (a.B + 1) / 2;             // four warps per sample, two samples per CTA
+    launch_pdl(tail4_kernel, dim3(grid), dim3(WARPS * 32), smem, s, pdl_enabled(), a);
+  }
 }
 
 }  // namespace b2g
