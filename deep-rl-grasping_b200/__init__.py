@@ -11,7 +11,7 @@ from .bdq import BDQ, BDQLearner  # noqa: F401
 from .sac_model import SAC, CnnPolicy, MlpPolicy  # noqa: F401
 from . import bench, common, deepq, evaluation, logger, sac  # noqa: F401  (stable_baselines-shaped namespaces)
 from .common import set_global_seeds  # noqa: F401
-from .vec_env import DummyVecEnv, VecNormalize  # noqa: F401
+from .vec_env import DummyVecEnv, SubprocVecEnv, VecNormalize  # noqa: F401
 
 _OUT_OF_SCOPE = ("DQN", "DDPG", "TD3", "TRPO", "PPO1", "PPO2", "A2C", "ACER", "ACKTR", "HER", "GAIL")
 

@@ -22,7 +22,7 @@ SYMBOLS = [
     "b2g_profile_step",
     "b2g_bdq_create", "b2g_bdq_destroy", "b2g_bdq_param_count", "b2g_bdq_param_info", "b2g_bdq_get_param", "b2g_bdq_set_param",
     "b2g_bdq_get_grad", "b2g_bdq_replay_add", "b2g_bdq_replay_size", "b2g_bdq_set_norm_stats", "b2g_bdq_step",
-    "b2g_bdq_step_explicit", "b2g_bdq_act",
+    "b2g_bdq_step_explicit", "b2g_bdq_act", "b2g_bdq_set_per_beta", "b2g_bdq_get_last_per",
     "b2g_encoder_create", "b2g_encoder_destroy", "b2g_encoder_n_layers", "b2g_encoder_layer_shape", "b2g_encoder_set_weights",
     "b2g_encoder_encode", "b2g_debug_gemm",
 ]
@@ -43,7 +43,8 @@ class BdqCfg(C.Structure):
         ("obs_dim", C.c_int32), ("n_branches", C.c_int32), ("n_bins", C.c_int32), ("trunk0", C.c_int32), ("trunk1", C.c_int32),
         ("branch_hidden", C.c_int32), ("batch", C.c_int32), ("buffer_capacity", C.c_int64), ("gamma", C.c_float),
         ("target_update_freq", C.c_int32), ("trunk_grad_rescale", C.c_int32), ("seed", C.c_uint64), ("device", C.c_int32),
-        ("rank", C.c_int32), ("nranks", C.c_int32),
+        ("rank", C.c_int32), ("nranks", C.c_int32), ("nccl_id", C.c_void_p), ("nccl_lib", C.c_char_p),
+        ("prioritized_replay", C.c_int32), ("per_alpha", C.c_float), ("per_eps", C.c_float),
     ]
 
 
@@ -131,6 +132,8 @@ def load():
     lib.b2g_bdq_step.argtypes = [vp, C.c_int, C.c_float, C.POINTER(BdqMetrics)]
     lib.b2g_bdq_step_explicit.argtypes = [vp, fp, fp, fp, fp, fp, fp, C.c_float, C.c_int, C.POINTER(BdqMetrics), fp]
     lib.b2g_bdq_act.argtypes = [vp, fp, C.c_int, C.POINTER(C.c_int32)]
+    lib.b2g_bdq_set_per_beta.argtypes = [vp, C.c_float]
+    lib.b2g_bdq_get_last_per.argtypes = [vp, C.POINTER(C.c_int32), fp, fp]
     lib.b2g_encoder_create.argtypes = [C.POINTER(EncoderCfg), C.POINTER(vp)]
     lib.b2g_encoder_destroy.argtypes = [vp]
     lib.b2g_encoder_n_layers.argtypes = [vp]

@@ -2,8 +2,10 @@
 (/root/reference/manipulation_main/training/train_stable_baselines.py:103-104, sb_helper.py:202-226; hyper-parameters
 config/gripper_grasp.yaml:104-118).  The reference's implementation is the author's stable-baselines fork ``bdq_sb``
 (absent from the tree), so this follows the published algorithm with the variable names of the shipped zips; see
-oracle/bdq_ref.py for every choice that is not pinned.  Prioritised replay is not built (gripper_grasp.yaml:106 runs
-without it); actions are branch bin indices, mapped to linspace(-1, 1, n_bins).
+oracle/bdq_ref.py for every choice that is not pinned.  Prioritised replay (zip data ``prioritized_replay True, alpha .6,
+beta0 .4``; config/simplified_object_picking.yaml:108-110) runs on device-resident sum / min segment trees; data
+parallelism (BASELINE config 4) = one replay shard per rank + one NCCL all-reduce of the gradients per step.  Actions
+are branch bin indices, mapped to linspace(-1, 1, n_bins).
 """
 from __future__ import annotations
 
@@ -24,12 +26,23 @@ class BDQLearner:
     """numpy-facing wrapper of one ``b2g_bdq`` handle (maps 1:1 onto the C ABI)."""
 
     def __init__(self, obs_dim=100, n_branches=3, n_bins=8, layers=((64, 64), (32,), (32,)), batch_size=64, buffer_size=100000,
-                 gamma=0.99, target_network_update_freq=1000, trunk_grad_rescale=True, seed=0, device=0):
+                 gamma=0.99, target_network_update_freq=1000, trunk_grad_rescale=True, seed=0, device=0, rank=0, nranks=1, nccl_id=None,
+                 prioritized_replay=False, prioritized_replay_alpha=0.6, prioritized_replay_eps=1e-6):
         self.lib = _lib.load()
         if layers[1][0] != layers[2][0]:
             raise NotImplementedError("branch and state-value hidden widths must match (every shipped zip / config)")
+        self._id_buf, idp, libp = None, None, None
+        if nranks > 1:
+            if nccl_id is None or len(nccl_id) != 128:
+                raise ValueError("nranks > 1 needs the 128-byte nccl_id shared by all ranks")
+            self._id_buf = C.create_string_buffer(bytes(nccl_id), 128)
+            idp = C.cast(self._id_buf, C.c_void_p)
+            lp = _lib.default_nccl_lib()
+            libp = lp.encode() if lp else None
         cfg = _lib.BdqCfg(obs_dim, n_branches, n_bins, layers[0][0], layers[0][1], layers[1][0], batch_size, buffer_size, gamma,
-                          target_network_update_freq, int(trunk_grad_rescale), seed, device, 0, 1)
+                          target_network_update_freq, int(trunk_grad_rescale), seed, device, rank, nranks, idp, libp,
+                          int(bool(prioritized_replay)), float(prioritized_replay_alpha), float(prioritized_replay_eps))
+        self.prioritized_replay = bool(prioritized_replay)
         self.h = C.c_void_p()
         _lib.check(self.lib.b2g_bdq_create(C.byref(cfg), C.byref(self.h)))
         self.obs_dim, self.n_branches, self.n_bins, self.batch_size = obs_dim, n_branches, n_bins, batch_size
@@ -103,6 +116,16 @@ class BDQLearner:
         _lib.check(self.lib.b2g_bdq_step(self.h, n_steps, lr, C.byref(m)))
         return m.as_dict()
 
+    def set_per_beta(self, beta: float):
+        _lib.check(self.lib.b2g_bdq_set_per_beta(self.h, float(beta)))
+
+    def last_per(self):
+        """Slots, importance weights and new priorities (sum_d |TD_d| + eps) of the last sampled step."""
+        B = self.batch_size
+        idx, w, p = np.empty(B, np.int32), np.empty(B, np.float32), np.empty(B, np.float32)
+        _lib.check(self.lib.b2g_bdq_get_last_per(self.h, idx.ctypes.data_as(C.POINTER(C.c_int32)), _fp(w), _fp(p)))
+        return idx, w, p
+
     def step_explicit(self, obs, act_idx, rew, next_obs, done, weights=None, lr=1e-4, apply_update=True):
         B, D = self.batch_size, self.n_branches
         td = np.empty((B, D), np.float32)
@@ -128,10 +151,13 @@ class BDQ:
 
     def __init__(self, policy, env, gamma=0.99, learning_rate=1e-4, buffer_size=1000000, exploration_fraction=0.1,
                  exploration_final_eps=0.02, train_freq=1, batch_size=64, learning_starts=1000, target_network_update_freq=1000,
-                 num_actions_pad=33, prioritized_replay=False, epsilon_greedy=True, policy_kwargs=None, verbose=0, tensorboard_log=None,
-                 seed=None, device=0, _init_setup_model=True, **_ignored):
-        if prioritized_replay:
-            raise NotImplementedError("prioritised replay is not built (config/gripper_grasp.yaml:106 runs uniform replay)")
+                 num_actions_pad=33, prioritized_replay=False, prioritized_replay_alpha=0.6, prioritized_replay_beta0=0.4,
+                 prioritized_replay_beta_iters=None, prioritized_replay_eps=1e-6, epsilon_greedy=True, policy_kwargs=None, verbose=0,
+                 tensorboard_log=None, seed=None, device=0, rank=0, nranks=1, nccl_id=None, _init_setup_model=True, **_ignored):
+        self.prioritized_replay = bool(prioritized_replay)
+        self.per_alpha, self.per_beta0, self.per_beta_iters, self.per_eps = prioritized_replay_alpha, prioritized_replay_beta0, \
+            prioritized_replay_beta_iters, prioritized_replay_eps
+        self._dp = dict(rank=rank, nranks=nranks, nccl_id=nccl_id)
         self.policy_kwargs = dict(policy_kwargs or {})
         self.layers = self.policy_kwargs.get("layers", [[64, 64], [32], [32]])
         self.gamma, self.learning_rate, self.buffer_size, self.batch_size = gamma, learning_rate, int(buffer_size), int(batch_size)
@@ -153,7 +179,9 @@ class BDQ:
         obs_dim = int(np.prod(self.observation_space.shape))
         n_br = int(np.prod(self.action_space.shape))
         self.learner = BDQLearner(obs_dim, n_br, self.num_actions_pad, tuple(tuple(l) for l in self.layers), self.batch_size,
-                                  self.buffer_size, self.gamma, self.target_network_update_freq, True, int(self.seed or 0), self.device)
+                                  self.buffer_size, self.gamma, self.target_network_update_freq, True, int(self.seed or 0), self.device,
+                                  prioritized_replay=self.prioritized_replay, prioritized_replay_alpha=self.per_alpha,
+                                  prioritized_replay_eps=self.per_eps, **self._dp)
         rng = np.random.default_rng(self.seed)
         p = OrderedDict()
         for n, shp in self.learner.param_shapes.items():
@@ -200,6 +228,9 @@ class BDQ:
             obs = new_obs
             if self.num_timesteps > self.learning_starts and self.num_timesteps % self.train_freq == 0 and \
                     self.learner.replay_size() >= self.batch_size:
+                if self.prioritized_replay:          # [SB2] LinearSchedule(beta_iters, initial_p=beta0, final_p=1.0)
+                    iters = self.per_beta_iters or total_timesteps
+                    self.learner.set_per_beta(self.per_beta0 + min(1.0, self.num_timesteps / iters) * (1.0 - self.per_beta0))
                 self.learner.step(1, lr)
         callback.on_training_end()
         return self
@@ -225,7 +256,8 @@ class BDQ:
         data = {"gamma": self.gamma, "learning_rate": float(self.learning_rate), "batch_size": self.batch_size, "buffer_size": self.buffer_size,
                 "exploration_fraction": self.exploration_fraction, "exploration_final_eps": self.exploration_final_eps,
                 "train_freq": self.train_freq, "learning_starts": self.learning_starts, "num_actions_pad": self.num_actions_pad,
-                "target_network_update_freq": self.target_network_update_freq, "prioritized_replay": False, "double_q": True,
+                "target_network_update_freq": self.target_network_update_freq, "prioritized_replay": self.prioritized_replay,
+                "prioritized_replay_alpha": self.per_alpha, "prioritized_replay_beta0": self.per_beta0, "double_q": True,
                 "epsilon_greedy": True, "policy_kwargs": {"layers": self.layers}}
         sb_io.save_sb_zip(save_path, data, self.learner.get_parameters())
 

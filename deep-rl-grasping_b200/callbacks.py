@@ -230,7 +230,7 @@ class EvalCallback(EventCallback):
         if self.verbose > 0:
             print("[eval] t={} reward {:.2f} +/- {:.2f}, length {:.1f} +/- {:.1f}".format(
                 self.num_timesteps, self.last_mean_reward, float(np.std(rewards)), float(np.mean(lengths)), float(np.std(lengths))))
-        if self.last_mean_reward <= self.best_mean_reward:
+        if self.last_mean_reward < self.best_mean_reward:        # '>=' keeps a tie as the new best, like base_callbacks.py:104
             return True
         self.best_mean_reward = self.last_mean_reward
         if self.best_model_save_path is not None:

@@ -115,6 +115,86 @@ __global__ void bdq_argmax_kernel(const float* const* A, int n_rows, int D, int 
   out[i] = best;
 }
 
+// ------------------------------------------------------------------------------------------------ prioritised replay
+// Proportional prioritisation ([SB2] common/buffers.py PrioritizedReplayBuffer over common/segment_tree.py; Schaul et al.
+// 2016) with the sum / min segment trees resident in HBM: leaves C..2C-1 (C = capacity rounded up to a power of two),
+// node i = f(2i, 2i+1).  Sums are kept in float64 like the Python floats of the reference.
+struct PerArgs {
+  double* tsum; double* tmin; long long C;
+  float* max_prio;                  // running max of the raw priorities (new transitions enter with it)
+  const long long* counters;        // [4] rng step, [5] replay size
+  unsigned long long seed;
+  int B; float alpha, eps; const float* beta;
+  int* indices; float* weights; float* prio_out;
+  const float* td; int D;
+};
+
+// one CTA, B threads: draws B slots proportionally to priority (find_prefixsum_idx descent) and their IS weights
+__global__ void per_sample_kernel(PerArgs a) {
+  const int b = threadIdx.x;
+  if (b >= a.B) return;
+  const unsigned long long step = (unsigned long long)a.counters[4];
+  const long long size = a.counters[5];
+  const uint4 r = philox4x32_10(make_uint4((unsigned)step, (unsigned)(step >> 32), (unsigned)(b >> 2), 2u), make_uint2((unsigned)a.seed, (unsigned)(a.seed >> 32)));
+  const unsigned v = (b & 3) == 0 ? r.x : (b & 3) == 1 ? r.y : (b & 3) == 2 ? r.z : r.w;
+  const double total = a.tsum[1];
+  double mass = ((double)v + 0.5) * (1.0 / 4294967296.0) * total;
+  long long node = 1;
+  while (node < a.C) {
+    const double left = a.tsum[2 * node];
+    if (left > mass) node = 2 * node;
+    else { mass -= left; node = 2 * node + 1; }
+  }
+  long long idx = node - a.C;
+  if (idx >= size) idx = size - 1;                       // (rounding at the right edge of the occupied range)
+  const double beta = (double)a.beta[0];
+  const double p_min = a.tmin[1] / total;
+  const double max_w = pow(p_min * (double)size, -beta);
+  const double p = a.tsum[a.C + idx] / total;
+  a.indices[b] = (int)idx;
+  a.weights[b] = (float)(pow(p * (double)size, -beta) / max_w);
+}
+
+// one CTA: writes `n` leaves and repairs their ancestors level by level (siblings recomputed redundantly: same values)
+__global__ void per_write_kernel(PerArgs a, const int* __restrict__ slots, long long first_slot, long long cap, int n, int from_td) {
+  const int i = threadIdx.x;
+  long long leaf = 0;
+  if (i < n) {
+    const long long slot = slots ? (long long)slots[i] : (first_slot + i) % cap;
+    float raw;
+    if (from_td) {
+      float s = 0.f;
+      for (int d = 0; d < a.D; ++d) s += fabsf(a.td[i * a.D + d]);
+      raw = s + a.eps;
+      atomicMax(reinterpret_cast<int*>(a.max_prio), __float_as_int(raw));      // positive floats order like their bit patterns
+      if (a.prio_out) a.prio_out[i] = raw;
+    } else raw = a.max_prio[0];
+    const double pr = pow((double)raw, (double)a.alpha);
+    leaf = a.C + slot;
+    a.tsum[leaf] = pr; a.tmin[leaf] = pr;
+  }
+  __syncthreads();
+  for (long long span = a.C; span > 1; span >>= 1) {
+    if (i < n) {
+      leaf >>= 1;
+      a.tsum[leaf] = a.tsum[2 * leaf] + a.tsum[2 * leaf + 1];
+      a.tmin[leaf] = fmin(a.tmin[2 * leaf], a.tmin[2 * leaf + 1]);
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void per_init_kernel(double* tsum, double* tmin, long long n2, float* max_prio) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) { tsum[i] = 0.0; tmin[i] = INFINITY; }
+  if (blockIdx.x == 0 && threadIdx.x == 0) max_prio[0] = 1.0f;
+}
+
+// hard target copy every `freq` updates, decided on the device so that the step can live in a CUDA graph
+__global__ void bdq_target_copy_kernel(float* __restrict__ P, long long n_train, const long long* __restrict__ counters, int freq) {
+  if (freq <= 0 || counters[3] % freq != 0) return;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_train; i += (long long)gridDim.x * blockDim.x) P[n_train + i] = P[i];
+}
+
 std::vector<int> iota_t(int n, int stride = 1, int base = 0) {
   std::vector<int> v(n);
   for (int i = 0; i < n; ++i) v[i] = base + i * stride;
@@ -151,6 +231,12 @@ struct b2g_bdq {
   long long n_updates = 0;
   float* h_met = nullptr;
   void* nccl_comm = nullptr;
+  // prioritised replay
+  bool per = false;
+  double *t_sum = nullptr, *t_min = nullptr;
+  long long per_C = 0;
+  float *max_prio = nullptr, *d_beta = nullptr, *prio_out = nullptr;
+  cudaGraphExec_t graph_exec = nullptr;
   float* p(const std::string& nm) { return P + tensors[tindex.at(nm)].off; }
   float* g(const std::string& nm) { return G + tensors[tindex.at(nm)].off; }
   float* pt(const std::string& nm) { return P + n_train + tensors[tindex.at(nm)].off; }
@@ -335,6 +421,13 @@ int bdq_issue(b2g_bdq* h, bool sampled, bool apply, const float* weights) {
   pa.indices = h->indices; pa.eps = h->eps_dummy; pa.B = h->B; pa.A = 1; pa.replay_size = nullptr;
   pa.seed = h->cfg.seed + 0x9E3779B97F4A7C15ull * (unsigned long long)h->cfg.rank; pa.gen = sampled ? 1 : 0; pa.apply = apply ? 1 : 0;
   prep_launch(pa, s);
+  PerArgs pr{};
+  if (h->per) {
+    pr.tsum = h->t_sum; pr.tmin = h->t_min; pr.C = h->per_C; pr.max_prio = h->max_prio; pr.counters = h->counters; pr.seed = pa.seed;
+    pr.B = h->B; pr.alpha = h->cfg.per_alpha; pr.eps = h->cfg.per_eps; pr.beta = h->d_beta; pr.indices = h->indices; pr.weights = h->weights;
+    pr.prio_out = h->prio_out; pr.td = h->td; pr.D = h->D;
+    if (sampled) { per_sample_kernel<<<1, ((h->B + 31) / 32) * 32, 0, s>>>(pr); weights = h->weights; }   // overwrites the uniform draw
+  }
   gather_launch(bgather(h, sampled, true), s);
   BCK(cudaMemsetAsync(h->G, 0, (size_t)(h->n_train + MET_COUNT) * sizeof(float), s));
   for (auto& g : h->fwd) gg_simt_launch(g.dev, (int)g.host.size(), g.total_tiles, s);
@@ -347,17 +440,20 @@ int bdq_issue(b2g_bdq* h, bool sampled, bool apply, const float* weights) {
   t.dV = h->dV; t.td = h->td; t.metrics = h->metrics;
   bdq_tail_kernel<<<(h->B + 127) / 128, 128, 0, s>>>(t);
   for (auto& g : h->bwd) gg_simt_launch(g.dev, (int)g.host.size(), g.total_tiles, s);
+  if (h->per && sampled) per_write_kernel<<<1, ((h->B + 31) / 32) * 32, 0, s>>>(pr, h->indices, 0, h->cfg.buffer_capacity, h->B, 1);   // update_priorities(|td| + eps)
+  if (h->cfg.nranks > 1) {      // gradients + loss scalars averaged over the ranks (each rank sampled its own replay shard)
+    BCK(cudaMemcpyAsync(h->G + h->n_train, h->metrics, 2 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    if (int rc = nccl_allreduce_sum_f32(h->nccl_comm, h->G, (size_t)(h->n_train + MET_COUNT), s)) return rc;
+    BCK(cudaMemcpyAsync(h->metrics, h->G + h->n_train, 2 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  }
   OptimArgs oa{};
   oa.P = h->P; oa.Mo = h->Mo; oa.Vo = h->Vo; oa.G = h->G; oa.T = h->P + h->n_train;
   oa.n_pi = (int)h->n_train; oa.n_values = 0; oa.n_ent = 0; oa.n_target = 0;
   oa.step_consts = h->step_consts; oa.tau = 0.f; oa.grad_scale = 1.0f / (float)h->cfg.nranks; oa.metrics = h->metrics; oa.apply = apply ? 1 : 0;
   optim_launch(oa, s);
   BCK(cudaGetLastError());
-  if (apply) {
-    ++h->n_updates;
-    if (h->cfg.target_update_freq > 0 && h->n_updates % h->cfg.target_update_freq == 0)   // hard target copy
-      BCK(cudaMemcpyAsync(h->P + h->n_train, h->P, h->n_train * sizeof(float), cudaMemcpyDeviceToDevice, s));
-  }
+  if (apply) bdq_target_copy_kernel<<<64, 256, 0, s>>>(h->P, h->n_train, h->counters, h->cfg.target_update_freq);   // counters[3] = n_updates (prep)
+  BCK(cudaGetLastError());
   return 0;
 }
 
@@ -373,7 +469,8 @@ int bfetch(b2g_bdq* h, b2g_bdq_metrics* out) {
   BCK(cudaMemcpyAsync(h->h_met, h->metrics, MET_COUNT * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
   BCK(cudaStreamSynchronize(h->stream));
   if (out) {
-    out->loss = h->h_met[BMET_LOSS]; out->mean_q = h->h_met[BMET_MEANQ]; out->grad_norm = sqrtf(h->h_met[BMET_GN]);
+    const float inv = 1.0f / (float)h->cfg.nranks;
+    out->loss = h->h_met[BMET_LOSS] * inv; out->mean_q = h->h_met[BMET_MEANQ] * inv; out->grad_norm = sqrtf(h->h_met[BMET_GN]);
     out->n_updates = h->n_updates;
   }
   return 0;
@@ -386,6 +483,8 @@ int b2g_bdq_destroy(b2g_bdq* h) {
   if (!h) return 0;
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+  nccl_comm_destroy(h->nccl_comm);
   for (void* q : h->allocs) cudaFree(q);
   if (h->h_met) cudaFreeHost(h->h_met);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -400,7 +499,9 @@ int b2g_bdq_create(const b2g_bdq_cfg* cfg, b2g_bdq** out) {
   if (cfg->trunk0 % 4 || cfg->trunk1 % 4 || cfg->branch_hidden % 4 || cfg->trunk0 < 4 || cfg->trunk1 < 4 || cfg->branch_hidden < 4)
     return bfail(B2G_EINVAL, "layer widths must be positive multiples of 4");
   if (cfg->obs_dim < 1 || cfg->batch < 1 || cfg->buffer_capacity < 1) return bfail(B2G_EINVAL, "obs_dim, batch, buffer_capacity must be positive");
-  if (cfg->nranks != 1) return bfail(B2G_EINVAL, "BDQ data parallelism is not built in this revision (nranks must be 1)");
+  if (cfg->nranks < 1 || cfg->rank < 0 || cfg->rank >= cfg->nranks) return bfail(B2G_EINVAL, "bad rank/nranks");
+  if (cfg->nranks > 1 && !cfg->nccl_id) return bfail(B2G_EINVAL, "nranks > 1 needs nccl_id");
+  if (cfg->prioritized_replay && cfg->batch > 1024) return bfail(B2G_EINVAL, "prioritised replay supports batch <= 1024");
   int ndev = 0;
   BCK(cudaGetDeviceCount(&ndev));
   if (cfg->device < 0 || cfg->device >= ndev) return bfail(B2G_ECUDA, "no such CUDA device");
@@ -410,6 +511,8 @@ int b2g_bdq_create(const b2g_bdq_cfg* cfg, b2g_bdq** out) {
   if (prop.major != 10) return bfail(B2G_ECUDA, std::string("libb200grasp is built for sm_100a only; found ") + prop.name);
   b2g_bdq* h = new b2g_bdq();
   h->cfg = *cfg;
+  h->cfg.nccl_id = nullptr; h->cfg.nccl_lib = nullptr;
+  h->per = cfg->prioritized_replay != 0;
   h->B = cfg->batch; h->D = cfg->n_branches; h->n = cfg->n_bins; h->NBS = (cfg->n_bins + 3) / 4 * 4;
   h->T0 = cfg->trunk0; h->T1 = cfg->trunk1; h->HB = cfg->branch_hidden; h->E = cfg->obs_dim;
   h->XS = (cfg->obs_dim + cfg->n_branches + 7) / 8 * 8;
@@ -450,6 +553,15 @@ int b2g_bdq_create(const b2g_bdq_cfg* cfg, b2g_bdq** out) {
   BA(h->rew_n, B); BA(h->done_n, B); BA(h->weights, B); BA(h->eps_dummy, B + 8); BA(h->indices, B + 4); BA(h->act_idx_out, B * D);
   BA(h->s_obs, (size_t)B * h->E); BA(h->s_next, (size_t)B * h->E); BA(h->s_act, B * D); BA(h->s_rew, B); BA(h->s_done, B);
   BA(h->d_Aptr, 8);
+  BA(h->d_beta, 1); BA(h->max_prio, 1); BA(h->prio_out, B);
+  if (h->per) {
+    h->per_C = 1;
+    while (h->per_C < cap) h->per_C <<= 1;
+    BA(h->t_sum, 2 * h->per_C); BA(h->t_min, 2 * h->per_C);
+    per_init_kernel<<<256, 256, 0, h->stream>>>(h->t_sum, h->t_min, 2 * h->per_C, h->max_prio);
+    const float beta0 = 0.4f;
+    if (cudaMemcpyAsync(h->d_beta, &beta0, sizeof(float), cudaMemcpyHostToDevice, h->stream) != cudaSuccess) return bail(bfail(B2G_ECUDA, "per init"));
+  }
 #undef BA
   if (cudaMallocHost((void**)&h->h_met, MET_COUNT * sizeof(float)) != cudaSuccess) return bail(bfail(B2G_ECUDA, "cudaMallocHost"));
   {
@@ -464,6 +576,10 @@ int b2g_bdq_create(const b2g_bdq_cfg* cfg, b2g_bdq** out) {
       return bail(bfail(B2G_ECUDA, "init copies"));
   }
   if ((rc = build(h))) return bail(rc);
+  if (cfg->nranks > 1) {
+    if ((rc = nccl_comm_init(&h->nccl_comm, cfg->nranks, cfg->nccl_id, cfg->rank, cfg->nccl_lib))) return bail(rc);
+    if ((rc = nccl_allreduce_sum_f32(h->nccl_comm, h->G, (size_t)(h->n_train + MET_COUNT), h->stream))) return bail(rc);   // warm-up outside capture
+  }
   if (cudaStreamSynchronize(h->stream) != cudaSuccess) return bail(bfail(B2G_ECUDA, "create sync"));
   *out = h;
   return 0;
@@ -537,6 +653,14 @@ int b2g_bdq_replay_add(b2g_bdq* h, const float* obs, const float* act_idx, const
     BCK(cudaMemcpyAsync(h->r_act + h->r_pos * D, act_idx + done_n * D, chunk * D * sizeof(float), cudaMemcpyDefault, h->stream));
     BCK(cudaMemcpyAsync(h->r_rew + h->r_pos, rew + done_n, chunk * sizeof(float), cudaMemcpyDefault, h->stream));
     BCK(cudaMemcpyAsync(h->r_done + h->r_pos, done + done_n, chunk * sizeof(float), cudaMemcpyDefault, h->stream));
+    if (h->per) {        // new transitions enter with the running maximum priority ([SB2] PrioritizedReplayBuffer.add)
+      PerArgs pr{};
+      pr.tsum = h->t_sum; pr.tmin = h->t_min; pr.C = h->per_C; pr.max_prio = h->max_prio; pr.alpha = h->cfg.per_alpha; pr.eps = h->cfg.per_eps;
+      for (int64_t o = 0; o < chunk; o += 1024) {
+        const int nn = (int)std::min<int64_t>(1024, chunk - o);
+        per_write_kernel<<<1, ((nn + 31) / 32) * 32, 0, h->stream>>>(pr, nullptr, h->r_pos + o, cap, nn, 0);
+      }
+    }
     h->r_pos = (h->r_pos + chunk) % cap;
     h->r_size = std::min(cap, h->r_size + chunk);
     done_n += chunk;
@@ -570,8 +694,43 @@ int b2g_bdq_step(b2g_bdq* h, int n_steps, float lr, b2g_bdq_metrics* out) {
   if (h->r_size < 1) return bfail(B2G_ESTATE, "replay buffer is empty");
   BCK(cudaSetDevice(h->cfg.device));
   if (int rc = bset_lr(h, lr)) return rc;
-  for (int i = 0; i < n_steps; ++i) if (int rc = bdq_issue(h, true, true, nullptr)) return rc;
+  static int no_graph = -1;
+  if (no_graph < 0) { const char* e = getenv("B2G_NO_GRAPH"); no_graph = (e && e[0] == '1') ? 1 : 0; }
+  if (!no_graph && !h->graph_exec) {       // the whole step (~14 launches of tiny layers) replays as one graph
+    cudaGraph_t graph = nullptr;
+    BCK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = bdq_issue(h, true, true, nullptr);
+    const cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess) return bfail(B2G_ECUDA, std::string("BDQ graph capture failed: ") + cudaGetErrorString(e));
+    const cudaError_t e2 = cudaGraphInstantiate(&h->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e2 != cudaSuccess) return bfail(B2G_ECUDA, std::string("BDQ graph instantiate failed: ") + cudaGetErrorString(e2));
+  }
+  for (int i = 0; i < n_steps; ++i) {
+    if (h->graph_exec) BCK(cudaGraphLaunch(h->graph_exec, h->stream));
+    else if (int rc = bdq_issue(h, true, true, nullptr)) return rc;
+    ++h->n_updates;
+  }
   return bfetch(h, out);
+}
+
+int b2g_bdq_set_per_beta(b2g_bdq* h, float beta) {
+  if (!h) return bfail(B2G_EINVAL, "NULL handle");
+  BCK(cudaSetDevice(h->cfg.device));
+  BCK(cudaStreamSynchronize(h->stream));
+  BCK(cudaMemcpy(h->d_beta, &beta, sizeof(float), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int b2g_bdq_get_last_per(b2g_bdq* h, int32_t* slots, float* weights, float* priorities) {
+  if (!h) return bfail(B2G_EINVAL, "NULL handle");
+  BCK(cudaSetDevice(h->cfg.device));
+  BCK(cudaStreamSynchronize(h->stream));
+  if (slots) BCK(cudaMemcpy(slots, h->indices, h->B * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  if (weights) BCK(cudaMemcpy(weights, h->weights, h->B * sizeof(float), cudaMemcpyDeviceToHost));
+  if (priorities) BCK(cudaMemcpy(priorities, h->prio_out, h->B * sizeof(float), cudaMemcpyDeviceToHost));
+  return 0;
 }
 
 int b2g_bdq_step_explicit(b2g_bdq* h, const float* obs, const float* act_idx, const float* rew, const float* next_obs, const float* done,
@@ -587,6 +746,7 @@ int b2g_bdq_step_explicit(b2g_bdq* h, const float* obs, const float* act_idx, co
   BCK(cudaMemcpyAsync(h->s_done, done, B * sizeof(float), cudaMemcpyDefault, h->stream));
   if (weights) BCK(cudaMemcpyAsync(h->weights, weights, B * sizeof(float), cudaMemcpyDefault, h->stream));
   if (int rc = bdq_issue(h, false, apply_update != 0, weights ? h->weights : nullptr)) return rc;
+  if (apply_update) ++h->n_updates;
   if (td_out) BCK(cudaMemcpyAsync(td_out, h->td, B * D * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
   return bfetch(h, out);
 }

@@ -92,6 +92,24 @@ int load_nccl(const char* path) {
 int64_t pad32(int64_t n) { return (n + 31) / 32 * 32; }
 }  // namespace
 
+// NCCL plumbing shared with bdq.cu (common.cuh declares these)
+namespace b2g {
+int nccl_comm_init(void** comm, int nranks, const void* id128, int rank, const char* lib) {
+  if (int rc = load_nccl(lib)) return rc;
+  UId id;
+  memcpy(id.b, id128, 128);
+  const int nrc = g_nccl.CommInitRank(comm, nranks, id, rank);
+  if (nrc != 0) return fail(B2G_ENCCL, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "?"));
+  return 0;
+}
+int nccl_allreduce_sum_f32(void* comm, float* buf, size_t count, cudaStream_t s) {
+  const int nrc = g_nccl.AllReduce(buf, buf, count, /*ncclFloat32*/ 7, /*ncclSum*/ 0, comm, s);
+  if (nrc != 0) return fail(B2G_ENCCL, std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "?"));
+  return 0;
+}
+void nccl_comm_destroy(void* comm) { if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm); }
+}  // namespace b2g
+
 namespace {
 
 template <class T>

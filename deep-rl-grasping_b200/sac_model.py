@@ -81,6 +81,7 @@ class SAC:
         self.ent_coef, self.target_entropy = ent_coef, target_entropy
         self.precision = precision
         self._dev = dict(device=device, rank=rank, nranks=nranks, nccl_id=nccl_id)
+        self._layout_from_zip = False
         self.num_timesteps, self.n_updates = 0, 0
         self.episode_rewards = [0.0]
         self.ep_info_buf = deque(maxlen=100)
@@ -111,9 +112,13 @@ class SAC:
     def setup_model(self):
         obs_shape = tuple(self.observation_space.shape)
         n_act = int(np.prod(self.action_space.shape))
-        if len(obs_shape) == 3 and "cnn_extractor" not in self.policy_kwargs and self.policy is not None \
-                and getattr(self.policy, "__name__", str(self.policy)) == "CnnPolicy" and not self.policy_kwargs.get("_augmented", True):
-            raise NotImplementedError("plain nature_cnn (simplified env) is not built; the path uses augmented_nature_cnn")
+        if len(obs_shape) == 3 and "cnn_extractor" not in self.policy_kwargs and not self._layout_from_zip:
+            # sb_helper.py:93-95: CnnPolicy with policy_kwargs={} means stable-baselines' plain nature_cnn over ALL planes and
+            # no direct feature -- a different network (and different zip variables) from augmented_nature_cnn.  Refuse
+            # instead of silently building the augmented extractor.  (SAC.load knows the layout from the zip itself.)
+            raise NotImplementedError("CnnPolicy without policy_kwargs['cnn_extractor'] selects stable-baselines' plain nature_cnn "
+                                      "(simplified + depth branch, sb_helper.py:93-95), which is not built; pass "
+                                      "cnn_extractor=create_augmented_nature_cnn(1) as sb_helper.py:88-91 does")
         tgt = -float(n_act) if self.target_entropy == "auto" else float(self.target_entropy)
         self.learner = Learner(obs_shape, n_act=n_act, hidden=64, batch_size=self.batch_size, buffer_size=self.buffer_size,
                                gamma=self.gamma, tau=self.tau, target_entropy=tgt, seed=int(self.seed or 0),
@@ -140,6 +145,12 @@ class SAC:
             else:
                 p[name] = np.zeros(shape, np.float32)
         self.learner.load_parameters(p)
+
+    def close(self):
+        """Releases the device learner (replay ring included: 2 * buffer_size * obs_elems * 4 bytes of HBM)."""
+        if self.learner is not None:
+            self.learner.close()
+            self.learner = None
 
     def _sync_norm_stats(self):
         vn = self._vec_normalize_env
@@ -184,6 +195,8 @@ class SAC:
                 action = self._scale_action(unscaled)
             else:
                 src = obs_ if vn is not None else obs        # the device normalises raw obs with the same statistics
+                if vn is not None:
+                    self._sync_norm_stats()                  # act on the wrapper's CURRENT statistics, like SB does
                 action = self.learner.act(np.asarray(src, np.float32), deterministic=False)
                 unscaled = self._unscale_action(action)
             new_obs, reward, done, infos = self.env.step(unscaled)
@@ -302,11 +315,14 @@ class SAC:
                 kw[k] = data[k]
         if isinstance(data.get("learning_rate"), (int, float)):
             kw["learning_rate"] = data["learning_rate"]
-        if env is None:
-            kw["buffer_size"] = min(int(kw.get("buffer_size", 1000)), 1000)     # inference-only handle: no large replay
+        # The zip's buffer_size (1e6 in every shipped model) is the TRAINING ring: 2 * 1e6 * obs_elems * 4 B = 65.6 GB for
+        # depth, 164 GB for RGB-D.  A loaded model is used for inference or as a parameter donor (sb_helper.py:113-115 builds
+        # a second model just to call get_parameters), so it gets a small ring unless the caller asks for one explicitly.
+        kw["buffer_size"] = min(int(kw.get("buffer_size", 1000)), 1000)
         kw.update(kwargs)
         model = cls(policy=data.get("policy", "CnnPolicy"), env=None, _init_setup_model=False,
                     policy_kwargs={"layers": [64, 64]}, **kw)
+        model._layout_from_zip = True
         model.env = env_like if env is not None else None
         model.n_envs = env_like.num_envs
         model.observation_space, model.action_space = env_like.observation_space, env_like.action_space

@@ -9,7 +9,7 @@ from __future__ import annotations
 import pickle
 import sys
 import types
-from typing import Callable, List, Sequence
+from typing import Optional,  Callable, List, Sequence
 
 import numpy as np
 
@@ -84,6 +84,113 @@ class DummyVecEnv(VecEnv):
 
     def env_method(self, name, *a, **k):
         return [getattr(e, name)(*a, **k) for e in self.envs]
+
+
+def _subproc_worker(remote, parent_remote, fn_bytes):
+    """One environment per process ([SB2] common/vec_env/subproc_vec_env.py protocol: step / reset / close / get_spaces /
+    get_attr / env_method); auto-reset on done with the terminal observation in ``info``."""
+    import pickle
+    parent_remote.close()
+    env = pickle.loads(fn_bytes)()
+    try:
+        while True:
+            cmd, data = remote.recv()
+            if cmd == "step":
+                o, r, d, info = env.step(data)
+                if d:
+                    info = dict(info)
+                    info["terminal_observation"] = np.asarray(o)
+                    o = env.reset()
+                remote.send((np.asarray(o), r, d, info))
+            elif cmd == "reset":
+                remote.send(np.asarray(env.reset()))
+            elif cmd == "get_spaces":
+                remote.send((env.observation_space, env.action_space))
+            elif cmd == "get_attr":
+                remote.send(getattr(env, data))
+            elif cmd == "env_method":
+                remote.send(getattr(env, data[0])(*data[1], **data[2]))
+            elif cmd == "close":
+                if hasattr(env, "close"):
+                    env.close()
+                remote.close()
+                break
+            else:
+                raise NotImplementedError(cmd)
+    except (EOFError, KeyboardInterrupt):
+        pass
+
+
+class SubprocVecEnv(VecEnv):
+    """Vectorised environments in worker processes: the host-side actor loop that feeds the GPU-resident replay buffer
+    (BASELINE config 5: 128 PyBullet envs on host cores; the reference imports it at sb_helper.py:19).  ``step_async``
+    sends every action first, ``step_wait`` collects, so the environments advance in parallel on the host cores while
+    the previous batch of transitions is already on its way to the device."""
+
+    def __init__(self, env_fns: Sequence[Callable], start_method: Optional[str] = None):
+        import multiprocessing as mp
+        import cloudpickle
+        ctx = mp.get_context(start_method or ("forkserver" if "forkserver" in mp.get_all_start_methods() else "spawn"))
+        self.num_envs = len(env_fns)
+        self.remotes, self.work_remotes = zip(*[ctx.Pipe() for _ in env_fns])
+        self.procs = []
+        for wr, r, fn in zip(self.work_remotes, self.remotes, env_fns):
+            p = ctx.Process(target=_subproc_worker, args=(wr, r, cloudpickle.dumps(fn)), daemon=True)
+            p.start()
+            self.procs.append(p)
+            wr.close()
+        self.remotes[0].send(("get_spaces", None))
+        self.observation_space, self.action_space = self.remotes[0].recv()
+        self.buf_infos: List[dict] = [{} for _ in env_fns]
+        self.waiting = self.closed = False
+
+    def step_async(self, actions):
+        for r, a in zip(self.remotes, actions):
+            r.send(("step", a))
+        self.waiting = True
+
+    def step_wait(self):
+        res = [r.recv() for r in self.remotes]
+        self.waiting = False
+        obs, rews, dones, infos = zip(*res)
+        self.buf_infos = list(infos)
+        return np.stack(obs), np.asarray(rews, np.float32), np.asarray(dones), list(infos)
+
+    def step(self, actions):
+        self.step_async(actions)
+        return self.step_wait()
+
+    def reset(self):
+        for r in self.remotes:
+            r.send(("reset", None))
+        return np.stack([r.recv() for r in self.remotes])
+
+    def get_attr(self, name, indices=None):
+        idx = range(self.num_envs) if indices is None else indices
+        for i in idx:
+            self.remotes[i].send(("get_attr", name))
+        return [self.remotes[i].recv() for i in idx]
+
+    def env_method(self, name, *a, **k):
+        for r in self.remotes:
+            r.send(("env_method", (name, a, k)))
+        return [r.recv() for r in self.remotes]
+
+    @property
+    def envs(self):
+        raise AttributeError("SubprocVecEnv has no in-process envs; use get_attr / env_method")
+
+    def close(self):
+        if self.closed:
+            return
+        if self.waiting:
+            for r in self.remotes:
+                r.recv()
+        for r in self.remotes:
+            r.send(("close", None))
+        for p in self.procs:
+            p.join(timeout=5)
+        self.closed = True
 
 
 class VecNormalize(VecEnv):
@@ -185,33 +292,44 @@ class VecNormalize(VecEnv):
             with open(path, "wb") as f:
                 pickle.dump(self, f)
             return
-        mods = {}
-        for name in ("stable_baselines", "stable_baselines.common", "stable_baselines.common.vec_env",
-                     "stable_baselines.common.vec_env.vec_normalize", "stable_baselines.common.running_mean_std"):
-            if name not in sys.modules:
-                mods[name] = types.ModuleType(name)
-        sys.modules.update(mods)
+        # The pickle must NAME stable_baselines' classes.  Stand-in classes carrying those module / class names are
+        # registered in sys.modules only for the duration of the dump; whatever was there before (a real stable_baselines
+        # install included) is put back in `finally`, also when the dump raises.
+        vn_mod, rm_mod = "stable_baselines.common.vec_env.vec_normalize", "stable_baselines.common.running_mean_std"
+        vn_cls = type("VecNormalize", (), {"__module__": vn_mod})
+        rm_cls = type("RunningMeanStd", (), {"__module__": rm_mod})
+        created, missing = [], object()
+        saved = {}
         try:
-            vn_cls = type("VecNormalize", (), {"__module__": "stable_baselines.common.vec_env.vec_normalize"})
-            rm_cls = type("RunningMeanStd", (), {"__module__": "stable_baselines.common.running_mean_std"})
-            had = [getattr(sys.modules[vn_cls.__module__], "VecNormalize", None), getattr(sys.modules[rm_cls.__module__], "RunningMeanStd", None)]
-            sys.modules[vn_cls.__module__].VecNormalize = vn_cls
-            sys.modules[rm_cls.__module__].RunningMeanStd = rm_cls
+            for name in ("stable_baselines", "stable_baselines.common", "stable_baselines.common.vec_env", vn_mod, rm_mod):
+                if name not in sys.modules:
+                    sys.modules[name] = types.ModuleType(name)
+                    created.append(name)
+            for mod, attr, cls in ((vn_mod, "VecNormalize", vn_cls), (rm_mod, "RunningMeanStd", rm_cls)):
+                saved[(mod, attr)] = getattr(sys.modules[mod], attr, missing)
+                setattr(sys.modules[mod], attr, cls)
             obj = vn_cls.__new__(vn_cls)
             st = self.__getstate__()
             for k in ("obs_rms", "ret_rms"):
                 r = rm_cls.__new__(rm_cls)
                 r.__dict__.update(st[k].__dict__)
                 st[k] = r
+            for k in ("observation_space", "action_space"):      # our Box is not importable on the reference side
+                st.pop(k, None)
             obj.__dict__.update(st)
             with open(path, "wb") as f:
                 pickle.dump(obj, f)
-            if had[0] is not None:
-                sys.modules[vn_cls.__module__].VecNormalize = had[0]
-            if had[1] is not None:
-                sys.modules[rm_cls.__module__].RunningMeanStd = had[1]
         finally:
-            for name in mods:
+            for (mod, attr), old in saved.items():
+                if mod in sys.modules and mod not in created:
+                    if old is missing:
+                        try:
+                            delattr(sys.modules[mod], attr)
+                        except AttributeError:
+                            pass
+                    else:
+                        setattr(sys.modules[mod], attr, old)
+            for name in created:
                 sys.modules.pop(name, None)
 
     @staticmethod

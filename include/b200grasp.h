@@ -161,7 +161,13 @@ typedef struct b2g_bdq_cfg {
   int32_t trunk_grad_rescale;  /* 1: scale the gradient entering the trunk by 1/(n_branches+1) (paper)   */
   uint64_t seed;
   int32_t device;
-  int32_t rank, nranks;        /* nranks must be 1 in this revision                                      */
+  int32_t rank, nranks;        /* data-parallel group (BASELINE config 4): each rank owns a replay shard, one NCCL
+                                  all-reduce averages the gradients; nranks == 1 -> no collective                    */
+  const void* nccl_id;         /* 128-byte ncclUniqueId shared by all ranks (nranks > 1)                           */
+  const char* nccl_lib;        /* optional libnccl path; NULL = default search                                     */
+  int32_t prioritized_replay;  /* 1: proportional prioritised replay (zip data: prioritized_replay True,
+                                  config/simplified_object_picking.yaml:108-110): device sum / min segment trees   */
+  float per_alpha, per_eps;    /* priority exponent (0.6) and the epsilon added to |TD| (1e-6)                     */
 } b2g_bdq_cfg;
 typedef struct b2g_bdq_metrics {
   float loss, mean_q, grad_norm;
@@ -183,6 +189,11 @@ int b2g_bdq_set_norm_stats(b2g_bdq* h, const double* obs_mean, const double* obs
 /* n_steps x { uniform sample -> forward (online s, online s', target s') -> double-Q TD loss -> backward -> Adam ->
  * hard target copy every target_update_freq updates } */
 int b2g_bdq_step(b2g_bdq* h, int n_steps, float lr, b2g_bdq_metrics* out);
+/* prioritised replay: importance-sampling exponent beta of the NEXT sampled steps (SB anneals beta0 -> 1 over
+ * prioritized_replay_beta_iters); last_out (may be NULL) = slots[batch], weights[batch], new priorities[batch] of the last
+ * sampled step, for inspection / tests */
+int b2g_bdq_set_per_beta(b2g_bdq* h, float beta);
+int b2g_bdq_get_last_per(b2g_bdq* h, int32_t* slots, float* weights, float* priorities);
 /* parity entry point: caller-supplied batch (+ optional importance weights); td_out (may be NULL): [batch, n_branches] */
 int b2g_bdq_step_explicit(b2g_bdq* h, const float* obs, const float* act_idx, const float* rew, const float* next_obs,
                           const float* done, const float* weights, float lr, int apply_update, b2g_bdq_metrics* out,

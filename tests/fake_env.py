@@ -32,3 +32,8 @@ class FakeGraspEnv:
 
     def close(self):
         pass
+
+
+def make_env(config, evaluate=False, validate=False, test=False):
+    """Factory with the signature train_cli expects (mirrors gym.make('gripper-env-v0', config=..., evaluate=..., ...))."""
+    return FakeGraspEnv(seed=1 if evaluate else 0, horizon=20)

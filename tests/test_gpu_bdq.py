@@ -94,3 +94,67 @@ def test_bdq_front_end_learn_predict_save_load(tmp_path):
     m2 = b200grasp.BDQ.load(path)
     a2, _ = m2.predict(np.zeros(100, np.float32))
     assert np.array_equal(a, a2)
+
+
+def test_bdq_prioritized_replay_trees_weights_and_distribution():
+    """f4: proportional prioritised replay on device segment trees ([SB2] PrioritizedReplayBuffer semantics: new transitions
+    enter with max_priority^alpha; sample ~ p_i / sum; w_i = (N p_i / sum)^-beta / max_w with max_w from the MIN tree;
+    update_priorities(sum_d |TD_d| + eps)).  A numpy mirror of the trees is driven by what the device reports and must
+    predict the importance weights of the next step exactly; with frozen weights (lr = 0) the slot frequencies follow the
+    stationary priorities (chi-square)."""
+    cfg = Q.BDQConfig(100, 3, 8, (64, 64), 32, 32, 0.99)
+    B, NSLOT, alpha, beta = 64, 200, 0.6, 0.7
+    params = Q.init_params(cfg, seed=3)
+    L = b200grasp.BDQLearner(cfg.obs_dim, cfg.n_branches, cfg.n_bins, (cfg.trunk, (cfg.branch_hidden,), (cfg.value_hidden,)), batch_size=B,
+                             buffer_size=256, gamma=cfg.gamma, target_network_update_freq=10 ** 9, prioritized_replay=True,
+                             prioritized_replay_alpha=alpha, prioritized_replay_eps=1e-6, seed=9)
+    L.load_parameters(params)
+    bt = _batch(cfg, NSLOT, 11)
+    bt["rew"] = (bt["rew"] * np.random.default_rng(1).uniform(0.1, 5.0, NSLOT)).astype(np.float32)       # spread of TD errors
+    for i in range(0, NSLOT, 70):                                                                         # several adds
+        sl = slice(i, min(NSLOT, i + 70))
+        L.replay_add(bt["obs"][sl], bt["act_idx"][sl].astype(np.float32), bt["rew"][sl], bt["next_obs"][sl], bt["done"][sl])
+    L.set_per_beta(beta)
+    prio = np.ones(NSLOT, np.float64)            # raw priorities; leaves hold prio ** alpha
+    counts = np.zeros(NSLOT, np.int64)
+    stationary_from = None
+    for it in range(1500):
+        L.step(1, lr=0.0)                        # lr = 0: the networks stay fixed, so every slot's TD error is a constant
+        slots, w, newp = L.last_per()
+        assert slots.min() >= 0 and slots.max() < NSLOT
+        leaves = prio ** alpha
+        p = leaves / leaves.sum()
+        max_w = (leaves.min() / leaves.sum() * NSLOT) ** (-beta)
+        w_ref = (p[slots] * NSLOT) ** (-beta) / max_w
+        assert np.abs(w - w_ref).max() <= 2e-5 * max(1.0, w_ref.max()), (it, np.abs(w - w_ref).max())
+        assert (newp > 0).all()
+        prio[slots] = newp                       # update_priorities; duplicates of a slot carry the same |TD| (lr = 0)
+        if stationary_from is None and (prio != 1.0).all() and it > 50:
+            stationary_from = it + 1
+        elif stationary_from is not None:
+            counts += np.bincount(slots, minlength=NSLOT)
+    assert stationary_from is not None
+    n = counts.sum()
+    leaves = prio ** alpha
+    expect = n * leaves / leaves.sum()
+    chi2 = float(((counts - expect) ** 2 / expect).sum())
+    assert abs(chi2 - (NSLOT - 1)) <= 6 * np.sqrt(2 * (NSLOT - 1)), (chi2, NSLOT - 1)
+    # priorities are the documented function of the TD errors: replay one slot through the explicit path
+    s0 = int(np.argmax(counts))
+    one = {k: np.repeat(v[s0:s0 + 1], B, axis=0) for k, v in bt.items()}
+    out = L.step_explicit(one["obs"], one["act_idx"].astype(np.float32), one["rew"], one["next_obs"], one["done"], lr=0.0, apply_update=False)
+    assert abs(np.abs(out["td"][0]).sum() + 1e-6 - prio[s0]) <= 1e-4 * prio[s0]
+    L.close()
+
+
+def test_bdq_two_rank_data_parallel_matches_oracle_on_concatenated_batch():
+    """cfg4: BDQ data parallel -- every rank takes its half of a seeded batch, one NCCL all-reduce averages the gradients,
+    the result equals the oracle's step on the concatenated batch and the replicas stay identical."""
+    import os, subprocess, sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29541", os.path.join(root, "tests", "multi_gpu_bdq_worker.py")], capture_output=True, text=True, timeout=600)
+    print(r.stdout[-3000:], r.stderr[-3000:])
+    assert r.returncode == 0

@@ -51,7 +51,7 @@ def test_learn_predict_save_load_roundtrip(tmp_path):
     a2, _ = m2.predict(obs, deterministic=True)
     assert np.abs(a1 - a2).max() <= 1e-6
     # sb_helper.py:113-115 warm start: load_parameters(get_parameters(), exact_match=False)
-    m3 = b200grasp.SAC(b200grasp.CnnPolicy, env, policy_kwargs={"layers": [64, 64]}, buffer_size=100, batch_size=8)
+    m3 = b200grasp.SAC(b200grasp.CnnPolicy, env, policy_kwargs={"layers": [64, 64], "cnn_extractor": None}, buffer_size=100, batch_size=8)
     m3.load_parameters({k: v for k, v in params.items() if "pi/" in k}, exact_match=False)
     a3, _ = m3.predict(obs, deterministic=True)
     assert np.abs(a1 - a3).max() <= 1e-6
@@ -72,3 +72,29 @@ def test_load_reference_trained_zip_and_predict(tmp_path):
     got = model.learner.act(raw, deterministic=True)
     ref = R.policy_act(params, R.normalize_obs(raw, vn["obs_mean"], vn["obs_var"]), cfg, deterministic=True)
     assert np.abs(got - ref).max() <= 1e-5
+
+
+def test_train_and_run_cli_on_a_reference_layout_model_dir(tmp_path):
+    """f2: the `train` / `run` sub-commands (train_stable_baselines.py:26-109) against the synthetic env: model_dir layout,
+    checkpoints, best_model + vecnormalize.pkl, then `run` loads config.yaml / vecnormalize.pkl / the zip and rolls out."""
+    import yaml
+    from b200grasp import train_cli
+    cfg = {"normalize": True, "discount_factor": 0.99, "simplified": False, "reward": {"shaped": False}, "robot": {"discrete": False},
+           "simulation": {"real_time": False, "visualize": False},
+           "SAC": {"layers": [64, 64], "buffer_size": 2000, "batch_size": 32, "step_size": 3e-4, "total_timesteps": 150, "tensorboard_logs": None}}
+    cpath = tmp_path / "cfg.yaml"
+    yaml.safe_dump(cfg, open(cpath, "w"))
+    mdir = str(tmp_path / "run1")
+    model = train_cli.main(["train", "--config", str(cpath), "--algo", "SAC", "--model_dir", mdir, "--env", "tests.fake_env:make_env",
+                            "--eval_freq", "60", "--checkpoint_freq", "50", "--n_envs", "2"])
+    assert model.n_updates > 0
+    for f in ("config.yaml", "best_model/config.yaml", "final_model.zip", "vecnormalize.pkl", "best_model/best_model.zip",
+              "best_model/vecnormalize.pkl"):
+        assert os.path.exists(os.path.join(mdir, f)), f
+    assert any(f.startswith("rl_model_") and f.endswith(".zip") for f in os.listdir(os.path.join(mdir, "logs")))
+    assert yaml.safe_load(open(os.path.join(mdir, "config.yaml")))["algorithm"] == "sac"
+    model.close()
+    out = train_cli.main(["run", "--model", os.path.join(mdir, "best_model", "best_model.zip"), "--env", "tests.fake_env:make_env", "--episodes", "3", "-t"])
+    assert out["episodes"] == 3 and np.isfinite(out["mean_reward"]) and out["mean_steps"] == 20
+    with pytest.raises(FileExistsError):
+        train_cli.main(["train", "--config", str(cpath), "--algo", "SAC", "--model_dir", mdir, "--env", "tests.fake_env:make_env"])

@@ -44,9 +44,9 @@ def test_out_of_scope_algorithms_and_policies_fail_loudly():
     from b200grasp.sac.policies import LnCnnPolicy
     with pytest.raises(NotImplementedError):
         sb.SAC(LnCnnPolicy, None, _init_setup_model=False)
-    from b200grasp.common.vec_env import SubprocVecEnv
+    from b200grasp.common.vec_env import VecFrameStack
     with pytest.raises(NotImplementedError):
-        SubprocVecEnv([])
+        VecFrameStack([])
 
 
 class _ConstModel:
@@ -134,3 +134,41 @@ def test_checkpoint_eval_and_every_n_callbacks(tmp_path):
     z = np.load(str(tmp_path / "ev" / "evaluations.npz"))
     assert list(z["timesteps"]) == [5, 10] and z["results"].shape == (2, 2)
     assert 5 in fired and 4 in fired and 8 in fired
+
+
+def test_subproc_vec_env_steps_environments_in_worker_processes():
+    """The host actor loop of BASELINE config 5 (sb_helper.py:19 imports SubprocVecEnv): N environments in worker
+    processes, auto-reset with the terminal observation kept in info, same arrays as DummyVecEnv on the same seeds."""
+    from b200grasp.vec_env import DummyVecEnv, SubprocVecEnv
+    from tests.fake_env import FakeGraspEnv
+    fns = [(lambda i=i: FakeGraspEnv(seed=i, horizon=3)) for i in range(3)]
+    sub, dum = SubprocVecEnv(fns), DummyVecEnv(fns)
+    try:
+        assert sub.num_envs == 3 and tuple(sub.observation_space.shape) == (64, 64, 2)
+        o1, o2 = sub.reset(), dum.reset()
+        assert o1.shape == (3, 64, 64, 2) and np.array_equal(o1, o2)
+        for t in range(4):
+            a = np.full((3, 5), 0.6 if t % 2 else -0.6, np.float32)
+            r1, r2 = sub.step(a), dum.step(a)
+            assert np.array_equal(r1[0], r2[0]) and np.array_equal(r1[1], r2[1]) and np.array_equal(r1[2], r2[2])
+            if t == 2:
+                assert r1[2].all() and all("terminal_observation" in i for i in r1[3])
+        assert sub.get_attr("horizon") == [3, 3, 3]
+    finally:
+        sub.close()
+
+
+def test_cnn_policy_without_extractor_is_refused_and_cli_parses():
+    """CnnPolicy with policy_kwargs={} is stable-baselines' plain nature_cnn (sb_helper.py:93-95), not the
+    augmented extractor -- refuse instead of silently building a different network.  Also the train / run CLI surface."""
+    from b200grasp.vec_env import DummyVecEnv
+    from b200grasp.train_cli import build_parser
+    from tests.fake_env import FakeGraspEnv
+    env = DummyVecEnv([lambda: FakeGraspEnv()])
+    with pytest.raises(NotImplementedError, match="nature_cnn"):
+        sb.SAC(sb.CnnPolicy, env, policy_kwargs={})
+    p = build_parser()
+    a = p.parse_args(["train", "--config", "c.yaml", "--algo", "SAC", "--model_dir", "out", "-s", "-sh", "--timestep", "1000"])
+    assert a.func.__name__ == "train" and a.simple and a.shaped and a.timestep == "1000" and a.load_dir is None
+    r = p.parse_args(["run", "--model", "m/best_model.zip", "-t", "-s"])
+    assert r.func.__name__ == "run" and r.test and r.stochastic
