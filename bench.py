@@ -23,13 +23,16 @@ import time
 
 import numpy as np
 
+os.environ.setdefault("NCCL_DEBUG", "WARN")        # no "NCCL version" banner on stdout: the driver reads ONE JSON line
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 GOLD = os.path.join(ROOT, "tests", "golden")
 FLOP_PER_STEP_B256 = 2 * 256 * 18_923_328          # 9.689 GFLOP
 LR = 3e-4
-KERNEL_DESC = ("gg_tc_kernel (tcgen05 gather-GEMM, cp.async-fed BF16 hi/lo planes: convs, cnn_fc1 and head fc0 layers, "
-               "fwd/wgrad/dgrad; 11 launches per step)")
+KERNEL_DESC = ("cg_kernel (TMA-fed tcgen05 contraction engine, csrc/cg.cu: one elected thread issues cp.async.bulk.tensor boxes -- "
+               "implicit-im2col / shifted-window / zero-bordered tensor-map views of the BF16 activation planes -- into a 128B-swizzled "
+               "smem ring; tcgen05.mma kind::f16 with fp32 TMEM accumulators; forward = 6-product 3-plane split, backward = "
+               "3-product 2-plane split; 10 launches per step) + gg_tc_kernel for the four small head wgrads")
 WORKLOAD = "SAC depth CNN (config/gripper_grasp.yaml), batch 256/GPU, 64x64x2 obs, 1M-slot replay"
 
 

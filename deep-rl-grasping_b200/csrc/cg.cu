@@ -253,10 +253,15 @@ cg_kernel(const __grid_constant__ CgPack pk, int nprob, int total_tiles, const C
                 db[pl] = mnm ? desc_mn(pb, b_lbo) : desc_k(pb);
               }
               const uint32_t first = (c == ti.c_begin && k == 0) ? 0u : 1u;
-              // smallest terms first: they are added to a small accumulator before the leading product arrives
-              if (nprod >= 6) { umma(acc, da[2], db[0], idesc, first); umma(acc, da[0], db[2], idesc, 1u); umma(acc, da[1], db[1], idesc, 1u); }
-              if (nprod >= 3) { umma(acc, da[1], db[0], idesc, nprod >= 6 ? 1u : first); umma(acc, da[0], db[1], idesc, 1u); }
-              umma(acc, da[0], db[0], idesc, nprod >= 3 ? 1u : first);
+              // Two accumulators per tile.  The tensor core truncates the fp32 accumulator at every MMA (measured:
+              // tools/tc_accum_probe.py, ~2^-25 relative bias per accumulation), so the CORRECTION products (hi*lo, lo*hi and
+              // the mid terms: 2^-8 .. 2^-16 of the leading product) go to their own accumulator, where that truncation is
+              // 2^-8 smaller, and the leading accumulator only sees one hi*hi per k-step (6x fewer truncations in the
+              // 6-product mode).  The epilogue adds the two in fp32 (round to nearest).
+              const uint32_t accc = acc + 128u;
+              if (nprod >= 6) { umma(accc, da[2], db[0], idesc, first); umma(accc, da[0], db[2], idesc, 1u); umma(accc, da[1], db[1], idesc, 1u); }
+              if (nprod >= 3) { umma(accc, da[1], db[0], idesc, nprod >= 6 ? 1u : first); umma(accc, da[0], db[1], idesc, 1u); }
+              umma(acc, da[0], db[0], idesc, first);
             }
           }
           umma_commit(smem_u32(&bar_empty[s]));
@@ -279,6 +284,7 @@ cg_kernel(const __grid_constant__ CgPack pk, int nprob, int total_tiles, const C
     int epi = 0, rows_tile = 0, lim_rows = 0, umma_n = 0, out_planes = 0, grp_stride = 32, n_valid = 0;
     long long roff = 0, rmoff = 0, o_tm = 0, m_tm = 0;
     int ri0 = 0, ri1 = 0, grp_tab = 0;
+    bool two_acc = false;
     const float* __restrict__ bias = nullptr;
     const uint16_t* __restrict__ mask = nullptr;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -290,7 +296,7 @@ cg_kernel(const __grid_constant__ CgPack pk, int nprob, int total_tiles, const C
         const int i0 = r % d0, i12 = r / d0, i1 = i12 % d1, i2 = i12 / d1;
         roff = Q.o_base + (long long)i0 * Q.o0 + (long long)i1 * Q.o1 + (long long)i2 * Q.o2;
         rmoff = Q.m_base + (long long)i0 * Q.m0 + (long long)i1 * Q.m1 + (long long)i2 * Q.m2;
-        ri0 = i0; ri1 = i1; grp_tab = Q.grp_tab;
+        ri0 = i0; ri1 = i1; grp_tab = Q.grp_tab; two_acc = Q.nprod > 1;
       }
       const Tile ti = w.tile(tile);
       if (ti.c_end <= ti.c_begin) continue;
@@ -314,6 +320,20 @@ cg_kernel(const __grid_constant__ CgPack pk, int nprob, int total_tiles, const C
               "=r"(v[31])
             : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (two_acc) {
+          uint32_t u[32];
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+              "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+              : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), "=r"(u[9]), "=r"(u[10]),
+                "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]), "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]),
+                "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]),
+                "=r"(u[31])
+              : "r"(taddr + 128u));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+        }
         if (dbg_nostore || ng >= n_valid) continue;
         bool valid = valid0;
         long long off = off0, moff = moff0;

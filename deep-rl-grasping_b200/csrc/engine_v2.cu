@@ -43,20 +43,46 @@ __global__ void __launch_bounds__(256) gather2_kernel(Gather2Args a) {
   const GatherArgs& g = a.g;
   const int b = blockIdx.x, which = blockIdx.y, tid = threadIdx.x;
   const int Ci = a.Ci, Cfull = g.Cfull, HW = g.H * g.W, npx = HW * Ci;
-  const int E = HW * Cfull;
+  const int Ec = npx + 4;                                  // compact replay row: image planes | actuator value | 3 pad floats
   long long slot = b;
   if (g.indices) slot = g.indices[b];
   else if (g.rng_counters) {
     slot = philox_slot(g.seed, (unsigned long long)g.rng_counters[4], b, (unsigned long long)g.rng_counters[5]);
     if (g.indices_out && which == 0 && tid == 0) g.indices_out[b] = (int)slot;
   }
-  const float* __restrict__ src = (which ? g.next_obs : g.obs) + (size_t)slot * E;
+  const float* __restrict__ src = (which ? g.next_obs : g.obs) + (size_t)slot * Ec;
   const double clip_obs = g.normc[1];
   const bool norm_obs = g.normc[3] != 0.0;
   const float scale = g.scale;
   uint16_t* s0 = sm_planes; uint16_t* s1 = s0 + npx; uint16_t* s2 = s1 + npx;
   uint16_t* xh = a.xp[which][0]; uint16_t* xl = a.xp[which][1];
-  auto put_feature = [&](float yy) {                         // direct feature -> column 512 of the feature rows
+  (void)Cfull;
+  // image block: exactly the NHWC image with Ci channels -> no index arithmetic; float64 VecNormalize chain per element
+  for (int e4 = tid; e4 < (npx >> 2); e4 += blockDim.x) {
+    const float4 v = *reinterpret_cast<const float4*>(src + 4 * e4);
+    float y[4] = {v.x, v.y, v.z, v.w};
+    if (norm_obs) {
+      const double2 m0 = *reinterpret_cast<const double2*>(g.mean + 4 * e4), m1 = *reinterpret_cast<const double2*>(g.mean + 4 * e4 + 2);
+      const double2 i0 = *reinterpret_cast<const double2*>(g.var + 4 * e4), i1 = *reinterpret_cast<const double2*>(g.var + 4 * e4 + 2);
+      y[0] = (float)fmin(fmax(((double)y[0] - m0.x) * i0.x, -clip_obs), clip_obs);
+      y[1] = (float)fmin(fmax(((double)y[1] - m0.y) * i0.y, -clip_obs), clip_obs);
+      y[2] = (float)fmin(fmax(((double)y[2] - m1.x) * i1.x, -clip_obs), clip_obs);
+      y[3] = (float)fmin(fmax(((double)y[3] - m1.y) * i1.y, -clip_obs), clip_obs);
+    }
+    uint16_t p[3][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) split3(y[j] / scale, p[0][j], p[1][j], p[2][j]);
+#pragma unroll
+    for (int pl = 0; pl < 3; ++pl) {
+      const uint2 w = make_uint2((uint32_t)p[pl][0] | ((uint32_t)p[pl][1] << 16), (uint32_t)p[pl][2] | ((uint32_t)p[pl][3] << 16));
+      reinterpret_cast<uint2*>(sm_planes + pl * npx)[e4] = w;
+      if (xh && pl < 2) reinterpret_cast<uint2*>((pl ? xl : xh) + (size_t)b * npx)[e4] = w;
+    }
+  }
+  if (tid == 0) {                                            // direct feature -> column 512 of the feature rows
+    float yy = src[npx];
+    if (norm_obs) yy = (float)fmin(fmax(((double)yy - g.mean[npx]) * g.var[npx], -clip_obs), clip_obs);
+    yy = yy / scale;
     uint16_t p0, p1, p2;
     split3(yy, p0, p1, p2);
     const size_t fo = (size_t)b * g.FS + g.feat_col, po = (size_t)b * a.KF + g.feat_col;
@@ -65,48 +91,6 @@ __global__ void __launch_bounds__(256) gather2_kernel(Gather2Args a) {
       g.F_pi[fo] = yy; g.F_v[fo] = yy;
       a.fp[0][0][po] = p0; a.fp[0][1][po] = p1; a.fp[0][2][po] = p2;
       a.fp[1][0][po] = p0; a.fp[1][1][po] = p1; a.fp[1][2][po] = p2;
-    }
-  };
-  if (Cfull == 2) {
-    // depth configuration: a 16-byte group is {pixel, actuator, pixel, actuator}; the float64 chain runs on the two image
-    // values only (the actuator plane is read at pixel [0,0] alone), no run-time div/mod, packed 4-byte plane stores
-    for (int e4 = tid; e4 < (E >> 2); e4 += blockDim.x) {
-      const float4 v = *reinterpret_cast<const float4*>(src + 4 * e4);
-      float y0 = v.x, y1 = v.z;
-      if (norm_obs) {
-        const double2 m0 = *reinterpret_cast<const double2*>(g.mean + 4 * e4), m1 = *reinterpret_cast<const double2*>(g.mean + 4 * e4 + 2);
-        const double2 i0 = *reinterpret_cast<const double2*>(g.var + 4 * e4), i1 = *reinterpret_cast<const double2*>(g.var + 4 * e4 + 2);
-        y0 = (float)fmin(fmax(((double)y0 - m0.x) * i0.x, -clip_obs), clip_obs);
-        y1 = (float)fmin(fmax(((double)y1 - m1.x) * i1.x, -clip_obs), clip_obs);
-        if (e4 == 0) put_feature((float)fmin(fmax(((double)v.y - m0.y) * i0.y, -clip_obs), clip_obs) / scale);
-      } else if (e4 == 0) put_feature(v.y / scale);
-      y0 = y0 / scale; y1 = y1 / scale;
-      uint16_t a0, a1, a2, b0, b1, b2;
-      split3(y0, a0, a1, a2);
-      split3(y1, b0, b1, b2);
-      const uint32_t w0 = (uint32_t)a0 | ((uint32_t)b0 << 16), w1 = (uint32_t)a1 | ((uint32_t)b1 << 16), w2 = (uint32_t)a2 | ((uint32_t)b2 << 16);
-      reinterpret_cast<uint32_t*>(s0)[e4] = w0; reinterpret_cast<uint32_t*>(s1)[e4] = w1; reinterpret_cast<uint32_t*>(s2)[e4] = w2;
-      if (xh) { reinterpret_cast<uint32_t*>(xh + (size_t)b * npx)[e4] = w0; reinterpret_cast<uint32_t*>(xl + (size_t)b * npx)[e4] = w1; }
-    }
-  } else
-  for (int e4 = tid; e4 < (E >> 2); e4 += blockDim.x) {
-    const float4 v = *reinterpret_cast<const float4*>(src + 4 * e4);
-    float y[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int e = 4 * e4 + j;
-      const int c = e % Cfull, pix = e / Cfull;
-      if (c == Ci && pix != 0) continue;                      // actuator plane: only pixel [0,0] is ever read
-      float yy = y[j];
-      if (norm_obs) yy = (float)fmin(fmax(((double)yy - g.mean[e]) * g.var[e], -clip_obs), clip_obs);
-      yy = yy / scale;
-      if (c < Ci) {
-        uint16_t p0, p1, p2;
-        split3(yy, p0, p1, p2);
-        const int o = pix * Ci + c;
-        s0[o] = p0; s1[o] = p1; s2[o] = p2;
-        if (xh) { xh[(size_t)b * npx + o] = p0; xl[(size_t)b * npx + o] = p1; }
-      } else put_feature(yy);
     }
   }
   __syncthreads();
@@ -144,6 +128,20 @@ __global__ void __launch_bounds__(256) gather2_kernel(Gather2Args a) {
       g.done_out[b] = g.done[slot];
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------ replay row compaction
+// full observation [HW][Cfull] -> compact row {image planes [HW][Ci] | value at pixel [0,0] of the last plane | 3 pad}
+__global__ void __launch_bounds__(256) compact_kernel(const float* __restrict__ src, float* __restrict__ dst, long long first_row, long long wrap,
+                                                       int HW, int Cfull, int Ec) {
+  const int Ci = Cfull - 1;
+  const float* s = src + (size_t)blockIdx.x * HW * Cfull;
+  float* d = dst + (size_t)((first_row + blockIdx.x) % wrap) * Ec;
+  for (int e = threadIdx.x; e < HW * Ci; e += blockDim.x) {
+    const int pix = e / Ci, c = e - pix * Ci;
+    d[e] = s[(size_t)pix * Cfull + c];
+  }
+  if (threadIdx.x < 4) d[HW * Ci + threadIdx.x] = threadIdx.x == 0 ? s[Ci] : 0.f;
 }
 
 // ------------------------------------------------------------------------------------------------ planes2
@@ -311,6 +309,7 @@ int push_group(b2g_sac* h, std::vector<CgGroup>& list, CgGroup& g, const char* n
   if (cg_finalize(g, cg_smem_limit()) != 0) return b2g_fail(B2G_EINVAL, std::string("engine v2: stage ring of group ") + name + " does not fit shared memory");
   for (int i = 0; i < g.n; ++i) {
     const CgProblem& P = g.host[i];
+    if (P.nprod > 1 && P.umma_n > 128) return b2g_fail(B2G_EINVAL, std::string("engine v2: split-precision tiles are at most 128 wide (group ") + name + ")");
     g.flops += 2.0 * P.tiles_m * 128.0 * P.tiles_n * P.umma_n * P.chunks * 64.0;      // issued (tile-padded) work
   }
   list.push_back(g);
@@ -628,7 +627,7 @@ int v2_create(b2g_sac* h) {
           P.ld[2] = mk_load(mB, 2, P.b_off); P.ld[2].d_c2[1] = 64;
           P.tm_tab = dtab;
           P.tiles_m = 5; P.tiles_n = 1;
-          P.splits = std::max(1, std::min(P.chunks, 14));
+          P.splits = std::max(1, std::min(P.chunks, std::max(14, (P.chunks + 15) / 16)));     // <= 16 chunks (64 k-steps) per accumulator chain
           P.lim_rows = 576; P.o_tm = 128 * 64; P.o0 = 64; P.n_valid = 64;
           P.out_f = h->g(std::string(nets[n]) + "/cnn3/w"); P.atomic = 1;
           g.host[g.n++] = P;
@@ -686,7 +685,7 @@ int v2_create(b2g_sac* h) {
         for (int a = 0; a < 2; ++a) { P.ld[a] = mk_load(mA, 4, a * 144 * 128); P.ld[a].c0[1] = 2 * a; P.ld[a].d_tm[2] = 1; P.ld[a].d_c2[3] = 4; }
         P.ld[2] = mk_load(mB, 2, P.b_off); P.ld[2].d_c2[1] = 144;
         P.tiles_m = 4; P.tiles_n = 1;
-        P.splits = std::max(1, std::min(P.chunks, 8));
+        P.splits = std::max(1, std::min(P.chunks, std::max(8, (P.chunks + 7) / 8)));           // <= 8 chunks (72 k-steps) per chain
         P.lim_rows = 512; P.o_tm = 128 * 64; P.o0 = 64; P.n_valid = 64;
         P.out_f = h->g(std::string(nets[n]) + "/cnn2/w"); P.atomic = 1;
         g.host[g.n++] = P;
@@ -702,7 +701,7 @@ int v2_create(b2g_sac* h) {
         for (int a = 0; a < 2; ++a) { P.ld[a] = mk_load(mA, 2, a * 8192); P.ld[a].c0[0] = 64 * a; P.ld[a].d_tm[0] = 128; P.ld[a].d_c2[1] = 64; }
         P.ld[2] = mk_load(mB, 2, P.b_off); P.ld[2].d_c2[1] = 64;
         P.tiles_m = (K1 + 127) / 128; P.tiles_n = 1;
-        P.splits = std::max(1, std::min(P.chunks, 84 / P.tiles_m));
+        P.splits = std::max(1, std::min(P.chunks, std::max(84 / P.tiles_m, (P.chunks + 15) / 16)));
         P.lim_rows = K1; P.o_tm = 128 * 32; P.o0 = 32; P.n_valid = 64;
         P.out_f = h->g("model/pi/cnn1/w"); P.f_grp = (long long)(h->g("model/values_fn/cnn1/w") - h->g("model/pi/cnn1/w")); P.atomic = 1;
         g.host[g.n++] = P;
@@ -711,24 +710,30 @@ int v2_create(b2g_sac* h) {
     }
     // ---- bias gradients from the gradient-map planes
     {
-      std::vector<Colsum2Job> cj;
-      int cstart = 0;
-      auto add_cs = [&](uint16_t* const* pl, float* dst, int rows, int pitch, int col0, int N) {
-        Colsum2Job j{pl[0], pl[1], dst, rows, pitch, col0, N, cstart};
-        const int rows_per_cta = 16 * (256 / (N >> 3));
-        cstart += (rows + rows_per_cta - 1) / rows_per_cta;
-        cj.push_back(j);
-      };
-      for (int n = 0; n < 2; ++n) {
-        add_cs(v.dZ1, h->g(std::string(nets[n]) + "/cnn1/b"), B * 225, 64, 32 * n, 32);
-        add_cs(v.dZ2[n], h->g(std::string(nets[n]) + "/cnn2/b"), B * 36, 64, 0, 64);
-        add_cs(v.dZ3[n], h->g(std::string(nets[n]) + "/cnn3/b"), B * 16, 64, 0, 64);
-        add_cs(v.dZ4[n], h->g(std::string(nets[n]) + "/cnn_fc1/b"), B, 512, 0, 512);
+      // two launches: [0] the cnn_fc1 biases (need dZ4 only: ready right after heads_dgrad, part of the EARLY all-reduce range),
+      // [1] the conv biases (need every gradient map)
+      for (int part = 0; part < 2; ++part) {
+        std::vector<Colsum2Job> cj;
+        int cstart = 0;
+        auto add_cs = [&](uint16_t* const* pl, float* dst, int rows, int pitch, int col0, int N) {
+          Colsum2Job j{pl[0], pl[1], dst, rows, pitch, col0, N, cstart};
+          const int rows_per_cta = 16 * (256 / (N >> 3));
+          cstart += (rows + rows_per_cta - 1) / rows_per_cta;
+          cj.push_back(j);
+        };
+        for (int n = 0; n < 2; ++n) {
+          if (part == 0) add_cs(v.dZ4[n], h->g(std::string(nets[n]) + "/cnn_fc1/b"), B, 512, 0, 512);
+          else {
+            add_cs(v.dZ1, h->g(std::string(nets[n]) + "/cnn1/b"), B * 225, 64, 32 * n, 32);
+            add_cs(v.dZ2[n], h->g(std::string(nets[n]) + "/cnn2/b"), B * 36, 64, 0, 64);
+            add_cs(v.dZ3[n], h->g(std::string(nets[n]) + "/cnn3/b"), B * 16, 64, 0, 64);
+          }
+        }
+        Colsum2Job* dcj = nullptr;
+        if (int rc = valloc(h, &dcj, cj.size())) return rc;
+        B2G_CK(cudaMemcpy(dcj, cj.data(), cj.size() * sizeof(Colsum2Job), cudaMemcpyHostToDevice));
+        v.colsum_part[part] = dcj; v.n_colsum_part[part] = (int)cj.size(); v.colsum_ctas_part[part] = cstart;
       }
-      Colsum2Job* dcj = nullptr;
-      if (int rc = valloc(h, &dcj, cj.size())) return rc;
-      B2G_CK(cudaMemcpy(dcj, cj.data(), cj.size() * sizeof(Colsum2Job), cudaMemcpyHostToDevice));
-      v.colsum_jobs = dcj; v.n_colsum_jobs = (int)cj.size(); v.colsum_ctas = cstart;
     }
   }
   if (int rc = valloc(h, &v.d_maps, v.maps.size())) return rc;
@@ -741,6 +746,11 @@ int v2_create(b2g_sac* h) {
 int v2_planes(b2g_sac* h, cudaStream_t s) {
   V2State& v = h->v2;
   planes2_kernel<<<v.plane_ctas, 256, 0, s>>>((const Plane2Job*)v.plane_jobs, v.n_plane_jobs);
+  return 0;
+}
+
+int v2_compact_rows(b2g_sac* h, const float* src_full, float* dst, long long first_row, long long wrap, int n, cudaStream_t s) {
+  if (n > 0) compact_kernel<<<n, 256, 0, s>>>(src_full, dst, first_row, wrap, h->Hi * h->Wi, h->Cimg + 1, h->Ec);
   return 0;
 }
 
@@ -764,14 +774,15 @@ int v2_gather(b2g_sac* h, const GatherArgs& ga, cudaStream_t s) {
   return 0;
 }
 
-int v2_colsum(b2g_sac* h, cudaStream_t s) {
+int v2_colsum(b2g_sac* h, cudaStream_t s, int part) {
   V2State& v = h->v2;
-  if (v.colsum_ctas > 0) colsum2_kernel<<<v.colsum_ctas, 256, 0, s>>>((const Colsum2Job*)v.colsum_jobs, v.n_colsum_jobs);
+  if (v.colsum_ctas_part[part] > 0)
+    colsum2_kernel<<<v.colsum_ctas_part[part], 256, 0, s>>>((const Colsum2Job*)v.colsum_part[part], v.n_colsum_part[part]);
   return 0;
 }
 
 int v2_launch(b2g_sac* h, const CgGroup& g, cudaStream_t s) {
-  B2G_CK(cg_launch(g, h->v2.d_maps, h->num_sms, s, pdl_enabled(), h->v2.dbg));
+  B2G_CK(cg_launch(g, h->v2.d_maps, h->num_sms - h->v2.sm_reserve, s, pdl_enabled(), h->v2.dbg));
   return 0;
 }
 

@@ -847,6 +847,15 @@ int issue_step(b2g_sac* h, bool sampled, bool apply, bool want_per_sample, Prof*
   }
   if (h->v2.on) {
     if (!fork) { if (int rc = v2_planes(h, s)) return rc; ++n; mark("weight_planes_v2"); }
+    if (h->compact) {
+      if (!sampled) {       // host-supplied batch (full layout): compact it like replay_add does
+        if (int rc = v2_compact_rows(h, h->s_obs, h->cs_obs, 0, h->B, h->B, s)) return rc;
+        if (int rc = v2_compact_rows(h, h->s_next, h->cs_next, 0, h->B, h->B, s)) return rc;
+        n += 2;
+        ga.obs = h->cs_obs; ga.next_obs = h->cs_next;
+      }
+      ga.mean = h->d_mean_c; ga.var = h->d_istd_c;
+    }
     if (int rc = v2_gather(h, ga, s)) return rc;
   } else gather_launch(ga, s);
   ++n; mark("gather_normalize");
@@ -907,7 +916,7 @@ int issue_step(b2g_sac* h, bool sampled, bool apply, bool want_per_sample, Prof*
     oa.metrics = h->metrics; oa.apply = apply ? 1 : 0;
     return oa;
   };
-  const bool overlap = !h->v2.bwd && h->overlap_ar && h->cnn && last_fc1 >= 0 && last_fc1 + 1 < (int)h->bwd_groups.size();
+  const bool overlap = h->overlap_ar && h->cnn && h->cfg.nranks > 1 && last_fc1 >= 0 && last_fc1 + 1 < (int)h->bwd_groups.size();
   const int64_t pi_fc1 = h->tensors[h->tindex.at("model/pi/" + std::string(h->cnn ? "cnn_fc1/w" : "fc0/kernel"))].off;
   const int64_t v_fc1 = h->tensors[h->tindex.at("model/values_fn/" + std::string(h->cnn ? "cnn_fc1/w" : "vf/fc0/kernel"))].off;
   const bool early_opt = !h->v2.bwd && fork && h->early_opt && h->cfg.nranks == 1 && h->cnn && last_fc1 >= 0 && last_fc1 + 1 < (int)h->bwd_groups.size() &&
@@ -918,21 +927,47 @@ int issue_step(b2g_sac* h, bool sampled, bool apply, bool want_per_sample, Prof*
   };
   if (h->v2.bwd) {
     // backward chain on engine v2; the small head wgrads (fc0 / fc1 kernels and biases: fp32 operands, register-staged) stay
-    // on the v1 engine and, like the bias column sums, run on the leaf branch
+    // on the v1 engine and, like the bias column sums, run on the leaf branch.
+    // N > 1: the gradients of [cnn_fc1 .. end] of both trainable blocks (+ log_ent_coef + the loss scalars: 84 % of the
+    // bytes) are final after fc1_bwd, so their all-reduce runs on a side stream / second communicator underneath the conv
+    // backward (the GEMM grids leave ar_sms SMs to it); only the conv ranges (0.6 MB) are reduced on the critical chain.
+    const bool ov = h->overlap_ar && h->cfg.nranks > 1;
+    h->v2.sm_reserve = 0;
+    cudaStream_t lx = fork ? ax : s;
     for (auto& g : h->bwd_groups) {
       if (g.name != "heads_wgrad") continue;
       if (fork) { CK(cudaEventRecord(h->ev_aux[2], s)); CK(cudaStreamWaitEvent(ax, h->ev_aux[2], 0)); }
-      if (int rc = run_group(g, fork ? ax : s)) return rc;
+      if (int rc = run_group(g, lx)) return rc;
     }
     for (auto& g : h->v2.bwd_groups) {
       if (int rc = v2_launch(h, g, s)) return rc;
       ++n; mark(g.name);
-      if (std::string(g.name) == "conv2_dgrad") {          // every gradient map exists: bias sums overlap the conv wgrads
-        if (fork) { CK(cudaEventRecord(h->ev_aux[4], s)); CK(cudaStreamWaitEvent(ax, h->ev_aux[4], 0)); }
-        if (int rc = v2_colsum(h, fork ? ax : s)) return rc;
+      const std::string gn(g.name);
+      if (gn == "heads_dgrad") {            // dZ4 exists: cnn_fc1 bias sums on the leaf branch
+        if (fork) { CK(cudaEventRecord(h->ev_aux[3], s)); CK(cudaStreamWaitEvent(ax, h->ev_aux[3], 0)); }
+        if (int rc = v2_colsum(h, lx, 0)) return rc;
+        ++n; if (!fork) mark("bias_grads_fc1");
+      }
+      if (gn == "fc1_bwd" && ov) {
+        CK(cudaMemcpyAsync(h->G + h->n_train, h->metrics, MET_GN_PI * sizeof(float), cudaMemcpyDeviceToDevice, s)); ++n;
+        CK(cudaEventRecord(h->ev_fork, s));
+        CK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+        if (fork) { CK(cudaEventRecord(h->ev_aux[4], ax)); CK(cudaStreamWaitEvent(h->side, h->ev_aux[4], 0)); }   // heads_wgrad + fc1 bias sums
+        if (int rc = nccl_ck(g_nccl.GroupStart())) return rc;
+        if (int rc = nccl_ck(g_nccl.AllReduce(h->G + pi_fc1, h->G + pi_fc1, (size_t)(h->n_pi - pi_fc1), 7, 0, h->nccl_comm2, h->side))) return rc;
+        if (int rc = nccl_ck(g_nccl.AllReduce(h->G + v_fc1, h->G + v_fc1, (size_t)(h->n_train + MET_COUNT - v_fc1), 7, 0, h->nccl_comm2, h->side))) return rc;
+        if (int rc = nccl_ck(g_nccl.GroupEnd())) return rc;
+        ++n;
+        CK(cudaEventRecord(h->ev_join, h->side));
+        h->v2.sm_reserve = h->ar_sms;
+      }
+      if (gn == "conv2_dgrad") {            // every gradient map exists: conv bias sums overlap the conv wgrads
+        if (fork) { CK(cudaEventRecord(h->ev_aux[0], s)); CK(cudaStreamWaitEvent(ax, h->ev_aux[0], 0)); }
+        if (int rc = v2_colsum(h, lx, 1)) return rc;
         ++n; if (!fork) mark("bias_grads");
       }
     }
+    h->v2.sm_reserve = 0;
   } else
   for (size_t i = 0; i < h->bwd_groups.size(); ++i) {
     const bool leaf = fork && h->bwd_groups[i].name == "heads_wgrad";
@@ -1108,6 +1143,7 @@ int b2g_sac_destroy(b2g_sac* h) {
   for (void* q : h->allocs) cudaFree(q);
   if (h->h_met) cudaFreeHost(h->h_met);
   if (h->h_cnt) cudaFreeHost(h->h_cnt);
+  for (int k = 0; k < 2; ++k) { if (h->hp_stats[k]) cudaFreeHost(h->hp_stats[k]); if (h->ev_stats[k]) cudaEventDestroy(h->ev_stats[k]); }
   for (int j = 0; j < 2; ++j) {
     if (h->ev_h2d[j]) cudaEventDestroy(h->ev_h2d[j]);
     if (h->ev_consumed[j]) cudaEventDestroy(h->ev_consumed[j]);
@@ -1174,8 +1210,26 @@ int b2g_sac_create(const b2g_sac_cfg* cfg, b2g_sac** out) {
   DA(h->P, h->n_all); DA(h->Mo, h->n_train); DA(h->Vo, h->n_train); DA(h->G, h->n_train + MET_COUNT);
   DA(h->dbg_trace, 64 * 8); DA(h->metrics, MET_COUNT); DA(h->counters, 8); DA(h->step_consts, 4); DA(h->d_lr, 1);
   const int64_t cap = cfg->buffer_capacity;
-  DA(h->r_obs, cap * h->E); DA(h->r_next, cap * h->E); DA(h->r_act, cap * h->A); DA(h->r_rew, cap); DA(h->r_done, cap);
+  {   // engine v2 (TMA-fed, cg.cu) drives the parity mode; B2G_ENGINE=v1 keeps the round-1 engine
+    const char* en = getenv("B2G_ENGINE");
+    h->v2.on = h->cnn && cfg->precision == B2G_PREC_BF16X3 && !(en && en[0] == 'v' && en[1] == '1') && h->Hi == 64 && h->Wi == 64;
+    if (const char* dbg = getenv("B2G_CG_DEBUG")) h->v2.dbg = atoi(dbg);
+    { const char* eb = getenv("B2G_ENGINE_BWD"); h->v2.bwd = h->v2.on && !(eb && eb[0] == 'v' && eb[1] == '1'); }
+    h->compact = h->v2.on;        // the v2 gather reads compact rows only
+    h->Ec = h->compact ? h->Hi * h->Wi * h->Cimg + 4 : h->E;
+  }
+  // replay ring: 2 * cap * Ec * 4 bytes (depth: 32.8 GB at 1M slots in the compact layout, 65.6 GB in the full one)
+  DA(h->r_obs, cap * h->Ec); DA(h->r_next, cap * h->Ec); DA(h->r_act, cap * h->A); DA(h->r_rew, cap); DA(h->r_done, cap);
   DA(h->d_mean, h->E); DA(h->d_istd, h->E); DA(h->d_normc, 8);
+  if (h->compact) {
+    DA(h->cs_obs, (size_t)B * h->Ec); DA(h->cs_next, (size_t)B * h->Ec); DA(h->add_stage, (size_t)2 * 256 * h->E);
+    DA(h->d_mean_c, h->Ec); DA(h->d_istd_c, h->Ec);
+  }
+  for (int k = 0; k < 2; ++k) {
+    if (cudaMallocHost((void**)&h->hp_stats[k], (size_t)(2 * h->E + 2 * h->Ec + 8) * sizeof(double)) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_stats[k], cudaEventDisableTiming) != cudaSuccess)
+      return bail(fail(B2G_ECUDA, "norm-stat staging"));
+  }
   DA(h->s_obs, (size_t)B * h->E); DA(h->s_next, (size_t)B * h->E); DA(h->s_act, B * h->A); DA(h->s_rew, B); DA(h->s_done, B);
   if (h->cnn) {
     DA(h->x_obs, (size_t)B * h->Hi * h->Wi * h->Cimg); DA(h->x_next, (size_t)B * h->Hi * h->Wi * h->Cimg);
@@ -1188,13 +1242,7 @@ int b2g_sac_create(const b2g_sac_cfg* cfg, b2g_sac** out) {
     }
   }
   h->use_planes = h->cnn && cfg->precision != B2G_PREC_FP32_SIMT;
-  {   // engine v2 (TMA-fed, cg.cu) drives the forward chain of the parity mode; B2G_ENGINE=v1 keeps the round-1 engine
-    const char* en = getenv("B2G_ENGINE");
-    h->v2.on = h->cnn && cfg->precision == B2G_PREC_BF16X3 && !(en && en[0] == 'v' && en[1] == '1') && h->Hi == 64 && h->Wi == 64;
-    if (const char* dbg = getenv("B2G_CG_DEBUG")) h->v2.dbg = atoi(dbg);
-    { const char* eb = getenv("B2G_ENGINE_BWD"); h->v2.bwd = h->v2.on && !(eb && eb[0] == 'v' && eb[1] == '1'); }
-    if (h->v2.on && (rc = v2_alloc(h))) return bail(rc);
-  }
+  if (h->v2.on && (rc = v2_alloc(h))) return bail(rc);
   if (const char* pl = getenv("B2G_TC_PLANES")) if (pl[0] == '0') h->use_planes = false;
   h->wgrad_planes = h->use_planes;
   if (const char* pl = getenv("B2G_TC_WGRAD_PLANES")) h->wgrad_planes = h->use_planes && pl[0] != '0';
@@ -1261,8 +1309,9 @@ int b2g_sac_create(const b2g_sac_cfg* cfg, b2g_sac** out) {
   }
   // identity normalisation until b2g_set_norm_stats is called
   {
-    std::vector<double> ones(h->E, 1.0);
-    if (cudaMemcpyAsync(h->d_istd, ones.data(), h->E * sizeof(double), cudaMemcpyHostToDevice, h->stream) != cudaSuccess ||
+    std::vector<double> ones(std::max(h->E, h->Ec), 1.0);
+    if ((h->compact && cudaMemcpyAsync(h->d_istd_c, ones.data(), h->Ec * sizeof(double), cudaMemcpyHostToDevice, h->stream) != cudaSuccess) ||
+        cudaMemcpyAsync(h->d_istd, ones.data(), h->E * sizeof(double), cudaMemcpyHostToDevice, h->stream) != cudaSuccess ||
         cudaStreamSynchronize(h->stream) != cudaSuccess)
       return bail(fail(B2G_ECUDA, "init copy failed"));
   }
@@ -1279,7 +1328,10 @@ int b2g_sac_create(const b2g_sac_cfg* cfg, b2g_sac** out) {
       const char* ov = getenv("B2G_AR_OVERLAP");
       // opt-in (B2G_AR_OVERLAP=1): verified bit-correct at N=2, but measured gain is ~1 % because the persistent GEMM
       // grids occupy every SM (even with SMs reserved the collective's launch latency dominates), see DESIGN.md section 5
-      if ((ov && ov[0] == '1') && g_nccl.CommSplit && g_nccl.GroupStart && g_nccl.GroupEnd) {
+      // default: on for the v2 backward chain (B2G_AR_OVERLAP=0 puts the whole all-reduce back on the critical chain);
+      // the v1 chain keeps it opt-in (B2G_AR_OVERLAP=1)
+      const bool want_ov = h->v2.bwd ? !(ov && ov[0] == '0') : (ov && ov[0] == '1');
+      if (want_ov && g_nccl.CommSplit && g_nccl.GroupStart && g_nccl.GroupEnd) {
         if (g_nccl.CommSplit(h->nccl_comm, 0, cfg->rank, &h->nccl_comm2, nullptr) == 0 && h->nccl_comm2 &&
             cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) == cudaSuccess &&
             cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
@@ -1367,10 +1419,19 @@ int b2g_replay_add(b2g_sac* h, const float* obs, const float* act, const float* 
   const int64_t cap = h->cfg.buffer_capacity;
   int64_t done_n = 0;
   while (done_n < n) {
-    const int64_t chunk = std::min(n - done_n, cap - h->r_pos);
+    int64_t chunk = std::min(n - done_n, cap - h->r_pos);
     const size_t E = h->E, A = h->A;
+    if (h->compact) {       // full-layout rows are staged on the device and compacted into the ring
+      chunk = std::min<int64_t>(chunk, 256);
+      float* st0 = h->add_stage; float* st1 = h->add_stage + (size_t)256 * E;
+      CK(cudaMemcpyAsync(st0, obs + done_n * E, chunk * E * sizeof(float), cudaMemcpyDefault, h->stream));
+      CK(cudaMemcpyAsync(st1, next_obs + done_n * E, chunk * E * sizeof(float), cudaMemcpyDefault, h->stream));
+      if (int rc = v2_compact_rows(h, st0, h->r_obs, h->r_pos, cap, (int)chunk, h->stream)) return rc;
+      if (int rc = v2_compact_rows(h, st1, h->r_next, h->r_pos, cap, (int)chunk, h->stream)) return rc;
+    } else {
     CK(cudaMemcpyAsync(h->r_obs + h->r_pos * E, obs + done_n * E, chunk * E * sizeof(float), cudaMemcpyDefault, h->stream));
     CK(cudaMemcpyAsync(h->r_next + h->r_pos * E, next_obs + done_n * E, chunk * E * sizeof(float), cudaMemcpyDefault, h->stream));
+    }
     CK(cudaMemcpyAsync(h->r_act + h->r_pos * A, act + done_n * A, chunk * A * sizeof(float), cudaMemcpyDefault, h->stream));
     CK(cudaMemcpyAsync(h->r_rew + h->r_pos, rew + done_n, chunk * sizeof(float), cudaMemcpyDefault, h->stream));
     CK(cudaMemcpyAsync(h->r_done + h->r_pos, done + done_n, chunk * sizeof(float), cudaMemcpyDefault, h->stream));
@@ -1392,8 +1453,22 @@ int b2g_replay_get(b2g_sac* h, int64_t slot, float* obs, float* act, float* rew,
   CK(cudaSetDevice(h->cfg.device));
   CK(cudaStreamSynchronize(h->stream));
   const size_t E = h->E, A = h->A;
+  if (h->compact) {        // expand: the actuator plane comes back as zeros except pixel [0,0] (all the policy ever reads of it)
+    std::vector<float> row(h->Ec);
+    const int Ci = h->Cimg, Cf = Ci + 1, HW = h->Hi * h->Wi;
+    for (int w = 0; w < 2; ++w) {
+      float* dst = w ? next_obs : obs;
+      if (!dst) continue;
+      CK(cudaMemcpy(row.data(), (w ? h->r_next : h->r_obs) + slot * h->Ec, h->Ec * sizeof(float), cudaMemcpyDeviceToHost));
+      for (int p = 0; p < HW; ++p) {
+        for (int c = 0; c < Ci; ++c) dst[(size_t)p * Cf + c] = row[(size_t)p * Ci + c];
+        dst[(size_t)p * Cf + Ci] = p == 0 ? row[(size_t)HW * Ci] : 0.f;
+      }
+    }
+  } else {
   if (obs) CK(cudaMemcpy(obs, h->r_obs + slot * E, E * sizeof(float), cudaMemcpyDeviceToHost));
   if (next_obs) CK(cudaMemcpy(next_obs, h->r_next + slot * E, E * sizeof(float), cudaMemcpyDeviceToHost));
+  }
   if (act) CK(cudaMemcpy(act, h->r_act + slot * A, A * sizeof(float), cudaMemcpyDeviceToHost));
   if (rew) CK(cudaMemcpy(rew, h->r_rew + slot, sizeof(float), cudaMemcpyDeviceToHost));
   if (done) CK(cudaMemcpy(done, h->r_done + slot, sizeof(float), cudaMemcpyDeviceToHost));
@@ -1417,17 +1492,33 @@ int b2g_set_norm_stats(b2g_sac* h, const double* obs_mean, const double* obs_var
   if (!h) return fail(B2G_EINVAL, "NULL handle");
   if (norm_obs && (!obs_mean || !obs_var)) return fail(B2G_EINVAL, "norm_obs needs obs_mean/obs_var");
   CK(cudaSetDevice(h->cfg.device));
-  CK(cudaStreamSynchronize(h->stream));
+  // Called once per environment step by the learn loop (VecNormalize statistics move with every observation): the values
+  // are staged in one of two pinned buffers and uploaded asynchronously IN STREAM ORDER -- no stream synchronisation, the
+  // next gradient step simply sees them.  A buffer is reused only after its previous upload has completed.
+  const int k = h->stats_k++ & 1;
+  CK(cudaEventSynchronize(h->ev_stats[k]));
+  double* st = h->hp_stats[k];
+  const int E = h->E, Ec = h->Ec;
   if (norm_obs) {
-    std::vector<double> istd(h->E);
-    for (int i = 0; i < h->E; ++i) istd[i] = 1.0 / sqrt(obs_var[i] + eps);
-    CK(cudaMemcpy(h->d_mean, obs_mean, h->E * sizeof(double), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(h->d_istd, istd.data(), h->E * sizeof(double), cudaMemcpyHostToDevice));
+    double* m = st; double* is = st + E; double* mc = st + 2 * E; double* isc = mc + Ec;
+    for (int i = 0; i < E; ++i) { m[i] = obs_mean[i]; is[i] = 1.0 / sqrt(obs_var[i] + eps); }
+    CK(cudaMemcpyAsync(h->d_mean, m, E * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_istd, is, E * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (h->compact) {
+      const int Ci = h->Cimg, Cf = Ci + 1, npx = h->Hi * h->Wi * Ci;
+      for (int e = 0; e < npx; ++e) { const int f = (e / Ci) * Cf + (e % Ci); mc[e] = m[f]; isc[e] = is[f]; }
+      mc[npx] = m[Ci]; isc[npx] = is[Ci];
+      for (int e = npx + 1; e < Ec; ++e) { mc[e] = 0.0; isc[e] = 1.0; }
+      CK(cudaMemcpyAsync(h->d_mean_c, mc, Ec * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      CK(cudaMemcpyAsync(h->d_istd_c, isc, Ec * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    }
   }
   h->ret_istd = 1.0 / sqrt(ret_var + eps);
   h->clip_obs = clip_obs; h->clip_rew = clip_rew; h->norm_obs = norm_obs; h->norm_rew = norm_reward;
-  const double nc[8] = {h->ret_istd, clip_obs, clip_rew, (double)norm_obs, (double)norm_reward, 0, 0, 0};
-  CK(cudaMemcpy(h->d_normc, nc, sizeof(nc), cudaMemcpyHostToDevice));
+  double* nc = st + 2 * E + 2 * Ec;
+  nc[0] = h->ret_istd; nc[1] = clip_obs; nc[2] = clip_rew; nc[3] = (double)norm_obs; nc[4] = (double)norm_reward; nc[5] = nc[6] = nc[7] = 0.0;
+  CK(cudaMemcpyAsync(h->d_normc, nc, 8 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaEventRecord(h->ev_stats[k], h->stream));
   return 0;
 }
 

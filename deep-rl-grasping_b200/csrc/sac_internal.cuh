@@ -62,7 +62,8 @@ struct V2State {
   uint16_t* K0n[2][2]{};         // [0] pi [513 -> 576 rows][64], [1] values packed [576 rows][192]
   float* z0v = nullptr;          // fc0 pre-activations of vf|q1|q2: [B][192]
   void* plane_jobs = nullptr; int n_plane_jobs = 0, plane_ctas = 0;
-  void* colsum_jobs = nullptr; int n_colsum_jobs = 0, colsum_ctas = 0;
+  void* colsum_part[2]{}; int n_colsum_part[2]{}, colsum_ctas_part[2]{};   // [0] cnn_fc1 biases (early), [1] conv biases
+  int sm_reserve = 0;            // SMs left to a collective that runs concurrently with the persistent GEMM grids
   std::vector<CUtensorMap> maps; // host copy
   CUtensorMap* d_maps = nullptr;
   std::vector<CgGroup> fwd, bwd_groups;
@@ -78,8 +79,9 @@ int v2_alloc(b2g_sac* h);    // plane tensors (before the v1 groups are built: t
 int v2_create(b2g_sac* h);   // tensor maps + problem groups
 int v2_planes(b2g_sac* h, cudaStream_t s);
 int v2_gather(b2g_sac* h, const GatherArgs& ga, cudaStream_t s);
+int v2_compact_rows(b2g_sac* h, const float* src_full, float* dst, long long first_row, long long wrap, int n, cudaStream_t s);   // full [n][E] -> compact rows (first_row + i) % wrap
 int v2_launch(b2g_sac* h, const CgGroup& g, cudaStream_t s);
-int v2_colsum(b2g_sac* h, cudaStream_t s);   // bias gradients from the gradient-map planes
+int v2_colsum(b2g_sac* h, cudaStream_t s, int part);   // bias gradients from the gradient-map planes
 }  // namespace b2g
 
 using namespace b2g;   // (internal header: only library translation units include it)
@@ -158,7 +160,7 @@ struct b2g_sac {
   bool fc0_split = true;                   // split-R heads_fc0 (needs z0 zeroed every step)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool overlap_ar = false;
-  int ar_sms = 16;
+  int ar_sms = 8;
   ColsumJob* d_colsum_early = nullptr;
   int n_colsum_early = 0, colsum_early_ctas = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -170,6 +172,16 @@ struct b2g_sac {
   long long* h_cnt = nullptr;    // pinned counters
 
   b2g::V2State v2;
+  // compact replay rows (engine v2, CNN policy): image planes + the ONE actuator value the policy reads (pixel [0,0] of the
+  // last plane) + 3 pad floats; the rest of that plane is never read by augmented_nature_cnn (custom_obs_policy.py:28-30)
+  bool compact = false;
+  int Ec = 0;                        // floats per compact row
+  float *cs_obs = nullptr, *cs_next = nullptr;     // compacted explicit batch [B][Ec]
+  float* add_stage = nullptr;        // full-layout staging of replay_add chunks [2][ADD_CHUNK][E]
+  double *d_mean_c = nullptr, *d_istd_c = nullptr; // statistics in the compact layout
+  double* hp_stats[2]{};             // pinned staging of set_norm_stats (asynchronous upload, no stream sync)
+  cudaEvent_t ev_stats[2]{};
+  int stats_k = 0;
   bool v2_skip = false;          // (policy inference: the v1 forward groups write the separate z0 blocks)
 
   float* p(const std::string& n) { return P + tensors[tindex.at(n)].off; }

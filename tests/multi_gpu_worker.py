@@ -48,8 +48,7 @@ def main():
     same = all(b == allp[0] for b in allp)
     q_err = rel_err(out["q1"], np.asarray(ref["q1"]).reshape(-1)[sl])
     print(f"rank {rank}: errs {errs} worst-grad {gerr:.2e} q1 {q_err:.2e} replicas_identical {same}", flush=True)
-    tol = 1e-4 if prec == 0 else 2e-4
-    ok = all(v <= tol for v in errs.values()) and gerr <= (1e-3 if prec == 0 else 5e-3) and same and q_err <= 1e-4
+    ok = all(v <= 1e-4 for v in errs.values()) and gerr <= 1e-3 and same and q_err <= 1e-4
     L.close()
     dist.barrier()
     dist.destroy_process_group()

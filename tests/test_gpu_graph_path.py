@@ -31,14 +31,15 @@ def _norm_batch(tr, idx, vn):
                 act=tr["act"][idx], rew=R.normalize_reward(tr["rew"][idx], float(vn["ret_var"])), done=tr["done"][idx])
 
 
-def _run_graph_steps(cfg, params, vn, tr, B, K, precision, seed=4321):
-    """K sampled steps (one b2g_sac_step call each) -> list of (metrics, last_batch) + final parameters."""
+def _run_graph_steps(cfg, params, vn, tr, B, K, precision, seed=4321, keep_params=False):
+    """K sampled steps (one b2g_sac_step call each) -> list of (metrics, last_batch[, parameters BEFORE the step]) + final parameters."""
     L = make_learner(cfg, vn, B, params, buffer_size=len(tr["rew"]), precision=precision, seed=seed)
     L.replay_add(tr["obs"], tr["act"], tr["rew"], tr["next_obs"], tr["done"])
     rows = []
     for _ in range(K):
+        pre = L.get_parameters() if keep_params else None
         m = L.step(1, lr=LR)
-        rows.append((m, L.last_batch()))
+        rows.append((m, L.last_batch(), pre) if keep_params else (m, L.last_batch()))
     p = L.get_parameters()
     L.close()
     return rows, p
@@ -46,7 +47,8 @@ def _run_graph_steps(cfg, params, vn, tr, B, K, precision, seed=4321):
 
 def _oracle_trajectory(cfg, params, vn, tr, rows, dtype):
     p, opt, out = dict(params), R.OptState.zeros(params), []
-    for m, lb in rows:
+    for row in rows:
+        m, lb = row[0], row[1]
         norm = _norm_batch(tr, lb["indices"].astype(np.int64), vn)
         ref, grads, p, opt = R.sac_step(p, opt, norm, lb["eps"], LR, cfg, dtype)
         p = {n: np.asarray(a, np.float32) for n, a in p.items()}
@@ -55,21 +57,25 @@ def _oracle_trajectory(cfg, params, vn, tr, rows, dtype):
 
 
 def test_graph_path_ten_steps_vs_oracle_bf16x3_b256():
-    """a10: 10 consecutive graph replays (bf16x3, depth, B=256, 4096 distinct replay slots) against the float64
-    oracle carrying ITS OWN parameters and Adam state through the same 10 batches.  Bar per step: 1e-4, or 3x the
-    distance of the fp32 oracle trajectory from the float64 one where fp32 arithmetic itself does not resolve 1e-4
-    (logp at saturated actions; the policy gradient norm late in the trajectory)."""
+    """a10: 10 consecutive graph replays (bf16x3 parity mode, depth, B=256, 4096 distinct replay slots).
+
+    (i) Every step's outputs -- per-sample Q/V/logp/pi, the five losses, both gradient norms -- against the float64 oracle
+    evaluated on the SAME batch (the device reports its slots and noise) from the parameters the device held BEFORE that
+    step: bar 1e-4, or 3x the fp32 oracle's own distance from float64 where fp32 arithmetic itself does not resolve 1e-4.
+    (ii) The parameters after the 10 updates against the float64 oracle running its OWN trajectory (parameters + Adam
+    state) through the same 10 batches."""
     cfg, params, vn = load_case("sac_depth")
     B, K, NS = 256, 10, 4096
     tr = synth.make_transitions(NS, vn["obs_mean"], vn["obs_var"], seed=9001)
-    rows, p_gpu = _run_graph_steps(cfg, params, vn, tr, B, K, precision=1)
-    for m, lb in rows:
+    rows, p_gpu = _run_graph_steps(cfg, params, vn, tr, B, K, precision=1, keep_params=True)
+    for m, lb, _ in rows:
         assert lb["indices"].min() >= 0 and lb["indices"].max() < NS
-    assert len({int(i) for _, lb in rows for i in lb["indices"]}) > 1500          # the batches really differ
-    ref64, p64 = _oracle_trajectory(cfg, params, vn, tr, rows, torch.float64)
-    ref32, _ = _oracle_trajectory(cfg, params, vn, tr, rows, torch.float32)
+    assert len({int(i) for _, lb, _ in rows for i in lb["indices"]}) > 1500          # the batches really differ
     worst = {}
-    for it, ((m, lb), r64, r32) in enumerate(zip(rows, ref64, ref32)):
+    for it, (m, lb, pre) in enumerate(rows):
+        norm = _norm_batch(tr, lb["indices"].astype(np.int64), vn)
+        r64, _, _, _ = R.sac_step(pre, R.OptState.zeros(pre), norm, lb["eps"], LR, cfg, torch.float64)
+        r32, _, _, _ = R.sac_step(pre, R.OptState.zeros(pre), norm, lb["eps"], LR, cfg, torch.float32)
         for k in VECTORS:
             e = rel_err(lb[k].reshape(-1), np.asarray(r64[k]).reshape(-1))
             bar = max(TOL, 3 * rel_err(np.asarray(r32[k]).reshape(-1), np.asarray(r64[k]).reshape(-1)))
@@ -82,6 +88,7 @@ def test_graph_path_ten_steps_vs_oracle_bf16x3_b256():
             assert e <= bar, (it, k, e, bar)
         assert m["n_updates"] == it + 1
     print("worst err/bar over 10 steps:", {k: f"{v:.2f}" for k, v in worst.items()})
+    _, p64 = _oracle_trajectory(cfg, params, vn, tr, rows, torch.float64)
     # parameters after 10 updates: every Adam step moves an entry by at most ~lr, and entries whose gradient is
     # numerically zero take a step of either sign (lr*g/(|g|+eps)), so the bar is a fraction of the 10-step budget:
     # <= 5 % of K*lr on 99 % of the entries of every tensor, and never more than 2*K*lr
