@@ -8,7 +8,11 @@ mkdir -p build
 objs=""
 for f in csrc/*.cu; do
   o=build/$(basename "${f%.cu}").o
-  if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ csrc/common.cuh -nt "$o" ] || [ ../include/b200grasp.h -nt "$o" ]; then
+  stale=0
+  for dep in "$f" csrc/*.cuh ../include/b200grasp.h; do          # every header is a dependency of every object
+    if [ ! -f "$o" ] || [ "$dep" -nt "$o" ]; then stale=1; fi
+  done
+  if [ $stale = 1 ]; then
     $NVCC $FLAGS -c "$f" -o "$o" &
   fi
   objs="$objs $o"

@@ -1,16 +1,20 @@
 // TMA-fed tcgen05 contraction engine (sm_100a).  See cg.cuh for the problem description.
 //
 // Persistent, warp-specialised kernel, one CTA per SM, grid = min(#tiles, #SMs):
-//   warp 0      : ONE elected thread issues cp.async.bulk.tensor boxes for every K-chunk of the CTA's tiles into a ring of
-//                 shared-memory stages (mbarrier expect_tx / complete_tx); nothing else touches the load path;
-//   warp 1      : owns the TMEM allocation; one thread issues tcgen05.mma.cta_group::1.kind::f16 (BF16 planes, fp32
-//                 accumulation in TMEM, two accumulators so the epilogue of tile i overlaps the mainloop of tile i+1).
-//                 Precision modes per problem: 1 product (hi*hi), 3 products (2-plane split: +hi*lo, lo*hi) or 6 products
-//                 (3-plane split hi/mid/lo: everything down to 2^-24) -- see profiles/precision_r2.md for why the
-//                 forward pass needs the 6-product mode;
-//   warps 2..9  : epilogue.  tcgen05.ld one accumulator row per thread, apply bias/ReLU or the ReLU mask, split into
+//   warps 0..1  : TMA producers (whole warps, converged; one elected lane issues).  The cp.async.bulk.tensor boxes of a K-chunk
+//                 (operands x planes) are dealt round-robin to the two warps; warp 0 posts the chunk's expect_tx.  More issuing
+//                 warps do not help: with 2 or 4 the 72 KB of a 3-plane chunk take ~1400 cycles to land either way (51 B/clk
+//                 per SM, ~14 TB/s chip-wide out of L2 -- profiles/cg_trace_r2.txt), which is the fabric, not the issue rate;
+//   warp 2      : owns the TMEM allocation; converged warp, one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (BF16
+//                 planes, fp32 accumulation in TMEM, two accumulator buffers so the epilogue of tile i overlaps the mainloop
+//                 of tile i+1).  Precision modes per problem: 1 product (hi*hi), 3 products (2-plane split) or 6 products
+//                 (3-plane split hi/mid/lo: everything down to 2^-24), issued as 1..3 WIDE MMAs per k-step (see the issue
+//                 loop) -- profiles/precision_r2.md explains why the forward pass needs the 6-product mode;
+//   warps 3..10 : epilogue.  tcgen05.ld one accumulator row per thread, apply bias/ReLU or the ReLU mask, split into
 //                 BF16 planes, transpose through a 1 KiB warp-private staging tile and write coalesced rows.
 #include <cuda_bf16.h>
+
+#include <cstdio>
 
 #include "cg.cuh"
 #include "common.cuh"
@@ -18,8 +22,10 @@
 namespace b2g {
 namespace {
 
-constexpr int NTHREADS = 32 * 10;
-constexpr int EPI_WARP0 = 2, NEPI_WARPS = 8;
+// warps 0..1: TMA producers, warp 2: MMA issuer (owns TMEM), warps 3..10: epilogue
+constexpr int NPROD_WARPS = 2, MMA_WARP = NPROD_WARPS;
+constexpr int EPI_WARP0 = NPROD_WARPS + 1, NEPI_WARPS = 8;
+constexpr int NTHREADS = 32 * (EPI_WARP0 + NEPI_WARPS);
 constexpr int STG_PER_WARP = 1024;
 constexpr int TMEM_COLS = 512;          // two accumulators of up to 256 fp32 columns
 
@@ -42,6 +48,21 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "CG_DONE:\n\t"
       "}" ::"r"(bar), "r"(parity)
       : "memory");
+}
+// one lane of a CONVERGED warp.  The producer and MMA roles run their loops with all 32 lanes so that every address,
+// descriptor and coordinate is warp-uniform and lives in the uniform register file UTMALDG / UTCHMMA read; a role entered
+// by one lane only (if (lane == 0) {...}) made the compiler wrap every such instruction in an R2UR + ELECT/BRA.U.ANY
+// value-serialisation loop -- ~75 cycles per MMA issued (profiles/cg_trace_r2.txt).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -141,19 +162,20 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {    // lo -
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 cg_kernel(const __grid_constant__ CgPack pk, int nprob, int total_tiles, const CUtensorMap* __restrict__ maps, int slot_bytes, int nstages,
-          int dbg) {
+          int dbg, long long* __restrict__ trace) {
   const CgProblem* __restrict__ probs = pk.p;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[CG_MAX_STAGES], bar_empty[CG_MAX_STAGES], bar_acc_full[2], bar_acc_empty[2];
   __shared__ uint32_t tmem_slot;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);          // warp-uniform for the compiler, not just in fact
   const bool dbg_noload = dbg & 1, dbg_nomma = dbg & 2, dbg_nostore = dbg & 4;
   if (tid == 0) {
     for (int s = 0; s < nstages; ++s) { mbar_init(smem_u32(&bar_full[s]), 1); mbar_init(smem_u32(&bar_empty[s]), 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&bar_acc_full[b]), 1); mbar_init(smem_u32(&bar_acc_empty[b]), NEPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {
+  if (warp == MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
@@ -166,17 +188,17 @@ cg_kernel(const __grid_constant__ CgPack pk, int nprob, int total_tiles, const C
   pdl_trigger();
   pdl_wait();
 
-  if (warp == 0) {
-    // ============================================================================================ TMA producer
-    if (lane == 0) {
+  if (warp < NPROD_WARPS) {
+    // ============================================================================================ TMA producers
+    {
       uint32_t gc = 0, s = 0, ph = 0;                    // ring slot and its phase, advanced without divisions
       Walker w;
-      int n2 = 1, nloads = 0, planes = 0, plane_bytes = 0, tx = 0;
+      int n2 = 1, nloads = 0, planes = 0, tx = 0;
       const int* tab = nullptr;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         if (w.advance(probs, nprob, tile)) {
           const CgProblem& P = probs[w.p];
-          n2 = P.n2; nloads = P.nloads; planes = P.planes; plane_bytes = P.plane_bytes; tx = P.tx_bytes; tab = P.tm_tab;
+          n2 = P.n2; nloads = P.nloads; planes = P.planes; tx = P.tx_bytes; tab = P.tm_tab;
         }
         const Tile ti = w.tile(tile);
         const CgProblem& P = probs[ti.p];
@@ -193,12 +215,17 @@ cg_kernel(const __grid_constant__ CgPack pk, int nprob, int total_tiles, const C
         }
         int c1 = n2 > 1 ? ti.c_begin / n2 : 0, c2 = ti.c_begin - c1 * n2;
         for (int c = ti.c_begin; c < ti.c_end; ++c, ++gc) {
+          const bool tr = trace && blockIdx.x == 0 && warp == 0 && gc < 64 && lane == 0;
+          if (tr) trace[gc * 8 + 0] = clock64();
           if (gc >= (uint32_t)nstages) mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1);
+          if (tr) trace[gc * 8 + 1] = clock64();
           const uint32_t full = smem_u32(&bar_full[s]);
-          if (dbg_noload) mbar_arrive(full);
+          const bool leader = elect_one();
+          if (dbg_noload) { if (warp == 0 && leader) mbar_arrive(full); }
           else {
-            mbar_expect_tx(full, (uint32_t)tx);
+            if (warp == 0 && leader) mbar_expect_tx(full, (uint32_t)tx);        // the one arrival of the phase; boxes may land before it
             const uint32_t sbase = ring + s * (uint32_t)slot_bytes;
+            int j = 0;                                                 // box index inside the chunk, dealt round-robin to the producer warps
 #pragma unroll
             for (int l = 0; l < CG_MAX_LOADS; ++l) {
               if (l < nloads) {
@@ -206,30 +233,39 @@ cg_kernel(const __grid_constant__ CgPack pk, int nprob, int total_tiles, const C
                 int crd[5];
 #pragma unroll
                 for (int d = 0; d < 5; ++d) crd[d] = base[l][d] + c1 * L.d_c1[d] + c2 * L.d_c2[d];
-                for (int pl = 0; pl < planes; ++pl)
-                  tma_load(sbase + (uint32_t)(pl * plane_bytes + L.smem_off), maps + L.map + pl, full, L.rank, crd);
+                if (L.plane_box) {                               // all planes in one box (plane = outermost coordinate, 0)
+                  if ((j & (NPROD_WARPS - 1)) == warp && leader) tma_load(sbase + (uint32_t)L.smem_off, maps + L.map, full, L.rank, crd);
+                  ++j;
+                } else {
+                  for (int pl = 0; pl < planes; ++pl, ++j)
+                    if ((j & (NPROD_WARPS - 1)) == warp && leader)
+                      tma_load(sbase + (uint32_t)(pl * L.plane_stride + L.smem_off), maps + L.map + pl, full, L.rank, crd);
+                }
               }
             }
           }
+          if (tr) trace[gc * 8 + 2] = clock64();
           if (++c2 == n2) { c2 = 0; ++c1; }
           if (++s == (uint32_t)nstages) { s = 0; ph ^= 1; }
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == MMA_WARP) {
     // ============================================================================================ MMA issuer
-    if (lane == 0) {
-      uint32_t it = 0, s = 0, ph = 0;
+    {
+      uint32_t it = 0, s = 0, ph = 0, gcm = 0;
       Walker w;
       bool mnm = false;
-      uint32_t idesc = 0, a_off = 0, b_off = 0, a_ks = 0, b_ks = 0, a_lbo = 0, b_lbo = 0;
-      int ksteps = 0, nprod = 1, plane_bytes = 0;
+      uint32_t idesc[3] = {0, 0, 0}, a_off = 0, b_off = 0, a_ks = 0, b_ks = 0, a_lbo = 0, b_lbo = 0, a_ps = 0, ncol = 0;
+      int ksteps = 0, nprod = 1;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         if (w.advance(probs, nprob, tile)) {
           const CgProblem& P = probs[w.p];
           mnm = P.mn_major != 0;
-          idesc = make_idesc(128, P.umma_n, mnm);
-          ksteps = P.ksteps; nprod = P.nprod; plane_bytes = P.plane_bytes;
+          ncol = (uint32_t)P.umma_n;
+#pragma unroll
+          for (int j = 0; j < 3; ++j) idesc[j] = make_idesc(128, P.umma_n * (j + 1), mnm);      // N = n, 2n, 3n
+          ksteps = P.ksteps; nprod = P.nprod; a_ps = (uint32_t)P.a_pstride;
           a_off = P.a_off; b_off = P.b_off; a_ks = P.a_kstep; b_ks = P.b_kstep; a_lbo = P.a_lbo; b_lbo = P.b_lbo;
         }
         const Tile ti = w.tile(tile);
@@ -239,35 +275,50 @@ cg_kernel(const __grid_constant__ CgPack pk, int nprob, int total_tiles, const C
         tc_fence_after();
         const uint32_t acc = tmem + buf * 256u;
         for (int c = ti.c_begin; c < ti.c_end; ++c) {
+          const bool tr = trace && blockIdx.x == 0 && gcm < 64 && lane == 0;
+          if (tr) trace[gcm * 8 + 3] = clock64();
           mbar_wait(smem_u32(&bar_full[s]), ph);
+          if (tr) trace[gcm * 8 + 4] = clock64();
           tc_fence_after();
           const uint32_t sbase = ring + s * (uint32_t)slot_bytes;
+          const bool leader = elect_one();
           if (!dbg_nomma) {
             for (int k = 0; k < ksteps; ++k) {
-              uint64_t da[3], db[3];
+// `planes` wide MMAs per k-step: A_p x [B_0 | .. | B_(planes-1-p)] -> accumulator columns [p*n, planes*n).
+              // Column group g therefore collects the products of order 2^(-8g): g0 = hi*hi, g1 = hi*mid + mid*hi,
+              // g2 = hi*lo + mid*mid + lo*hi.  The tensor core truncates the fp32 accumulator at every MMA (measured:
+              // tools/tc_accum_probe.py, ~2^-25 relative per accumulation), so keeping each order in its own columns keeps that
+              // truncation 2^-8g smaller on the correction terms; the epilogue adds the groups small-to-large in fp32.
+              // One wide MMA reads the A plane from shared memory once for up to three products -- at N = 64 the SS-mode
+              // MMA is shared-memory bound (55 cycles where the tensor floor is 32: profiles/cg_trace_r2.txt).
+              const uint32_t pb = sbase + b_off + (uint32_t)k * b_ks;
+              const uint64_t db = mnm ? desc_mn(pb, b_lbo) : desc_k(pb);
+              uint64_t da[3];
 #pragma unroll
               for (int pl = 0; pl < 3; ++pl) {
-                const uint32_t pa = sbase + (uint32_t)(pl * plane_bytes) + a_off + (uint32_t)k * a_ks;
-                const uint32_t pb = sbase + (uint32_t)(pl * plane_bytes) + b_off + (uint32_t)k * b_ks;
+                const uint32_t pa = sbase + (uint32_t)pl * a_ps + a_off + (uint32_t)k * a_ks;
                 da[pl] = mnm ? desc_mn(pa, a_lbo) : desc_k(pa);
-                db[pl] = mnm ? desc_mn(pb, b_lbo) : desc_k(pb);
               }
               const uint32_t first = (c == ti.c_begin && k == 0) ? 0u : 1u;
-              // Two accumulators per tile.  The tensor core truncates the fp32 accumulator at every MMA (measured:
-              // tools/tc_accum_probe.py, ~2^-25 relative bias per accumulation), so the CORRECTION products (hi*lo, lo*hi and
-              // the mid terms: 2^-8 .. 2^-16 of the leading product) go to their own accumulator, where that truncation is
-              // 2^-8 smaller, and the leading accumulator only sees one hi*hi per k-step (6x fewer truncations in the
-              // 6-product mode).  The epilogue adds the two in fp32 (round to nearest).
-              const uint32_t accc = acc + 128u;
-              if (nprod >= 6) { umma(accc, da[2], db[0], idesc, first); umma(accc, da[0], db[2], idesc, 1u); umma(accc, da[1], db[1], idesc, 1u); }
-              if (nprod >= 3) { umma(accc, da[1], db[0], idesc, nprod >= 6 ? 1u : first); umma(accc, da[0], db[1], idesc, 1u); }
-              umma(acc, da[0], db[0], idesc, first);
+              if (leader) {
+                if (nprod >= 6) {
+                  umma(acc, da[0], db, idesc[2], first); umma(acc + ncol, da[1], db, idesc[1], 1u); umma(acc + 2u * ncol, da[2], db, idesc[0], 1u);
+                } else if (nprod >= 3) {
+                  umma(acc, da[0], db, idesc[1], first); umma(acc + ncol, da[1], db, idesc[0], 1u);
+                } else {
+                  umma(acc, da[0], db, idesc[0], first);
+                }
+              }
             }
           }
-          umma_commit(smem_u32(&bar_empty[s]));
+          if (leader) umma_commit(smem_u32(&bar_empty[s]));
+          __syncwarp();
+          if (tr) trace[gcm * 8 + 5] = clock64();
+          ++gcm;
           if (++s == (uint32_t)nstages) { s = 0; ph ^= 1; }
         }
-        umma_commit(smem_u32(&bar_acc_full[buf]));
+        if (elect_one()) umma_commit(smem_u32(&bar_acc_full[buf]));
+        __syncwarp();
         ++it;
       }
     }
@@ -284,7 +335,7 @@ cg_kernel(const __grid_constant__ CgPack pk, int nprob, int total_tiles, const C
     int epi = 0, rows_tile = 0, lim_rows = 0, umma_n = 0, out_planes = 0, grp_stride = 32, n_valid = 0;
     long long roff = 0, rmoff = 0, o_tm = 0, m_tm = 0;
     int ri0 = 0, ri1 = 0, grp_tab = 0;
-    bool two_acc = false;
+    int ngrp_acc = 1;
     const float* __restrict__ bias = nullptr;
     const uint16_t* __restrict__ mask = nullptr;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -296,7 +347,7 @@ cg_kernel(const __grid_constant__ CgPack pk, int nprob, int total_tiles, const C
         const int i0 = r % d0, i12 = r / d0, i1 = i12 % d1, i2 = i12 / d1;
         roff = Q.o_base + (long long)i0 * Q.o0 + (long long)i1 * Q.o1 + (long long)i2 * Q.o2;
         rmoff = Q.m_base + (long long)i0 * Q.m0 + (long long)i1 * Q.m1 + (long long)i2 * Q.m2;
-        ri0 = i0; ri1 = i1; grp_tab = Q.grp_tab; two_acc = Q.nprod > 1;
+        ri0 = i0; ri1 = i1; grp_tab = Q.grp_tab; ngrp_acc = Q.nprod >= 6 ? 3 : (Q.nprod >= 3 ? 2 : 1);
       }
       const Tile ti = w.tile(tile);
       if (ti.c_end <= ti.c_begin) continue;
@@ -305,7 +356,10 @@ cg_kernel(const __grid_constant__ CgPack pk, int nprob, int total_tiles, const C
       const bool valid0 = r < rows_tile && ti.tm * rows_tile + r < lim_rows;
       const long long off0 = roff + (long long)ti.tm * o_tm, moff0 = rmoff + (long long)ti.tm * m_tm;
       const int n0 = ti.tn * umma_n, ngroups = umma_n >> 5;
+      const bool tre = trace && blockIdx.x == 0 && ew == 0 && lane == 0 && it < 16;
+      if (tre) trace[512 + it * 4 + 0] = clock64();
       mbar_wait(smem_u32(&bar_acc_full[buf]), (it >> 1) & 1);
+      if (tre) trace[512 + it * 4 + 1] = clock64();
       tc_fence_after();
       for (int g = half; g < ngroups; g += 2) {
         const int ng = n0 + 32 * g;                      // first problem column of the group
@@ -320,7 +374,7 @@ cg_kernel(const __grid_constant__ CgPack pk, int nprob, int total_tiles, const C
               "=r"(v[31])
             : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (two_acc) {
+        if (ngrp_acc > 1) {                                // correction column groups, smallest order first
           uint32_t u[32];
           asm volatile(
               "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -329,8 +383,22 @@ cg_kernel(const __grid_constant__ CgPack pk, int nprob, int total_tiles, const C
                 "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]), "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]),
                 "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]),
                 "=r"(u[31])
-              : "r"(taddr + 128u));
+              : "r"(taddr + (uint32_t)umma_n));
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (ngrp_acc > 2) {
+            uint32_t t[32];
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]), "=r"(t[8]), "=r"(t[9]), "=r"(t[10]),
+                  "=r"(t[11]), "=r"(t[12]), "=r"(t[13]), "=r"(t[14]), "=r"(t[15]), "=r"(t[16]), "=r"(t[17]), "=r"(t[18]), "=r"(t[19]), "=r"(t[20]),
+                  "=r"(t[21]), "=r"(t[22]), "=r"(t[23]), "=r"(t[24]), "=r"(t[25]), "=r"(t[26]), "=r"(t[27]), "=r"(t[28]), "=r"(t[29]), "=r"(t[30]),
+                  "=r"(t[31])
+                : "r"(taddr + 2u * (uint32_t)umma_n));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 32; ++j) u[j] = __float_as_uint(__uint_as_float(u[j]) + __uint_as_float(t[j]));
+          }
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
         }
@@ -464,12 +532,13 @@ cg_kernel(const __grid_constant__ CgPack pk, int nprob, int total_tiles, const C
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty[buf]));
+      if (tre) trace[512 + it * 4 + 2] = clock64();
       ++it;
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == MMA_WARP) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS));
   }
@@ -507,7 +576,9 @@ int cg_finalize(CgGroup& g, int smem_budget) {
     CgProblem& P = g.host[i];
     P.tile_start = start;
     start += P.tiles_m * P.tiles_n * P.splits;
-    slot = slot > P.planes * P.plane_bytes ? slot : P.planes * P.plane_bytes;
+    for (int l = 0; l < P.nloads; ++l) P.ld[l].plane_stride = P.ld[l].smem_off >= P.b_off ? P.b_pstride : P.a_pstride;
+    const int need = P.planes * (P.a_pstride + P.b_pstride);
+    slot = slot > need ? slot : need;
   }
   g.total_tiles = start;
   g.slot_bytes = (slot + 1023) / 1024 * 1024;
@@ -516,6 +587,8 @@ int cg_finalize(CgGroup& g, int smem_budget) {
   if (g.nstages > CG_MAX_STAGES) g.nstages = CG_MAX_STAGES;
   return g.nstages >= 2 ? 0 : -1;
 }
+
+long long* g_cg_trace = nullptr;      // bring-up: clock64 stamps of CTA 0 (set by tools through b2g_debug_cg_trace)
 
 cudaError_t cg_launch(const CgGroup& g, const CUtensorMap* dev_maps, int num_sms, cudaStream_t s, bool pdl, int debug_flags) {
   if (g.total_tiles <= 0 || (debug_flags & 8)) return cudaSuccess;     // bit 3: skip the launch (timing ablation)
@@ -530,7 +603,9 @@ cudaError_t cg_launch(const CgGroup& g, const CUtensorMap* dev_maps, int num_sms
   CgPack pk;              // (host staging; the launch copies it into the parameter buffer)
   static_assert(sizeof(CgPack) < 16 * 1024, "problem list must fit the kernel parameter space");
   for (int i = 0; i < g.n; ++i) pk.p[i] = g.host[i];
-  return launch_pdl(cg_kernel, dim3(grid), dim3(NTHREADS), (size_t)smem, s, pdl, pk, g.n, g.total_tiles, dev_maps, g.slot_bytes, g.nstages, debug_flags);
+  cudaError_t e = launch_pdl(cg_kernel, dim3(grid), dim3(NTHREADS), (size_t)smem, s, pdl, pk, g.n, g.total_tiles, dev_maps, g.slot_bytes, g.nstages, debug_flags, g_cg_trace);
+  if (e != cudaSuccess) fprintf(stderr, "cg_launch %s: %s (grid %d, %d threads, smem %d = %d stages x %d)\n", g.name, cudaGetErrorString(e), grid, NTHREADS, smem, g.nstages, g.slot_bytes);
+  return e;
 }
 
 }  // namespace b2g

@@ -27,7 +27,10 @@ enum CgEpiKind : int {
 struct CgLoad {
   int map;            // index of the plane-0 tensor map in the map table; plane p uses map + p
   int rank;           // tensor-map rank (2..5)
-  int smem_off;       // byte offset of the box inside one plane block of a stage
+  int smem_off;       // byte offset of the plane-0 box inside a stage (A boxes below b_off, B boxes from b_off on)
+  int plane_stride;   // bytes between the plane copies of the box inside the stage (filled by cg_finalize: a_pstride | b_pstride)
+  int plane_box;      // 1: the planes are the OUTERMOST box dimension of one (rank)-D map -> one instruction per chunk;
+                      // 0: one instruction per plane with map + p (boxes smaller than the plane stride)
   int c0[5];          // box start coordinates: c0 + tm*d_tm + tn*d_tn + c1*d_c1 + c2*d_c2 (+ tm_tab)
   int d_tm[5], d_tn[5], d_c1[5], d_c2[5];
 };
@@ -38,18 +41,21 @@ struct CgProblem {
   int chunks, n2;
   // ---- operand fetch
   int nloads, planes;
-  int plane_bytes;            // bytes of one plane block (A region + B region) inside a stage
+  int a_pstride, b_pstride;   // stage layout: [A plane 0 | A plane 1 | ..][B plane 0 | B plane 1 | ..]; bytes of one A / B plane.
+                              // The B planes are CONTIGUOUS so that one UMMA descriptor spans [B0|B1|B2] (see nprod)
   int tx_bytes;               // bytes all boxes of one stage deliver (planes x sum of box bytes)
   CgLoad ld[CG_MAX_LOADS];
   const int* tm_tab;          // optional [tiles_m][CG_MAX_LOADS][2]: extra offsets of coordinates 1 and 2 per (tm, load)
   // ---- MMA
   int mn_major;               // 0: K-major A and B (rows = M|N, 128 B of K); 1: MN-major (rows = K, 128 B of M|N)
   int ksteps;                 // UMMA K = 16 steps per chunk
-  int a_off, b_off;           // region offsets inside a plane block
+  int a_off, b_off;           // region offsets inside a stage (b_off = planes * a_pstride)
   int a_kstep, b_kstep;       // descriptor start-address advance per k-step (bytes)
   int a_lbo, b_lbo;           // MN-major: byte stride between 64-element atoms along M|N
   int umma_n;                 // tile width (multiple of 16, <= 256)
-  int nprod;                  // products per k-step: 1 (hi*hi), 3 (+hi*lo, lo*hi), 6 (+mid terms of the 3-plane split)
+  int nprod;                  // products per k-step: 1 (hi*hi), 3 (+hi*lo, lo*hi), 6 (+mid terms of the 3-plane split), issued as
+                              // `planes` wide MMAs: A_p x [B_0 | .. | B_(planes-1-p)] into accumulator columns [p*n, planes*n), so
+                              // column group g collects the products of order 2^(-8g) (planes * umma_n <= 256)
   // ---- epilogue
   int epi;
   int rows_tile;              // real rows of a full tile (<= 128)

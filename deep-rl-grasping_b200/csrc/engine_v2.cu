@@ -13,6 +13,8 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "sac_internal.cuh"
@@ -38,7 +40,7 @@ __device__ __forceinline__ void split3(float y, uint16_t& p0, uint16_t& p1, uint
 }
 
 // one CTA per (sample, obs | next_obs): normalise into shared-memory planes, then emit the patch matrix rows
-__global__ void __launch_bounds__(256) gather2_kernel(Gather2Args a) {
+__global__ void __launch_bounds__(512) gather2_kernel(Gather2Args a) {
   extern __shared__ uint16_t sm_planes[];            // [3][H*W*Ci]
   const GatherArgs& g = a.g;
   const int b = blockIdx.x, which = blockIdx.y, tid = threadIdx.x;
@@ -154,36 +156,60 @@ struct Plane2Job {
   int tile_start;
 };
 
+// 64 (r) x 32 (n) source tile per CTA.  Loads are float4 along n; the transposed copy is written as 16-byte runs of 8
+// consecutive r values per plane (the 2-byte scattered stores of the first version made this the longest leaf kernel).
 __global__ void __launch_bounds__(256) planes2_kernel(const Plane2Job* __restrict__ jobs, int njobs) {
-  __shared__ float tile[32][33];
+  __shared__ float tile[64][33];
   int j = 0;
   while (j + 1 < njobs && (int)blockIdx.x >= jobs[j + 1].tile_start) ++j;
   const Plane2Job job = jobs[j];
   const int t = blockIdx.x - job.tile_start;
   const int tiles_n = (job.N + 31) / 32;
-  const int r0 = (t / tiles_n) * 32, n0 = (t % tiles_n) * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  for (int i = ty; i < 32; i += 8) {
-    const int r = r0 + i, n = n0 + tx;
-    float v = 0.f;
-    if (r < job.R && n < job.N) {
-      v = job.src[(size_t)r * job.N + n];
-      if (!job.transpose) {
-        uint16_t p[3];
-        split3(v, p[0], p[1], p[2]);
-        for (int k = 0; k < job.np; ++k) job.dst[k][(size_t)r * job.ld + n + job.off0] = p[k];
+  const int r0 = (t / tiles_n) * 64, n0 = (t % tiles_n) * 32;
+  const int tid = threadIdx.x;
+  // ---- load 64 x 32 (8 float4 per row, 2 passes of 32 rows)
+  const bool vec_ok = (job.N & 3) == 0;
+  for (int i = tid; i < 64 * 8; i += 256) {
+    const int rr = i >> 3, c4 = i & 7, r = r0 + rr, n = n0 + 4 * c4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < job.R) {
+      const float* sp = job.src + (size_t)r * job.N + n;
+      if (vec_ok && n + 3 < job.N) v = *reinterpret_cast<const float4*>(sp);
+      else { if (n < job.N) v.x = sp[0]; if (n + 1 < job.N) v.y = sp[1]; if (n + 2 < job.N) v.z = sp[2]; if (n + 3 < job.N) v.w = sp[3]; }
+    }
+    tile[rr][4 * c4] = v.x; tile[rr][4 * c4 + 1] = v.y; tile[rr][4 * c4 + 2] = v.z; tile[rr][4 * c4 + 3] = v.w;
+    if (!job.transpose && r < job.R) {      // natural layout: dst[r * ld + off0 + n], 8-byte runs of 4
+      const float x[4] = {v.x, v.y, v.z, v.w};
+      uint16_t p[3][4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) split3(x[u], p[0][u], p[1][u], p[2][u]);
+      for (int k = 0; k < job.np; ++k) {
+        uint16_t* d = job.dst[k] + (size_t)r * job.ld + job.off0 + n;
+        if (n + 3 < job.N && (((size_t)r * job.ld + job.off0 + n) & 3) == 0)
+          *reinterpret_cast<uint2*>(d) = make_uint2((uint32_t)p[k][0] | ((uint32_t)p[k][1] << 16), (uint32_t)p[k][2] | ((uint32_t)p[k][3] << 16));
+        else
+          for (int u = 0; u < 4; ++u) if (n + u < job.N) d[u] = p[k][u];
       }
     }
-    tile[i][tx] = v;
   }
   if (!job.transpose) return;
   __syncthreads();
-  for (int i = ty; i < 32; i += 8) {
-    const int n = n0 + i, r = r0 + tx;
-    if (r < job.R && n < job.N) {
-      uint16_t p[3];
-      split3(tile[tx][i], p[0], p[1], p[2]);
-      for (int k = 0; k < job.np; ++k) job.dst[k][(size_t)(n + job.off0) * job.ld + r] = p[k];
+  // ---- transposed copy: dst[(n + off0) * ld + r]; thread = (n, group of 8 r)
+  {
+    const int nn = tid >> 3, g8 = tid & 7, n = n0 + nn, rb = r0 + 8 * g8;
+    if (n < job.N && rb < job.R) {
+      uint16_t p[3][8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) split3(tile[8 * g8 + u][nn], p[0][u], p[1][u], p[2][u]);
+      const size_t o = (size_t)(n + job.off0) * job.ld + rb;
+      for (int k = 0; k < job.np; ++k) {
+        uint16_t* d = job.dst[k] + o;
+        if (rb + 7 < job.R && (o & 7) == 0)
+          *reinterpret_cast<uint4*>(d) = make_uint4((uint32_t)p[k][0] | ((uint32_t)p[k][1] << 16), (uint32_t)p[k][2] | ((uint32_t)p[k][3] << 16),
+                                                    (uint32_t)p[k][4] | ((uint32_t)p[k][5] << 16), (uint32_t)p[k][6] | ((uint32_t)p[k][7] << 16));
+        else
+          for (int u = 0; u < 8; ++u) if (rb + u < job.R) d[u] = p[k][u];
+      }
     }
   }
 }
@@ -270,8 +296,8 @@ CgProblem kmajor(int planes, int n_tile, int chunks, int n2, int a_box_rows) {
   P.tiles_m = P.tiles_n = P.splits = 1;
   P.chunks = chunks; P.n2 = n2;
   P.planes = planes;
-  P.a_off = 0; P.b_off = 128 * 128;
-  P.plane_bytes = 128 * 128 + n_tile * 128;
+  P.a_off = 0; P.a_pstride = 128 * 128;
+  P.b_off = planes * P.a_pstride; P.b_pstride = n_tile * 128;
   P.tx_bytes = planes * (a_box_rows * 128 + n_tile * 128);
   P.mn_major = 0; P.ksteps = 4; P.a_kstep = P.b_kstep = 32;
   P.umma_n = n_tile;
@@ -290,8 +316,8 @@ CgProblem mnmajor(int planes, int kr, int a_atoms, int b_atoms, int chunks) {
   P.chunks = chunks; P.n2 = chunks > 0 ? chunks : 1;
   P.planes = planes;
   const int atom = kr * 128;
-  P.a_off = 0; P.b_off = 2 * atom;                 // the A region always has room for two atoms (M = 128)
-  P.plane_bytes = 2 * atom + b_atoms * atom;
+  P.a_off = 0; P.a_pstride = 2 * atom;             // an A plane always has room for two atoms (M = 128)
+  P.b_off = planes * P.a_pstride; P.b_pstride = b_atoms * atom;
   P.tx_bytes = planes * (a_atoms + b_atoms) * atom;
   P.mn_major = 1; P.ksteps = kr / 16; P.a_kstep = P.b_kstep = 2048;
   P.a_lbo = atom; P.b_lbo = atom;
@@ -309,7 +335,7 @@ int push_group(b2g_sac* h, std::vector<CgGroup>& list, CgGroup& g, const char* n
   if (cg_finalize(g, cg_smem_limit()) != 0) return b2g_fail(B2G_EINVAL, std::string("engine v2: stage ring of group ") + name + " does not fit shared memory");
   for (int i = 0; i < g.n; ++i) {
     const CgProblem& P = g.host[i];
-    if (P.nprod > 1 && P.umma_n > 128) return b2g_fail(B2G_EINVAL, std::string("engine v2: split-precision tiles are at most 128 wide (group ") + name + ")");
+    if (P.planes * P.umma_n > 256) return b2g_fail(B2G_EINVAL, std::string("engine v2: planes x tile width exceeds one accumulator buffer (group ") + name + ")");
     g.flops += 2.0 * P.tiles_m * 128.0 * P.tiles_n * P.umma_n * P.chunks * 64.0;      // issued (tile-padded) work
   }
   list.push_back(g);
@@ -378,7 +404,7 @@ int v2_create(b2g_sac* h) {
     Plane2Job j{};
     j.src = src; j.R = R; j.N = N; j.np = np; j.transpose = transpose; j.ld = ld; j.off0 = off0; j.tile_start = start;
     for (int k = 0; k < np; ++k) j.dst[k] = dst[k];
-    start += ((R + 31) / 32) * ((N + 31) / 32);
+    start += ((R + 63) / 64) * ((N + 31) / 32);
     jobs.push_back(j);
   };
   add_job(h->p("model/pi/cnn1/w"), K1, 32, v.W1T[0], 3, 1, K1, 0);
@@ -770,7 +796,7 @@ int v2_gather(b2g_sac* h, const GatherArgs& ga, cudaStream_t s) {
     B2G_CK(cudaFuncSetAttribute(gather2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
-  gather2_kernel<<<dim3(ga.B, ga.next_obs ? 2 : 1), 256, smem, s>>>(a);
+  gather2_kernel<<<dim3(ga.B, ga.next_obs ? 2 : 1), 512, smem, s>>>(a);
   return 0;
 }
 
@@ -781,7 +807,35 @@ int v2_colsum(b2g_sac* h, cudaStream_t s, int part) {
   return 0;
 }
 
+extern long long* g_cg_trace;
+static long long* s_trace_buf = nullptr;
+
 int v2_launch(b2g_sac* h, const CgGroup& g, cudaStream_t s) {
+  const char* tn = getenv("B2G_CG_TRACE");
+  cudaStreamCaptureStatus cs0 = cudaStreamCaptureStatusNone;
+  if (tn) cudaStreamIsCapturing(s, &cs0);
+  if (tn && cs0 == cudaStreamCaptureStatusNone && std::string(tn) == g.name) {        // bring-up: per-chunk clock64 stamps of CTA 0 -> stderr (serialises the launch)
+    if (!s_trace_buf) cudaMalloc(&s_trace_buf, 640 * sizeof(long long));
+    cudaMemsetAsync(s_trace_buf, 0, 640 * sizeof(long long), s);
+    g_cg_trace = s_trace_buf;
+    cudaError_t e = cg_launch(g, h->v2.d_maps, h->num_sms - h->v2.sm_reserve, s, false, h->v2.dbg);
+    g_cg_trace = nullptr;
+    if (e != cudaSuccess) return b2g_fail(B2G_ECUDA, cudaGetErrorString(e));
+    static int shots = 0;
+    if (shots++ == 3) {
+      long long t[640];
+      cudaStreamSynchronize(s);
+      cudaMemcpy(t, s_trace_buf, sizeof(t), cudaMemcpyDeviceToHost);
+      const long long t0 = t[0];
+      fprintf(stderr, "cg trace %s (cycles; per chunk: prod wait_start wait_done issued | mma wait_start full_seen committed)\n", g.name);
+      for (int i = 0; i < 40 && t[i * 8 + 2]; ++i)
+        fprintf(stderr, "  chunk %2d: %7lld %7lld %7lld | %7lld %7lld %7lld\n", i, t[i * 8] - t0, t[i * 8 + 1] - t0, t[i * 8 + 2] - t0, t[i * 8 + 3] - t0,
+                t[i * 8 + 4] - t0, t[i * 8 + 5] - t0);
+      for (int i = 0; i < 8 && t[512 + i * 4 + 2]; ++i)
+        fprintf(stderr, "  tile %d epilogue: wait_start %7lld acc_full %7lld done %7lld\n", i, t[512 + i * 4] - t0, t[512 + i * 4 + 1] - t0, t[512 + i * 4 + 2] - t0);
+    }
+    return 0;
+  }
   B2G_CK(cg_launch(g, h->v2.d_maps, h->num_sms - h->v2.sm_reserve, s, pdl_enabled(), h->v2.dbg));
   return 0;
 }
