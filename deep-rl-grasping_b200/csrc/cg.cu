@@ -10,11 +10,12 @@
 //                 of tile i+1).  Precision modes per problem: 1 product (hi*hi), 3 products (2-plane split) or 6 products
 //                 (3-plane split hi/mid/lo: everything down to 2^-24), issued as 1..3 WIDE MMAs per k-step (see the issue
 //                 loop) -- profiles/precision_r2.md explains why the forward pass needs the 6-product mode;
-//   warps 3..10 : epilogue.  tcgen05.ld one accumulator row per thread, apply bias/ReLU or the ReLU mask, split into
-//                 BF16 planes, transpose through a 1 KiB warp-private staging tile and write coalesced rows.
+//   warps 3..10 : epilogue.  tcgen05.ld one accumulator row per thread, apply bias/ReLU or the ReLU mask (+ the bias-gradient column
+//                 sums), split into BF16 planes and store the row's 32 columns of every plane directly (16-byte vectors).
 #include <cuda_bf16.h>
 
 #include <cstdio>
+#include <cstdlib>
 
 #include "cg.cuh"
 #include "common.cuh"
@@ -24,9 +25,8 @@ namespace {
 
 // warps 0..1: TMA producers, warp 2: MMA issuer (owns TMEM), warps 3..10: epilogue
 constexpr int NPROD_WARPS = 2, MMA_WARP = NPROD_WARPS;
-constexpr int EPI_WARP0 = NPROD_WARPS + 1, NEPI_WARPS = 8;
+constexpr int EPI_WARP0 = NPROD_WARPS + 1, NEPI_WARPS = CG_EPI_WARPS;
 constexpr int NTHREADS = 32 * (EPI_WARP0 + NEPI_WARPS);
-constexpr int STG_PER_WARP = 1024;
 constexpr int TMEM_COLS = 512;          // two accumulators of up to 256 fp32 columns
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -162,17 +162,18 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {    // lo -
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 cg_kernel(const __grid_constant__ CgPack pk, int nprob, int total_tiles, const CUtensorMap* __restrict__ maps, int slot_bytes, int nstages,
-          int dbg, long long* __restrict__ trace) {
+          int dbg, long long* __restrict__ trace, int epi_tiles) {
   const CgProblem* __restrict__ probs = pk.p;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[CG_MAX_STAGES], bar_empty[CG_MAX_STAGES], bar_acc_full[2], bar_acc_empty[2];
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);          // warp-uniform for the compiler, not just in fact
-  const bool dbg_noload = dbg & 1, dbg_nomma = dbg & 2, dbg_nostore = dbg & 4;
+  const int trace_cta = dbg >> 8;                    // bring-up: the CTA whose roles write clock stamps
+  const bool dbg_noload = dbg & 1, dbg_nomma = dbg & 2, dbg_nostore = dbg & 4, dbg_nost = dbg & 16;    // 16: epilogue math without the global stores
   if (tid == 0) {
     for (int s = 0; s < nstages; ++s) { mbar_init(smem_u32(&bar_full[s]), 1); mbar_init(smem_u32(&bar_empty[s]), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&bar_acc_full[b]), 1); mbar_init(smem_u32(&bar_acc_empty[b]), NEPI_WARPS); }
+    for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&bar_acc_full[b]), 1); mbar_init(smem_u32(&bar_acc_empty[b]), epi_tiles ? NEPI_WARPS / 2 : NEPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == MMA_WARP) {
@@ -184,7 +185,6 @@ cg_kernel(const __grid_constant__ CgPack pk, int nprob, int total_tiles, const C
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
   const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t stg_base = ring + (uint32_t)nstages * (uint32_t)slot_bytes;
   pdl_trigger();
   pdl_wait();
 
@@ -202,6 +202,21 @@ cg_kernel(const __grid_constant__ CgPack pk, int nprob, int total_tiles, const C
         }
         const Tile ti = w.tile(tile);
         const CgProblem& P = probs[ti.p];
+        if (P.dep_ctr) {                                                 // fused layers: wait for the tiles this one reads
+          const int* __restrict__ ctr = P.dep_ctr;
+          const int x0 = P.dep_by_chunk ? ti.c_begin : ti.tm, x1 = P.dep_by_chunk ? ti.c_end : ti.tm + 1;
+          const int lo = x0 * P.dep_rows / P.dep_rows_tile, hi = min(P.dep_tiles - 1, (x1 * P.dep_rows - 1) / P.dep_rows_tile);
+          const int expect = P.dep_expect * (epi_tiles ? NEPI_WARPS / 2 : NEPI_WARPS);
+          for (int j = lo + lane; j <= hi; j += 32) {
+            int seen;
+            do {
+              asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(ctr + j) : "memory");
+              if (seen < expect) __nanosleep(100);
+            } while (seen < expect);
+          }
+          __syncwarp();
+          asm volatile("fence.proxy.async.global;" ::: "memory");
+        }
         // per-tile box origins: everything but the chunk terms
         int base[CG_MAX_LOADS][5];
 #pragma unroll
@@ -215,7 +230,7 @@ cg_kernel(const __grid_constant__ CgPack pk, int nprob, int total_tiles, const C
         }
         int c1 = n2 > 1 ? ti.c_begin / n2 : 0, c2 = ti.c_begin - c1 * n2;
         for (int c = ti.c_begin; c < ti.c_end; ++c, ++gc) {
-          const bool tr = trace && blockIdx.x == 0 && warp == 0 && gc < 64 && lane == 0;
+          const bool tr = trace && blockIdx.x == trace_cta && warp == 0 && gc < 64 && lane == 0;
           if (tr) trace[gc * 8 + 0] = clock64();
           if (gc >= (uint32_t)nstages) mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1);
           if (tr) trace[gc * 8 + 1] = clock64();
@@ -237,14 +252,17 @@ cg_kernel(const __grid_constant__ CgPack pk, int nprob, int total_tiles, const C
                   if ((j & (NPROD_WARPS - 1)) == warp && leader) tma_load(sbase + (uint32_t)L.smem_off, maps + L.map, full, L.rank, crd);
                   ++j;
                 } else {
-                  for (int pl = 0; pl < planes; ++pl, ++j)
+                  for (int pl = 0; pl < planes; ++pl, ++j) {
+#pragma unroll
+                    for (int d = 2; d < 5; ++d) if (d == L.rank - 1) crd[d] = pl;
                     if ((j & (NPROD_WARPS - 1)) == warp && leader)
-                      tma_load(sbase + (uint32_t)(pl * L.plane_stride + L.smem_off), maps + L.map + pl, full, L.rank, crd);
+                      tma_load(sbase + (uint32_t)(pl * L.plane_stride + L.smem_off), maps + L.map, full, L.rank, crd);
+                  }
                 }
               }
             }
           }
-          if (tr) trace[gc * 8 + 2] = clock64();
+          if (tr) { trace[gc * 8 + 2] = clock64(); trace[gc * 8 + 6] = ti.p * 100000 + ti.tm * 10 + ti.tn; }
           if (++c2 == n2) { c2 = 0; ++c1; }
           if (++s == (uint32_t)nstages) { s = 0; ph ^= 1; }
         }
@@ -275,7 +293,7 @@ cg_kernel(const __grid_constant__ CgPack pk, int nprob, int total_tiles, const C
         tc_fence_after();
         const uint32_t acc = tmem + buf * 256u;
         for (int c = ti.c_begin; c < ti.c_end; ++c) {
-          const bool tr = trace && blockIdx.x == 0 && gcm < 64 && lane == 0;
+          const bool tr = trace && blockIdx.x == trace_cta && gcm < 64 && lane == 0;
           if (tr) trace[gcm * 8 + 3] = clock64();
           mbar_wait(smem_u32(&bar_full[s]), ph);
           if (tr) trace[gcm * 8 + 4] = clock64();
@@ -326,7 +344,6 @@ cg_kernel(const __grid_constant__ CgPack pk, int nprob, int total_tiles, const C
   } else {
     // ============================================================================================ epilogue
     const int ew = warp - EPI_WARP0, q = warp & 3, half = ew >> 2;
-    const uint32_t stg = stg_base + (uint32_t)ew * STG_PER_WARP;
     uint32_t it = 0;
     Walker w;
     const int r = q * 32 + lane;                         // accumulator row of this thread
@@ -353,56 +370,21 @@ cg_kernel(const __grid_constant__ CgPack pk, int nprob, int total_tiles, const C
       if (ti.c_end <= ti.c_begin) continue;
       const CgProblem& P = probs[ti.p];
       const uint32_t buf = it & 1;
+      // epi_tiles: the two warp quads alternate TILES (quad h owns accumulator buffer h) instead of splitting the column groups of
+      // one tile, so that one quad's TMEM / ALU phase overlaps the other's store phase
+      if (epi_tiles && (int)buf != half) { ++it; continue; }
       const bool valid0 = r < rows_tile && ti.tm * rows_tile + r < lim_rows;
       const long long off0 = roff + (long long)ti.tm * o_tm, moff0 = rmoff + (long long)ti.tm * m_tm;
       const int n0 = ti.tn * umma_n, ngroups = umma_n >> 5;
-      const bool tre = trace && blockIdx.x == 0 && ew == 0 && lane == 0 && it < 16;
+      const bool tre = trace && blockIdx.x == trace_cta && (ew & 3) == 0 && lane == 0 && it < 16 && (epi_tiles || ew == 0);
       if (tre) trace[512 + it * 4 + 0] = clock64();
       mbar_wait(smem_u32(&bar_acc_full[buf]), (it >> 1) & 1);
       if (tre) trace[512 + it * 4 + 1] = clock64();
       tc_fence_after();
-      for (int g = half; g < ngroups; g += 2) {
+      for (int g = epi_tiles ? 0 : half; g < ngroups; g += epi_tiles ? 1 : 2) {
         const int ng = n0 + 32 * g;                      // first problem column of the group
-        uint32_t v[32];
-        const uint32_t taddr = tmem + buf * 256u + ((uint32_t)(q * 32) << 16) + (uint32_t)(32 * g);
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-            "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
-              "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
-              "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
-              "=r"(v[31])
-            : "r"(taddr));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (ngrp_acc > 1) {                                // correction column groups, smallest order first
-          uint32_t u[32];
-          asm volatile(
-              "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-              "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-              : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), "=r"(u[9]), "=r"(u[10]),
-                "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]), "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]),
-                "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]),
-                "=r"(u[31])
-              : "r"(taddr + (uint32_t)umma_n));
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          if (ngrp_acc > 2) {
-            uint32_t t[32];
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-                : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]), "=r"(t[8]), "=r"(t[9]), "=r"(t[10]),
-                  "=r"(t[11]), "=r"(t[12]), "=r"(t[13]), "=r"(t[14]), "=r"(t[15]), "=r"(t[16]), "=r"(t[17]), "=r"(t[18]), "=r"(t[19]), "=r"(t[20]),
-                  "=r"(t[21]), "=r"(t[22]), "=r"(t[23]), "=r"(t[24]), "=r"(t[25]), "=r"(t[26]), "=r"(t[27]), "=r"(t[28]), "=r"(t[29]), "=r"(t[30]),
-                  "=r"(t[31])
-                : "r"(taddr + 2u * (uint32_t)umma_n));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-            for (int j = 0; j < 32; ++j) u[j] = __float_as_uint(__uint_as_float(u[j]) + __uint_as_float(t[j]));
-          }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
-        }
-        if (dbg_nostore || ng >= n_valid) continue;
+        // ---- everything that does not depend on the accumulator is fetched BEFORE the TMEM loads are waited for: the epilogue of
+        //      a tile is a dependent chain of long-latency operations on 8 warps, so latency, not bandwidth, sets its length
         bool valid = valid0;
         long long off = off0, moff = moff0;
         if (grp_tab) {
@@ -410,9 +392,49 @@ cg_kernel(const __grid_constant__ CgPack pk, int nprob, int total_tiles, const C
           valid = valid0 && ri0 < P.grp_lim0[gg] && ri1 < P.grp_lim1[gg];
           off = off0 + P.grp_off[gg]; moff = moff0 + P.grp_moff[gg] - ng;     // (the mask load below adds ng)
         }
-        float x[32];
+        const bool live = !dbg_nostore && ng < n_valid;
+        float4 bv[8];
+        uint4 mk[4];
+        if (epi == CG_EPI_ACT && live) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+          for (int j = 0; j < 8; ++j) bv[j] = __ldg(reinterpret_cast<const float4*>(bias + (long long)(ng >> 5) * P.bias_grp) + j);
+        }
+        if (epi == CG_EPI_DGRAD && live) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) mk[j] = valid ? __ldg(reinterpret_cast<const uint4*>(mask + moff + ng) + j) : make_uint4(0, 0, 0, 0);
+        }
+        uint32_t v[32], u[32], t[32];
+        const uint32_t taddr = tmem + buf * 256u + ((uint32_t)(q * 32) << 16) + (uint32_t)(32 * g);
+#define CG_TMEM_LD32(dst, addr)                                                                                                              \
+  asm volatile(                                                                                                                             \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                                             \
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"     \
+      : "=r"(dst[0]), "=r"(dst[1]), "=r"(dst[2]), "=r"(dst[3]), "=r"(dst[4]), "=r"(dst[5]), "=r"(dst[6]), "=r"(dst[7]), "=r"(dst[8]),       \
+        "=r"(dst[9]), "=r"(dst[10]), "=r"(dst[11]), "=r"(dst[12]), "=r"(dst[13]), "=r"(dst[14]), "=r"(dst[15]), "=r"(dst[16]),              \
+        "=r"(dst[17]), "=r"(dst[18]), "=r"(dst[19]), "=r"(dst[20]), "=r"(dst[21]), "=r"(dst[22]), "=r"(dst[23]), "=r"(dst[24]),             \
+        "=r"(dst[25]), "=r"(dst[26]), "=r"(dst[27]), "=r"(dst[28]), "=r"(dst[29]), "=r"(dst[30]), "=r"(dst[31])                             \
+      : "r"(addr))
+        CG_TMEM_LD32(v, taddr);
+        if (ngrp_acc > 1) CG_TMEM_LD32(u, taddr + (uint32_t)umma_n);
+        if (ngrp_acc > 2) CG_TMEM_LD32(t, taddr + 2u * (uint32_t)umma_n);
+#undef CG_TMEM_LD32
+        if (tre && g == 0) trace[576 + it * 4 + 0] = clock64();
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (tre && g == 0) trace[576 + it * 4 + 1] = clock64();
+        float x[32];
+        if (ngrp_acc > 2) {                                // correction column groups, smallest order first
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) + (__uint_as_float(u[j]) + __uint_as_float(t[j]));
+        } else if (ngrp_acc > 1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) + __uint_as_float(u[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+        }
+        if (!live) continue;
+        // Every lane owns one output row and writes its 32 columns itself (64 B per BF16 plane, 128 B of fp32): 16-byte vector
+        // stores, no shared-memory transpose -- partial-sector writes are cheap next to the staging round trips they replace.
         if (epi == CG_EPI_RAW) {
           if (valid) {
             float* dst = P.out_f + off + (long long)(ng >> 5) * P.f_grp;
@@ -430,68 +452,67 @@ cg_kernel(const __grid_constant__ CgPack pk, int nprob, int total_tiles, const C
           continue;
         }
         if (epi == CG_EPI_WGRAD) {
-          const float sc = P.scale;
-          float* __restrict__ G = P.out_f;
-          const bool atomic = P.atomic != 0;
-          // 8 rows x 128 B per pass through the staging tile, then 8 lanes cover one row's 32 floats
-#pragma unroll 1
-          for (int pass = 0; pass < 4; ++pass) {
-            if ((lane >> 3) == pass) {
-              const int rr = lane & 7;
+          if (valid) {
+            const float sc = P.scale;
+            float* dst = P.out_f + off + (long long)(ng >> 5) * P.f_grp;
+            if (P.atomic) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const uint32_t a = stg + (uint32_t)(rr * 128 + ((j ^ rr) << 4));
-                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(x[4 * j] * sc), "f"(x[4 * j + 1] * sc), "f"(x[4 * j + 2] * sc),
-                             "f"(x[4 * j + 3] * sc)
+              for (int j = 0; j < 8; ++j)
+                asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst + 4 * j), "f"(x[4 * j] * sc), "f"(x[4 * j + 1] * sc),
+                             "f"(x[4 * j + 2] * sc), "f"(x[4 * j + 3] * sc)
                              : "memory");
-              }
-            }
-            __syncwarp();
+            } else {
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              const int idx = lane + 32 * i, rr = idx >> 3, ch = idx & 7, rq = pass * 8 + rr;
-              const long long o = __shfl_sync(0xffffffffu, off, rq);
-              const bool ok = __shfl_sync(0xffffffffu, (int)valid, rq) != 0;
-              float4 w;
-              const uint32_t a = stg + (uint32_t)(rr * 128 + ((ch ^ rr) << 4));
-              asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(w.x), "=f"(w.y), "=f"(w.z), "=f"(w.w) : "r"(a));
-              if (ok) {
-                float* dst = G + o + (long long)(ng >> 5) * P.f_grp + 4 * ch;
-                if (atomic) asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "f"(w.x), "f"(w.y), "f"(w.z), "f"(w.w) : "memory");
-                else *reinterpret_cast<float4*>(dst) = w;
-              }
+              for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(x[4 * j] * sc, x[4 * j + 1] * sc, x[4 * j + 2] * sc, x[4 * j + 3] * sc);
             }
-            __syncwarp();
           }
           continue;
         }
         if (epi == CG_EPI_ACT) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(bias + (long long)(ng >> 5) * P.bias_grp) + j);
-            x[4 * j] = fmaxf(x[4 * j] + b.x, 0.f); x[4 * j + 1] = fmaxf(x[4 * j + 1] + b.y, 0.f);
-            x[4 * j + 2] = fmaxf(x[4 * j + 2] + b.z, 0.f); x[4 * j + 3] = fmaxf(x[4 * j + 3] + b.w, 0.f);
+            x[4 * j] = fmaxf(x[4 * j] + bv[j].x, 0.f); x[4 * j + 1] = fmaxf(x[4 * j + 1] + bv[j].y, 0.f);
+            x[4 * j + 2] = fmaxf(x[4 * j + 2] + bv[j].z, 0.f); x[4 * j + 3] = fmaxf(x[4 * j + 3] + bv[j].w, 0.f);
           }
-          if (P.f0 > 0 && valid) {        // optional fp32 copy (cnn_fc1 features for the head kernels)
+          if (P.f0 > 0 && valid && !dbg_nost) {        // optional fp32 copy (cnn_fc1 features for the head kernels)
             float* dst = P.out_f + (long long)ti.tm * P.f_tm + (long long)r * P.f0 + (long long)(ng >> 5) * P.f_grp;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+            for (int j = 0; j < 4; ++j)
+              asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + 8 * j), "f"(x[8 * j]), "f"(x[8 * j + 1]), "f"(x[8 * j + 2]),
+                           "f"(x[8 * j + 3]), "f"(x[8 * j + 4]), "f"(x[8 * j + 5]), "f"(x[8 * j + 6]), "f"(x[8 * j + 7])
+                           : "memory");
           }
         } else {   // CG_EPI_DGRAD: ReLU mask = hi plane of the forward activation at the same position
-          uint4 mk[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) mk[j] = valid ? __ldg(reinterpret_cast<const uint4*>(mask + moff + ng) + j) : make_uint4(0, 0, 0, 0);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const uint32_t w[4] = {mk[j].x, mk[j].y, mk[j].z, mk[j].w};
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              if (!(w[u] & 0x00007FFFu)) x[8 * j + 2 * u] = 0.f;
-              if (!(w[u] & 0x7FFF0000u)) x[8 * j + 2 * u + 1] = 0.f;
+            for (int uu = 0; uu < 4; ++uu) {
+              if (!(w[uu] & 0x00007FFFu)) x[8 * j + 2 * uu] = 0.f;
+              if (!(w[uu] & 0x7FFF0000u)) x[8 * j + 2 * uu + 1] = 0.f;
             }
           }
+          if (P.colsum) {
+            // bias gradient: column sums over this warp's 32 rows (invalid rows are zero: their mask words were not loaded) by a
+            // transposing butterfly -- 31 shuffles leave lane c with the sum of column c -- then one 128-byte red.add per warp
+            float cs[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) cs[j] = x[j];
+#pragma unroll
+            for (int wd = 16; wd >= 1; wd >>= 1) {
+              const bool up = (lane & wd) != 0;
+#pragma unroll
+              for (int j = 0; j < wd; ++j) {
+                const float send = up ? cs[j] : cs[j + wd], keep = up ? cs[j + wd] : cs[j];
+                cs[j] = keep + __shfl_xor_sync(0xffffffffu, send, wd);
+              }
+            }
+            atomicAdd(P.colsum + ((ng + lane) & P.colsum_mask), cs[0]);
+          }
         }
-        // ---- BF16 planes: hi = bf16(x), then the residual feeds the next plane; 16 rows x 64 B per pass through staging
+        if (tre && g == 0) trace[576 + it * 4 + 2] = clock64();
+        // ---- BF16 planes: hi = bf16(x), then the residual feeds the next plane
         const long long gcol = grp_tab ? 0 : (long long)(ng >> 5) * grp_stride;
 #pragma unroll 1
         for (int pl = 0; pl < out_planes; ++pl) {
@@ -502,37 +523,26 @@ cg_kernel(const __grid_constant__ CgPack pk, int nprob, int total_tiles, const C
             x[2 * j] -= __uint_as_float(pk[j] << 16);
             x[2 * j + 1] -= __uint_as_float(pk[j] & 0xFFFF0000u);
           }
-          uint16_t* __restrict__ dstp = P.out_p[pl];
-#pragma unroll 1
-          for (int pass = 0; pass < 2; ++pass) {
-            if ((lane >> 4) == pass) {
-              const int rr = lane & 15;
+          if (valid && !dbg_nost) {              // 2 x 256-bit stores: every lane writes whole 32-byte sectors
+            uint16_t* dst = P.out_p[pl] + off + gcol;
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const uint32_t a = stg + (uint32_t)(rr * 64 + ((j ^ ((rr >> 1) & 3)) << 4));
-                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(pk[4 * j]), "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
-                             : "memory");
-              }
-            }
-            __syncwarp();
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              const int idx = lane + 32 * i, rr = idx >> 2, ch = idx & 3, rq = pass * 16 + rr;
-              const long long o = __shfl_sync(0xffffffffu, off, rq);
-              const bool ok = __shfl_sync(0xffffffffu, (int)valid, rq) != 0;
-              uint4 w;
-              const uint32_t a = stg + (uint32_t)(rr * 64 + ((ch ^ ((rr >> 1) & 3)) << 4));
-              asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "r"(a));
-              if (ok) *reinterpret_cast<uint4*>(dstp + o + gcol + 8 * ch) = w;
-            }
-            __syncwarp();
+            for (int j = 0; j < 2; ++j)
+              asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + 16 * j), "r"(pk[8 * j]), "r"(pk[8 * j + 1]), "r"(pk[8 * j + 2]),
+                           "r"(pk[8 * j + 3]), "r"(pk[8 * j + 4]), "r"(pk[8 * j + 5]), "r"(pk[8 * j + 6]), "r"(pk[8 * j + 7])
+                           : "memory");
           }
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty[buf]));
-      if (tre) trace[512 + it * 4 + 2] = clock64();
+      if (lane == 0) {
+        mbar_arrive(smem_u32(&bar_acc_empty[buf]));
+        if (P.done_ctr) {                                                // this warp's rows of the tile are in global memory
+          __threadfence();
+          atomicAdd(P.done_ctr + ti.tm, 1);
+        }
+      }
+      if (tre) { trace[512 + it * 4 + 2] = clock64(); trace[512 + it * 4 + 3] = ti.p * 100000 + ti.tm * 10 + ti.tn; }
       ++it;
     }
   }
@@ -576,13 +586,17 @@ int cg_finalize(CgGroup& g, int smem_budget) {
     CgProblem& P = g.host[i];
     P.tile_start = start;
     start += P.tiles_m * P.tiles_n * P.splits;
-    for (int l = 0; l < P.nloads; ++l) P.ld[l].plane_stride = P.ld[l].smem_off >= P.b_off ? P.b_pstride : P.a_pstride;
-    const int need = P.planes * (P.a_pstride + P.b_pstride);
+    for (int l = 0; l < P.nloads; ++l) {
+      CgLoad& L = P.ld[l];
+      L.plane_stride = L.smem_off >= P.b_off ? P.b_pstride : P.a_pstride;
+      if (L.plane_box && L.box_bytes != L.plane_stride) return -2;      // stacked planes must land where the MMA descriptors look
+    }
+    const int need = P.b_off + P.planes * P.b_pstride;
     slot = slot > need ? slot : need;
   }
   g.total_tiles = start;
   g.slot_bytes = (slot + 1023) / 1024 * 1024;
-  const int avail = smem_budget - 1024 /* alignment slack */ - NEPI_WARPS * STG_PER_WARP;
+  const int avail = smem_budget - 1024 /* alignment slack */;
   g.nstages = g.slot_bytes > 0 ? avail / g.slot_bytes : 0;
   if (g.nstages > CG_MAX_STAGES) g.nstages = CG_MAX_STAGES;
   return g.nstages >= 2 ? 0 : -1;
@@ -598,12 +612,14 @@ cudaError_t cg_launch(const CgGroup& g, const CUtensorMap* dev_maps, int num_sms
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  const int smem = 1024 + g.nstages * g.slot_bytes + NEPI_WARPS * STG_PER_WARP;
+  static int epi_tiles = -1;
+  if (epi_tiles < 0) { const char* e = getenv("B2G_EPI_TILES"); epi_tiles = (e && e[0] == '1') ? 1 : 0; }
+  const int smem = 1024 + g.nstages * g.slot_bytes;
   const int grid = g.total_tiles < num_sms ? g.total_tiles : num_sms;
   CgPack pk;              // (host staging; the launch copies it into the parameter buffer)
   static_assert(sizeof(CgPack) < 16 * 1024, "problem list must fit the kernel parameter space");
   for (int i = 0; i < g.n; ++i) pk.p[i] = g.host[i];
-  cudaError_t e = launch_pdl(cg_kernel, dim3(grid), dim3(NTHREADS), (size_t)smem, s, pdl, pk, g.n, g.total_tiles, dev_maps, g.slot_bytes, g.nstages, debug_flags, g_cg_trace);
+  cudaError_t e = launch_pdl(cg_kernel, dim3(grid), dim3(NTHREADS), (size_t)smem, s, pdl, pk, g.n, g.total_tiles, dev_maps, g.slot_bytes, g.nstages, debug_flags, g_cg_trace, epi_tiles);
   if (e != cudaSuccess) fprintf(stderr, "cg_launch %s: %s (grid %d, %d threads, smem %d = %d stages x %d)\n", g.name, cudaGetErrorString(e), grid, NTHREADS, smem, g.nstages, g.slot_bytes);
   return e;
 }

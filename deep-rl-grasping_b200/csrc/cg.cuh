@@ -13,9 +13,10 @@
 namespace b2g {
 
 constexpr int CG_MAX_LOADS = 4;     // TMA boxes per K-chunk and plane (A atoms + B atoms)
-constexpr int CG_MAX_PROBLEMS = 12; // problems per grouped launch (the whole list travels as a __grid_constant__ kernel parameter)
+constexpr int CG_MAX_PROBLEMS = 16; // problems per grouped launch (the whole list travels as a __grid_constant__ kernel parameter)
 constexpr int CG_MAX_STAGES = 8;
 constexpr int CG_MAX_PLANES = 3;
+constexpr int CG_EPI_WARPS = 8;    // epilogue warps of a CTA; each signals a finished tile once (dependency counters)
 
 enum CgEpiKind : int {
   CG_EPI_ACT = 0,     // relu(acc + bias[n]) -> BF16 planes (activations; optional fp32 copy)
@@ -25,12 +26,13 @@ enum CgEpiKind : int {
 };
 
 struct CgLoad {
-  int map;            // index of the plane-0 tensor map in the map table; plane p uses map + p
-  int rank;           // tensor-map rank (2..5)
+  int map;            // index of the tensor map (all planes of the tensor: plane = outermost dimension)
+  int rank;           // tensor-map rank including the plane dimension (3..5)
+  int box_bytes;      // bytes one plane of the box occupies (host-side check)
   int smem_off;       // byte offset of the plane-0 box inside a stage (A boxes below b_off, B boxes from b_off on)
   int plane_stride;   // bytes between the plane copies of the box inside the stage (filled by cg_finalize: a_pstride | b_pstride)
-  int plane_box;      // 1: the planes are the OUTERMOST box dimension of one (rank)-D map -> one instruction per chunk;
-                      // 0: one instruction per plane with map + p (boxes smaller than the plane stride)
+  int plane_box;      // 1: the box spans every plane -> one instruction per chunk, planes land box_bytes apart (== plane_stride);
+                      // 0: one instruction per plane (plane = last coordinate)
   int c0[5];          // box start coordinates: c0 + tm*d_tm + tn*d_tn + c1*d_c1 + c2*d_c2 (+ tm_tab)
   int d_tm[5], d_tn[5], d_c1[5], d_c2[5];
 };
@@ -76,8 +78,19 @@ struct CgProblem {
   int bias_grp;               // element distance between the bias blocks of consecutive 32-column groups (32 = contiguous)
   long long f_grp;            // same for the fp32 copy
   const uint16_t* mask;       // hi plane of the forward activation (DGRAD)
+  float* colsum;              // DGRAD: bias gradient of the layer = column sums of the masked gradient map, accumulated (red.add) from the
+  int colsum_mask;            //        fp32 accumulators: colsum[(column) & colsum_mask]   (nullptr: none)
   int atomic;                 // WGRAD: 1 = red.add (split-K or shared output), 0 = store
   float scale;                // WGRAD: multiply before accumulation (1 = none)
+  // ---- dependencies between the problems of ONE launch (fused layers).  Tiles are dealt to the CTAs in increasing order and
+  //      every CTA of the grid is resident, so a tile may wait for lower-numbered tiles of an earlier problem: the producers of
+  //      tile tm spin until the row-tiles [tm * dep_rows / dep_rows_tile, ((tm + 1) * dep_rows - 1) / dep_rows_tile] of the
+  //      producing problem have each collected dep_expect arrivals (one per epilogue warp and (tn, split) tile), then order the
+  //      generic-proxy stores they observed before their own async-proxy (TMA) reads.
+  int* done_ctr;              // arrival counters of THIS problem, one per tm (nullptr: nobody waits on it); zeroed before the launch
+  const int* dep_ctr;         // counters of the producing problem (nullptr: no dependency)
+  int dep_rows, dep_rows_tile, dep_tiles, dep_expect;
+  int dep_by_chunk;           // 1: the rows are indexed by the tile's K-chunk range [c_begin, c_end) instead of its tm (weight gradients)
 };
 
 struct CgGroup {               // one launch

@@ -264,28 +264,43 @@ int valloc(b2g_sac* h, T** ptr, size_t count) {
   return 0;
 }
 
-// np consecutive maps (one per plane base) with the same geometry; returns the index of the first or -1
+// ONE map over the np equidistant planes of a tensor: the given geometry plus an outermost plane dimension.  The box covers all
+// planes (one instruction fetches them, stacked plane after plane in shared memory) when one plane's box is a whole number of
+// 1024-byte swizzle atoms, else one plane (an instruction per plane, plane = last coordinate).  Distinct maps per plane cost a
+// descriptor fetch per instruction: ~375 cycles each whatever the box size (profiles/cg_trace_r2.txt).  Returns the map index or -1.
 int add_maps(V2State& v, uint16_t* const* planes, int np, int rank, std::initializer_list<uint64_t> dims, std::initializer_list<uint64_t> strides_b,
-             std::initializer_list<uint32_t> box, std::initializer_list<uint32_t> estr = {}) {
+             std::initializer_list<uint32_t> box, std::initializer_list<uint32_t> estr = {}, bool allow_whole = true) {
   uint64_t d[5] = {1, 1, 1, 1, 1}, s[5] = {0, 0, 0, 0, 0};
   uint32_t bx[5] = {1, 1, 1, 1, 1}, es[5] = {1, 1, 1, 1, 1};
   int i = 0; for (auto x : dims) d[i++] = x;
   i = 0; for (auto x : strides_b) s[i++] = x;
   i = 0; for (auto x : box) bx[i++] = x;
   i = 0; for (auto x : estr) es[i++] = x;
-  const int first = (int)v.maps.size();
-  for (int p = 0; p < np; ++p) {
-    CUtensorMap m;
-    if (cg_encode_map(&m, planes[p], rank, d, s, bx, es) != 0) return -1;
-    v.maps.push_back(m);
-  }
-  return first;
+  if (rank >= 5 || np < 1) return -1;
+  size_t rows = 1;
+  for (int k = 1; k < rank; ++k) rows *= (bx[k] + es[k] - 1) / es[k];
+  const size_t box_bytes = rows * bx[0] * 2;
+  const bool whole = allow_whole && np > 1 && box_bytes % 1024 == 0;
+  const long long pitch = np > 1 ? (long long)((const char*)planes[1] - (const char*)planes[0]) : 16;
+  for (int p = 2; p < np; ++p)
+    if ((const char*)planes[p] - (const char*)planes[p - 1] != pitch) return -1;
+  if (pitch <= 0 || pitch % 16) return -1;
+  d[rank] = (uint64_t)np; s[rank - 1] = (uint64_t)pitch; bx[rank] = whole ? (uint32_t)np : 1u; es[rank] = 1;
+  CUtensorMap m;
+  if (cg_encode_map(&m, planes[0], rank + 1, d, s, bx, es) != 0) return -1;
+  v.maps.push_back(m);
+  v.map_whole.push_back(whole ? 1 : 0);
+  v.map_box_bytes.push_back((int)box_bytes);
+  return (int)v.maps.size() - 1;
 }
 
+const V2State* g_mk_state = nullptr;     // set by v2_create: mk_load looks up whether the map's box holds every plane
 CgLoad mk_load(int map, int rank, int smem_off) {
   CgLoad L;
   memset(&L, 0, sizeof(L));
-  L.map = map; L.rank = rank; L.smem_off = smem_off;
+  L.map = map; L.rank = rank + 1; L.smem_off = smem_off;        // + the plane dimension
+  L.plane_box = g_mk_state->map_whole[map];
+  L.box_bytes = g_mk_state->map_box_bytes[map];
   return L;
 }
 
@@ -316,11 +331,13 @@ CgProblem mnmajor(int planes, int kr, int a_atoms, int b_atoms, int chunks) {
   P.chunks = chunks; P.n2 = chunks > 0 ? chunks : 1;
   P.planes = planes;
   const int atom = kr * 128;
-  P.a_off = 0; P.a_pstride = 2 * atom;             // an A plane always has room for two atoms (M = 128)
-  P.b_off = planes * P.a_pstride; P.b_pstride = b_atoms * atom;
+  // A region: [atom 0: plane 0, plane 1, ..][atom 1: ..] (each atom is one box with the planes stacked; M = 128 = two atoms);
+  // B region: [plane 0: atoms][plane 1: atoms] so that [B_0 | B_1] is one wide operand
+  P.a_off = 0; P.a_pstride = atom;
+  P.b_off = 2 * planes * atom; P.b_pstride = b_atoms * atom;
   P.tx_bytes = planes * (a_atoms + b_atoms) * atom;
   P.mn_major = 1; P.ksteps = kr / 16; P.a_kstep = P.b_kstep = 2048;
-  P.a_lbo = atom; P.b_lbo = atom;
+  P.a_lbo = planes * atom; P.b_lbo = atom;
   P.umma_n = 64 * b_atoms;
   P.nprod = planes == 3 ? 6 : (planes == 2 ? 3 : 1);
   P.d0 = 1 << 20; P.d1 = 1;
@@ -340,6 +357,44 @@ int push_group(b2g_sac* h, std::vector<CgGroup>& list, CgGroup& g, const char* n
   }
   list.push_back(g);
   return 0;
+}
+
+// Concatenates layer groups into one launch and chains them by arrival counters.  A wire says: problem `ci` of part `cons` reads
+// rows [x * dep_rows, (x + 1) * dep_rows) of the output of problem `pi` of part `prod`, x = its row-tile index (by_chunk = 0) or its
+// K-chunk index (by_chunk = 1: weight gradients reduce over the producer's rows); the producer finishes dep_rows_tile such rows per tile.
+struct Wire { int cons, ci, prod, pi, dep_rows, dep_rows_tile, by_chunk; };
+int fuse_groups(b2g_sac* h, const std::vector<const CgGroup*>& parts, const std::vector<Wire>& wires, const char* name, std::vector<CgGroup>& out, int& n_ctr) {
+  CgGroup f;
+  std::vector<int> first(parts.size());
+  for (size_t gi = 0; gi < parts.size(); ++gi) {
+    first[gi] = f.n;
+    for (int i = 0; i < parts[gi]->n; ++i) {
+      if (f.n >= CG_MAX_PROBLEMS) return b2g_fail(B2G_EINVAL, std::string("engine v2: too many problems in fused launch ") + name);
+      f.host[f.n++] = parts[gi]->host[i];
+    }
+  }
+  std::vector<int> ctr_of(f.n, -1);
+  for (const Wire& w : wires) {
+    const int pi = first[w.prod] + w.pi, qi = first[w.cons] + w.ci;
+    CgProblem& Pp = f.host[pi];
+    CgProblem& Pc = f.host[qi];
+    if (ctr_of[pi] < 0) { ctr_of[pi] = n_ctr; n_ctr += Pp.tiles_m; }
+    Pc.dep_rows = w.dep_rows; Pc.dep_rows_tile = w.dep_rows_tile; Pc.dep_tiles = Pp.tiles_m; Pc.dep_by_chunk = w.by_chunk;
+    Pc.dep_expect = Pp.tiles_n * Pp.splits;                      // x the signalling epilogue warps per tile (kernel side)
+    Pc.dep_ctr = (const int*)(intptr_t)(ctr_of[pi] + 1);        // counter index + 1; turned into pointers once the array exists
+  }
+  for (int i = 0; i < f.n; ++i) f.host[i].done_ctr = (int*)(intptr_t)(ctr_of[i] + 1);
+  return push_group(h, out, f, name);
+}
+
+void bind_counters(std::vector<CgGroup>& groups, int* base) {
+  for (CgGroup& g : groups)
+    for (int i = 0; i < g.n; ++i) {
+      CgProblem& P = g.host[i];
+      const intptr_t d = (intptr_t)P.done_ctr, c = (intptr_t)P.dep_ctr;
+      P.done_ctr = d ? base + (d - 1) : nullptr;
+      P.dep_ctr = c ? base + (c - 1) : nullptr;
+    }
 }
 
 }  // namespace
@@ -363,37 +418,42 @@ int v2_alloc(b2g_sac* h) {
     }
   for (int w = 0; w < 2; ++w) for (int p = 0; p < 3; ++p) v.A1[w][p] = bA1 + (w * 3 + p) * na;
   if (int rc = valloc(h, &v.z0v, (size_t)B * 192)) return rc;
-  // ---- gradient maps (2 planes) and natural-layout weight planes of the backward chain
-  for (int p = 0; p < 2; ++p) {
-    if (int rc = valloc(h, &v.dz0pi[p], (size_t)B * 64)) return rc;
-    if (int rc = valloc(h, &v.dz0v[p], (size_t)B * 192)) return rc;
-    if (int rc = valloc(h, &v.dZ1[p], (size_t)B * 225 * 64)) return rc;
-    for (int n = 0; n < 2; ++n) {
-      if (int rc = valloc(h, &v.dZ4[n][p], (size_t)B * 512)) return rc;
-      if (int rc = valloc(h, &v.dZ3[n][p], n3)) return rc;
-      if (int rc = valloc(h, &v.dZ2[n][p], n2)) return rc;
-      if (int rc = valloc(h, &v.W2n[n][p], 512 * 64)) return rc;
-      if (int rc = valloc(h, &v.W3n[n][p], 576 * 64)) return rc;
-      if (int rc = valloc(h, &v.Wfn[n][p], 1024 * 512)) return rc;
-      if (int rc = valloc(h, &v.K0n[n][p], (size_t)KF * (n == 1 ? 192 : 64))) return rc;
-    }
+  // ---- gradient maps (2 planes) and natural-layout weight planes of the backward chain.  The planes of a tensor are
+  //      equidistant in one allocation: the tensor maps address them through an extra (outermost) plane dimension
+  auto palloc = [&](uint16_t** arr, int np, size_t count) -> int {
+    const size_t pitch = (count + 63) / 64 * 64;
+    uint16_t* base = nullptr;
+    if (int rc = valloc(h, &base, pitch * np)) return rc;
+    for (int p = 0; p < np; ++p) arr[p] = base + p * pitch;
+    return 0;
+  };
+  if (int rc = palloc(v.dz0pi, 2, (size_t)B * 64)) return rc;
+  if (int rc = palloc(v.dz0v, 2, (size_t)B * 192)) return rc;
+  if (int rc = palloc(v.dZ1, 2, (size_t)B * 225 * 64)) return rc;
+  for (int n = 0; n < 2; ++n) {
+    if (int rc = palloc(v.dZ4[n], 2, (size_t)B * 512)) return rc;
+    if (int rc = palloc(v.dZ3[n], 2, n3)) return rc;
+    if (int rc = palloc(v.dZ2[n], 2, n2)) return rc;
+    if (int rc = palloc(v.W2n[n], 2, 512 * 64)) return rc;
+    if (int rc = palloc(v.W3n[n], 2, 576 * 64)) return rc;
+    if (int rc = palloc(v.Wfn[n], 2, 1024 * 512)) return rc;
+    if (int rc = palloc(v.K0n[n], 2, (size_t)KF * (n == 1 ? 192 : 64))) return rc;
   }
   // ---- weight planes
-  for (int p = 0; p < 3; ++p) {
-    if (int rc = valloc(h, &v.W1T[0][p], (size_t)64 * K1)) return rc;
-    if (int rc = valloc(h, &v.W1T[1][p], (size_t)32 * K1)) return rc;
-    for (int n = 0; n < 3; ++n) {
-      if (int rc = valloc(h, &v.W2T[n][p], 64 * 512)) return rc;
-      if (int rc = valloc(h, &v.W3T[n][p], 64 * 576)) return rc;
-      if (int rc = valloc(h, &v.WfT[n][p], 512 * 1024)) return rc;
-      if (int rc = valloc(h, &v.K0T[n][p], (size_t)(n == 1 ? 192 : 64) * KF)) return rc;
-    }
+  if (int rc = palloc(v.W1T[0], 3, (size_t)64 * K1)) return rc;
+  if (int rc = palloc(v.W1T[1], 3, (size_t)32 * K1)) return rc;
+  for (int n = 0; n < 3; ++n) {
+    if (int rc = palloc(v.W2T[n], 3, 64 * 512)) return rc;
+    if (int rc = palloc(v.W3T[n], 3, 64 * 576)) return rc;
+    if (int rc = palloc(v.WfT[n], 3, 512 * 1024)) return rc;
+    if (int rc = palloc(v.K0T[n], 3, (size_t)(n == 1 ? 192 : 64) * KF)) return rc;
   }
   return 0;
 }
 
 int v2_create(b2g_sac* h) {
   V2State& v = h->v2;
+  g_mk_state = &v;
   const int B = h->B, Ci = h->Cimg, K1 = 64 * Ci, KF = v.KF, FS = h->FS;
   const size_t n1 = (size_t)B * 225 * 32;
   // ---- plane jobs (weights change every step)
@@ -554,6 +614,7 @@ int v2_create(b2g_sac* h) {
   }
 
   // ================================================================================ backward problems (3-product mode)
+  { const char* e = getenv("B2G_BIAS_EPI"); v.epi_colsum = !(e && e[0] == '0'); }
   if (v.bwd) {
     const int NB = 2;
     // ---- heads dgrad: dZ4 = dz0 . K0^T, masked by the cnn_fc1 ReLU (F > 0)
@@ -574,6 +635,7 @@ int v2_create(b2g_sac* h) {
         P.o_tm = 128 * 512; P.o0 = 512; P.n_valid = 512; P.out_planes = 2;
         for (int p = 0; p < 2; ++p) P.out_p[p] = v.dZ4[n][p];
         P.mask = v.F[n][0]; P.m_tm = (long long)128 * KF; P.m0 = KF;
+        if (v.epi_colsum) { P.colsum = h->g(std::string(nets[n]) + "/cnn_fc1/b"); P.colsum_mask = 511; }
         g.host[g.n++] = P;
       }
       if (int rc = push_group(h, v.bwd_groups, g, "heads_dgrad")) return rc;
@@ -595,16 +657,17 @@ int v2_create(b2g_sac* h) {
           P.o_tm = 128 * 1024; P.o0 = 1024; P.n_valid = 1024; P.out_planes = 2;
           for (int p = 0; p < 2; ++p) P.out_p[p] = v.dZ3[n][p];
           P.mask = v.H3[n][0]; P.m_tm = 128 * 1024; P.m0 = 1024;
+          if (v.epi_colsum) { P.colsum = h->g(std::string(nets[n]) + "/cnn3/b"); P.colsum_mask = 63; }     // dZ3 row = [16 pixels][64 channels]
           g.host[g.n++] = P;
         }
         {
           const int mA = add_maps(v, v.H3[n], NB, 2, {1024, (uint64_t)B}, {2048}, {64, 64});
-          const int mB = add_maps(v, v.dZ4[n], NB, 2, {512, (uint64_t)B}, {1024}, {64, 64});
+          const int mB = add_maps(v, v.dZ4[n], NB, 2, {512, (uint64_t)B}, {1024}, {64, 64}, {}, false);     // two B atoms per plane
           if (mA < 0 || mB < 0) return b2g_fail(B2G_ECUDA, "engine v2: cuTensorMapEncodeTiled failed (fc1 wgrad)");
           CgProblem P = mnmajor(NB, 64, 2, 2, (B + 63) / 64);
           P.nloads = 4;
           for (int a = 0; a < 2; ++a) {
-            P.ld[a] = mk_load(mA, 2, a * 8192); P.ld[a].c0[0] = 64 * a; P.ld[a].d_tm[0] = 128; P.ld[a].d_c2[1] = 64;
+            P.ld[a] = mk_load(mA, 2, a * P.a_lbo); P.ld[a].c0[0] = 64 * a; P.ld[a].d_tm[0] = 128; P.ld[a].d_c2[1] = 64;
             P.ld[2 + a] = mk_load(mB, 2, P.b_off + a * 8192); P.ld[2 + a].c0[0] = 64 * a; P.ld[2 + a].d_tn[0] = 128; P.ld[2 + a].d_c2[1] = 64;
           }
           P.tiles_m = 8; P.tiles_n = 4;
@@ -641,6 +704,7 @@ int v2_create(b2g_sac* h) {
           P.o_tm = 108 * 64; P.o0 = 64; P.n_valid = 64; P.out_planes = 2;
           for (int p = 0; p < 2; ++p) P.out_p[p] = v.dZ2[n][p];
           P.mask = v.H2[n][0]; P.m_tm = 108 * 64; P.m0 = 64;
+          if (v.epi_colsum) { P.colsum = h->g(std::string(nets[n]) + "/cnn2/b"); P.colsum_mask = 63; }
           g.host[g.n++] = P;
         }
         {
@@ -649,7 +713,7 @@ int v2_create(b2g_sac* h) {
           if (mA < 0 || mB < 0) return b2g_fail(B2G_ECUDA, "engine v2: cuTensorMapEncodeTiled failed (conv3 wgrad)");
           CgProblem P = mnmajor(NB, 64, 2, 1, (B + 3) / 4);
           P.nloads = 3;
-          for (int a = 0; a < 2; ++a) { P.ld[a] = mk_load(mA, 4, a * 8192); P.ld[a].d_c2[3] = 4; }
+          for (int a = 0; a < 2; ++a) { P.ld[a] = mk_load(mA, 4, a * P.a_lbo); P.ld[a].d_c2[3] = 4; }
           P.ld[2] = mk_load(mB, 2, P.b_off); P.ld[2].d_c2[1] = 64;
           P.tm_tab = dtab;
           P.tiles_m = 5; P.tiles_n = 1;
@@ -669,7 +733,7 @@ int v2_create(b2g_sac* h) {
       CgGroup g;
       for (int n = 0; n < 2; ++n) {
         const int mA = add_maps(v, v.dZ2[n], NB, 4, {64, 6, 6, (uint64_t)B}, {128, 768, 4608}, {64, 8, 8, 2});
-        const int mB = add_maps(v, v.W2n[n], NB, 2, {64, 512}, {128}, {64, 64});
+        const int mB = add_maps(v, v.W2n[n], NB, 2, {64, 512}, {128}, {64, 64}, {}, false);      // two boxes (py) per plane
         if (mA < 0 || mB < 0) return b2g_fail(B2G_ECUDA, "engine v2: cuTensorMapEncodeTiled failed (conv2 dgrad)");
         CgProblem P = kmajor(NB, 128, 4, 2, 128);
         P.tx_bytes = NB * (128 * 128 + 2 * 64 * 128);
@@ -695,6 +759,7 @@ int v2_create(b2g_sac* h) {
         P.n_valid = 128; P.out_planes = 2;
         for (int p = 0; p < 2; ++p) P.out_p[p] = v.dZ1[p];
         P.mask = v.H1[n][0];
+        if (v.epi_colsum) { P.colsum = h->g(std::string(nets[n]) + "/cnn1/b"); P.colsum_mask = 31; }       // four parity classes x 32 channels
         g.host[g.n++] = P;
       }
       if (int rc = push_group(h, v.bwd_groups, g, "conv2_dgrad")) return rc;
@@ -708,7 +773,7 @@ int v2_create(b2g_sac* h) {
         if (mA < 0 || mB < 0) return b2g_fail(B2G_ECUDA, "engine v2: cuTensorMapEncodeTiled failed (conv2 wgrad)");
         CgProblem P = mnmajor(NB, 144, 2, 1, (B + 3) / 4);
         P.nloads = 3;
-        for (int a = 0; a < 2; ++a) { P.ld[a] = mk_load(mA, 4, a * 144 * 128); P.ld[a].c0[1] = 2 * a; P.ld[a].d_tm[2] = 1; P.ld[a].d_c2[3] = 4; }
+        for (int a = 0; a < 2; ++a) { P.ld[a] = mk_load(mA, 4, a * P.a_lbo); P.ld[a].c0[1] = 2 * a; P.ld[a].d_tm[2] = 1; P.ld[a].d_c2[3] = 4; }
         P.ld[2] = mk_load(mB, 2, P.b_off); P.ld[2].d_c2[1] = 144;
         P.tiles_m = 4; P.tiles_n = 1;
         P.splits = std::max(1, std::min(P.chunks, std::max(8, (P.chunks + 7) / 8)));           // <= 8 chunks (72 k-steps) per chain
@@ -724,7 +789,7 @@ int v2_create(b2g_sac* h) {
         P.nloads = 3;
         // both 64-wide atoms of the M tile are always fetched; an atom beyond K1 (one image channel: K1 = 64) is out of
         // bounds and arrives as zeros, its output rows are masked by lim_rows
-        for (int a = 0; a < 2; ++a) { P.ld[a] = mk_load(mA, 2, a * 8192); P.ld[a].c0[0] = 64 * a; P.ld[a].d_tm[0] = 128; P.ld[a].d_c2[1] = 64; }
+        for (int a = 0; a < 2; ++a) { P.ld[a] = mk_load(mA, 2, a * P.a_lbo); P.ld[a].c0[0] = 64 * a; P.ld[a].d_tm[0] = 128; P.ld[a].d_c2[1] = 64; }
         P.ld[2] = mk_load(mB, 2, P.b_off); P.ld[2].d_c2[1] = 64;
         P.tiles_m = (K1 + 127) / 128; P.tiles_n = 1;
         P.splits = std::max(1, std::min(P.chunks, std::max(84 / P.tiles_m, (P.chunks + 15) / 16)));
@@ -761,6 +826,47 @@ int v2_create(b2g_sac* h) {
         v.colsum_part[part] = dcj; v.n_colsum_part[part] = (int)cj.size(); v.colsum_ctas_part[part] = cstart;
       }
     }
+  }
+  // ================================================================================ fused launches
+  // One persistent launch for the forward chain (conv1 -> conv2 -> conv3 -> cnn_fc1 -> head fc0) and one for the backward chain up
+  // to the conv2 dgrad: a launch boundary costs ~7 us of an ~20 us layer (launch + TMEM allocation, first-fetch latency, the last
+  // tile's epilogue and the ragged last wave: profiles/cg_trace_r2.txt), a counter wait between dependent TILES costs nothing
+  // once the pipeline is full.  The conv wgrad launch stays separate (its 108 KB stages would halve every other problem's ring).
+  {
+    const char* ef = getenv("B2G_FUSE");
+    v.fuse = !(ef && ef[0] == '0');
+  }
+  if (v.fuse) {
+    int n_ctr = 0;
+    {
+      std::vector<const CgGroup*> parts;
+      for (auto& g : v.fwd) parts.push_back(&g);                 // conv1 (obs, next), conv2 x3, conv3 x3, fc1 x3, fc0 x3
+      std::vector<Wire> w;
+      for (int n = 0; n < 3; ++n) {
+        w.push_back({1, n, 0, n < 2 ? 0 : 1, 3 * 225, 128, 0});  // conv2 tile: 3 samples of H1 (225 rows each; conv1 tiles are 128 rows)
+        w.push_back({2, n, 1, n, 8 * 36, 108, 0});               // conv3 tile: 8 samples of H2 (36 rows each; conv2 tiles are 3 samples)
+        w.push_back({3, n, 2, n, 128 * 16, 128, 0});             // fc1 tile: 128 samples of H3 (16 rows each)
+        w.push_back({4, n, 3, n, 128, 128, 0});                  // fc0 tile: 128 feature rows (all 8 column tiles of them)
+      }
+      if (int rc = fuse_groups(h, parts, w, "fwd_fused", v.fwd_fused, n_ctr)) return rc;
+    }
+    if (v.bwd) {
+      std::vector<const CgGroup*> parts;
+      for (auto& g : v.bwd_groups) if (std::string(g.name) != "conv_wgrad") parts.push_back(&g);   // heads_dgrad, fc1_bwd, conv3_bwd, conv2_dgrad
+      std::vector<Wire> w;
+      for (int n = 0; n < 2; ++n) {
+        w.push_back({1, 2 * n, 0, n, 128, 128, 0});              // fc1 dgrad tile: 128 rows of dZ4
+        w.push_back({1, 2 * n + 1, 0, n, 64, 128, 1});           // fc1 wgrad chunk: 64 rows of dZ4
+        w.push_back({2, 2 * n, 1, 2 * n, 3, 128, 0});            // conv3 dgrad tile: 3 samples of dZ3 (fc1 dgrad rows are samples)
+        w.push_back({2, 2 * n + 1, 1, 2 * n, 4, 128, 1});        // conv3 wgrad chunk: 4 samples of dZ3
+        w.push_back({3, n, 2, 2 * n, 72, 108, 0});               // conv2 dgrad tile: 2 samples of dZ2 (36 rows each; conv3 dgrad tiles are 3 samples)
+      }
+      if (int rc = fuse_groups(h, parts, w, "bwd_fused", v.bwd_fused, n_ctr)) return rc;
+    }
+    if (int rc = valloc(h, &v.dep_ctr, (size_t)n_ctr)) return rc;
+    v.n_dep_ctr = n_ctr;
+    bind_counters(v.fwd_fused, v.dep_ctr);
+    bind_counters(v.bwd_fused, v.dep_ctr);
   }
   if (int rc = valloc(h, &v.d_maps, v.maps.size())) return rc;
   B2G_CK(cudaMemcpyAsync(v.d_maps, v.maps.data(), v.maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, h->stream));
@@ -802,6 +908,7 @@ int v2_gather(b2g_sac* h, const GatherArgs& ga, cudaStream_t s) {
 
 int v2_colsum(b2g_sac* h, cudaStream_t s, int part) {
   V2State& v = h->v2;
+  if (v.epi_colsum) return 0;
   if (v.colsum_ctas_part[part] > 0)
     colsum2_kernel<<<v.colsum_ctas_part[part], 256, 0, s>>>((const Colsum2Job*)v.colsum_part[part], v.n_colsum_part[part]);
   return 0;
@@ -818,7 +925,8 @@ int v2_launch(b2g_sac* h, const CgGroup& g, cudaStream_t s) {
     if (!s_trace_buf) cudaMalloc(&s_trace_buf, 640 * sizeof(long long));
     cudaMemsetAsync(s_trace_buf, 0, 640 * sizeof(long long), s);
     g_cg_trace = s_trace_buf;
-    cudaError_t e = cg_launch(g, h->v2.d_maps, h->num_sms - h->v2.sm_reserve, s, false, h->v2.dbg);
+    const char* tc = getenv("B2G_CG_TRACE_CTA");
+    cudaError_t e = cg_launch(g, h->v2.d_maps, h->num_sms - h->v2.sm_reserve, s, false, h->v2.dbg | ((tc ? atoi(tc) : 0) << 8));
     g_cg_trace = nullptr;
     if (e != cudaSuccess) return b2g_fail(B2G_ECUDA, cudaGetErrorString(e));
     static int shots = 0;
@@ -828,11 +936,13 @@ int v2_launch(b2g_sac* h, const CgGroup& g, cudaStream_t s) {
       cudaMemcpy(t, s_trace_buf, sizeof(t), cudaMemcpyDeviceToHost);
       const long long t0 = t[0];
       fprintf(stderr, "cg trace %s (cycles; per chunk: prod wait_start wait_done issued | mma wait_start full_seen committed)\n", g.name);
-      for (int i = 0; i < 40 && t[i * 8 + 2]; ++i)
-        fprintf(stderr, "  chunk %2d: %7lld %7lld %7lld | %7lld %7lld %7lld\n", i, t[i * 8] - t0, t[i * 8 + 1] - t0, t[i * 8 + 2] - t0, t[i * 8 + 3] - t0,
-                t[i * 8 + 4] - t0, t[i * 8 + 5] - t0);
-      for (int i = 0; i < 8 && t[512 + i * 4 + 2]; ++i)
-        fprintf(stderr, "  tile %d epilogue: wait_start %7lld acc_full %7lld done %7lld\n", i, t[512 + i * 4] - t0, t[512 + i * 4 + 1] - t0, t[512 + i * 4 + 2] - t0);
+      for (int i = 0; i < 64 && t[i * 8 + 2]; ++i)
+        fprintf(stderr, "  chunk %2d (p %lld tm %lld): %7lld %7lld %7lld | %7lld %7lld %7lld\n", i, t[i * 8 + 6] / 100000, t[i * 8 + 6] % 100000 / 10, t[i * 8] - t0,
+                t[i * 8 + 1] - t0, t[i * 8 + 2] - t0, t[i * 8 + 3] - t0, t[i * 8 + 4] - t0, t[i * 8 + 5] - t0);
+      for (int i = 0; i < 16 && t[512 + i * 4 + 2]; ++i)
+        fprintf(stderr, "  tile %d (p %lld tm %lld) epilogue: wait_start %7lld acc_full %7lld done %7lld | first group: ld issued %7lld ld done %7lld math done %7lld\n", i,
+                t[512 + i * 4 + 3] / 100000, t[512 + i * 4 + 3] % 100000 / 10, t[512 + i * 4] - t0, t[512 + i * 4 + 1] - t0, t[512 + i * 4 + 2] - t0,
+                t[576 + i * 4] - t0, t[576 + i * 4 + 1] - t0, t[576 + i * 4 + 2] - t0);
     }
     return 0;
   }

@@ -895,7 +895,12 @@ int issue_step(b2g_sac* h, bool sampled, bool apply, bool want_per_sample, Prof*
     }
     return 0;
   };
-  if (h->v2.on) {
+  const bool fused = h->v2.on && h->v2.fuse && !h->v2.fwd_fused.empty();
+  if (fused) {
+    CK(cudaMemsetAsync(h->v2.dep_ctr, 0, (size_t)h->v2.n_dep_ctr * sizeof(int), s)); ++n;
+    if (int rc = v2_launch(h, h->v2.fwd_fused[0], s)) return rc;
+    ++n; mark("fwd_fused");
+  } else if (h->v2.on) {
     for (auto& g : h->v2.fwd) { if (int rc = v2_launch(h, g, s)) return rc; ++n; mark(g.name); }
   } else {
     for (auto& g : h->fwd_groups) if (int rc = run_group(g, s)) return rc;
@@ -937,16 +942,43 @@ int issue_step(b2g_sac* h, bool sampled, bool apply, bool want_per_sample, Prof*
     for (auto& g : h->bwd_groups) {
       if (g.name != "heads_wgrad") continue;
       if (fork) { CK(cudaEventRecord(h->ev_aux[2], s)); CK(cudaStreamWaitEvent(ax, h->ev_aux[2], 0)); }
-      if (int rc = run_group(g, lx)) return rc;
+      if (h->heads_wgrad_simt && h->H == 64) {
+        HeadsWgradArgs wa{};
+        const char* hp[4] = {"model/pi", "model/values_fn/vf", "model/values_fn/qf1", "model/values_fn/qf2"};
+        for (int q = 0; q < 4; ++q) {
+          wa.X0[q] = h->F[q == 0 ? 0 : 1];
+          wa.dz0[q] = q == 0 ? h->dz0_pi : h->dz0_v3 + (q - 1) * h->H;
+          wa.dz0_ld[q] = q == 0 ? h->H : 3 * h->H;
+          wa.a0[q] = h->a0[q]; wa.dz1[q] = h->dz1[q];
+          wa.M0[q] = q >= 2 ? h->feat_dim + h->A : h->feat_dim;
+          wa.g_k0[q] = h->g(std::string(hp[q]) + "/fc0/kernel"); wa.g_b0[q] = h->g(std::string(hp[q]) + "/fc0/bias");
+          wa.g_k1[q] = h->g(std::string(hp[q]) + "/fc1/kernel"); wa.g_b1[q] = h->g(std::string(hp[q]) + "/fc1/bias");
+        }
+        wa.x0_ld = h->FS; wa.B = h->B;
+        heads_wgrad_launch(wa, lx); ++n; if (!fork) mark("heads_wgrad");
+      } else if (int rc = run_group(g, lx)) return rc;
+    }
+    // single GPU: the chain heads_dgrad .. conv2_dgrad is one fused launch; both bias-sum launches then overlap the conv wgrads
+    const bool fused_bwd = fused && !h->v2.bwd_fused.empty() && !ov;
+    if (fused_bwd) {
+      if (int rc = v2_launch(h, h->v2.bwd_fused[0], s)) return rc;
+      ++n; mark("bwd_fused");
+      if (fork) { CK(cudaEventRecord(h->ev_aux[3], s)); CK(cudaStreamWaitEvent(ax, h->ev_aux[3], 0)); }
+      if (!h->v2.epi_colsum) {
+        if (int rc = v2_colsum(h, lx, 0)) return rc;
+        if (int rc = v2_colsum(h, lx, 1)) return rc;
+        n += 2; if (!fork) mark("bias_grads");
+      }
     }
     for (auto& g : h->v2.bwd_groups) {
+      if (fused_bwd && std::string(g.name) != "conv_wgrad") continue;
       if (int rc = v2_launch(h, g, s)) return rc;
       ++n; mark(g.name);
       const std::string gn(g.name);
       if (gn == "heads_dgrad") {            // dZ4 exists: cnn_fc1 bias sums on the leaf branch
         if (fork) { CK(cudaEventRecord(h->ev_aux[3], s)); CK(cudaStreamWaitEvent(ax, h->ev_aux[3], 0)); }
         if (int rc = v2_colsum(h, lx, 0)) return rc;
-        ++n; if (!fork) mark("bias_grads_fc1");
+        if (!h->v2.epi_colsum) { ++n; if (!fork) mark("bias_grads_fc1"); }
       }
       if (gn == "fc1_bwd" && ov) {
         CK(cudaMemcpyAsync(h->G + h->n_train, h->metrics, MET_GN_PI * sizeof(float), cudaMemcpyDeviceToDevice, s)); ++n;
@@ -964,7 +996,7 @@ int issue_step(b2g_sac* h, bool sampled, bool apply, bool want_per_sample, Prof*
       if (gn == "conv2_dgrad") {            // every gradient map exists: conv bias sums overlap the conv wgrads
         if (fork) { CK(cudaEventRecord(h->ev_aux[0], s)); CK(cudaStreamWaitEvent(ax, h->ev_aux[0], 0)); }
         if (int rc = v2_colsum(h, lx, 1)) return rc;
-        ++n; if (!fork) mark("bias_grads");
+        if (!h->v2.epi_colsum) { ++n; if (!fork) mark("bias_grads"); }
       }
     }
     h->v2.sm_reserve = 0;

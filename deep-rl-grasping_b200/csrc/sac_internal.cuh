@@ -65,8 +65,15 @@ struct V2State {
   void* colsum_part[2]{}; int n_colsum_part[2]{}, colsum_ctas_part[2]{};   // [0] cnn_fc1 biases (early), [1] conv biases
   int sm_reserve = 0;            // SMs left to a collective that runs concurrently with the persistent GEMM grids
   std::vector<CUtensorMap> maps; // host copy
+  std::vector<char> map_whole;   // per map: the box spans every plane
+  std::vector<int> map_box_bytes;
   CUtensorMap* d_maps = nullptr;
   std::vector<CgGroup> fwd, bwd_groups;
+  // fused launches: the layer groups above concatenated into one persistent launch each, chained by arrival counters
+  std::vector<CgGroup> fwd_fused, bwd_fused;
+  bool fuse = false;
+  bool epi_colsum = true;        // conv / cnn_fc1 bias gradients come from the DGRAD epilogues (else: colsum2 launches over the planes)
+  int* dep_ctr = nullptr; int n_dep_ctr = 0;
   std::vector<int*> tabs;
   int dbg = 0;
 };
@@ -111,6 +118,7 @@ struct b2g_sac {
   float *h1[3]{}, *h2[3]{}, *h3[3]{}, *F[3]{};
   float *dZ4[2]{}, *dZ3p[2]{}, *dZ2p[2]{}, *dZ1[2]{};
   float *z0[5]{}, *a0[4]{}, *dz1[4]{}, *dz0_pi = nullptr, *dz0_v3 = nullptr;
+  bool heads_wgrad_simt = true;  // head weight gradients on the CUDA cores (tail.cu) instead of a v1 tensor-engine launch
   // BF16 hi/lo planes ([..][0] = hi, [..][1] = lo) of the tensors that feed forward / dgrad contractions
   bool use_planes = false;
   uint16_t *xp[2][2]{}, *h1p[3][2]{}, *h2p[3][2]{}, *h3p[3][2]{};

@@ -689,7 +689,61 @@ void act_launch(const TailArgs& t, int n, int deterministic, float* act_out, cud
 }
 
 namespace {
+// grid (10, 4 heads, HW_KSPLIT batch slices), 256 threads: x = 0..8 -> rows [64x, 64x + 64) of the fc0 kernel gradient
+// X0^T . dz0 (x = 0 also the fc0 bias gradient: column sums of dz0), x = 9 -> the fc1 kernel gradient a0^T . dz1 and the fc1 bias.  Every CTA
+// reduces its batch slice in chunks of 32 samples through shared memory (4 x 4 outputs per thread) and accumulates into the
+// zeroed gradient arena with red.add.
+constexpr int HW_KSPLIT = 4;
+__global__ void __launch_bounds__(256) heads_wgrad_kernel(const HeadsWgradArgs a) {
+  __shared__ __align__(16) float As[32][64], Bs[32][64];
+  const int q = blockIdx.y, rb = blockIdx.x, tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const bool fc1 = rb == 9;
+  const int M = fc1 ? 64 : a.M0[q], row0 = fc1 ? 0 : rb * 64;
+  if (row0 >= M) return;
+  const float* __restrict__ X = fc1 ? a.a0[q] : a.X0[q];
+  const float* __restrict__ D = fc1 ? a.dz1[q] : a.dz0[q];
+  const int xld = fc1 ? 64 : a.x0_ld, dld = fc1 ? 64 : a.dz0_ld[q];
+  const int per = (a.B + HW_KSPLIT - 1) / HW_KSPLIT, b0 = blockIdx.z * per, b1 = min(a.B, b0 + per);
+  float acc[4][4] = {};
+  float cs = 0.f;                         // bias sum: column tid of this CTA's gradient tile (x == 0: fc0 bias from dz0, x == 9: fc1 bias from dz1)
+  for (int bb = b0; bb < b1; bb += 32) {
+    for (int i = tid; i < 32 * 64; i += 256) {
+      const int k = i >> 6, c = i & 63, b = bb + k;
+      const bool ok = b < b1;
+      As[k][c] = (ok && row0 + c < M) ? X[(size_t)b * xld + row0 + c] : 0.f;
+      Bs[k][c] = ok ? D[(size_t)b * dld + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) {
+      const float4 av = *reinterpret_cast<const float4*>(&As[k][4 * ty]);
+      const float4 bv = *reinterpret_cast<const float4*>(&Bs[k][4 * tx]);
+      const float ar[4] = {av.x, av.y, av.z, av.w}, br[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+    }
+    if ((fc1 || rb == 0) && tid < 64) {
+#pragma unroll 8
+      for (int k = 0; k < 32; ++k) cs += Bs[k][tid];
+    }
+    __syncthreads();
+  }
+  float* __restrict__ G = fc1 ? a.g_k1[q] : a.g_k0[q];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = row0 + 4 * ty + i;
+    if (r < M)
+      asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(G + (size_t)r * 64 + 4 * tx), "f"(acc[i][0]), "f"(acc[i][1]), "f"(acc[i][2]),
+                   "f"(acc[i][3])
+                   : "memory");
+  }
+  if ((fc1 || rb == 0) && tid < 64) atomicAdd((fc1 ? a.g_b1[q] : a.g_b0[q]) + tid, cs);
+}
 }  // namespace
+
+void heads_wgrad_launch(const HeadsWgradArgs& a, cudaStream_t s) { heads_wgrad_kernel<<<dim3(10, 4, HW_KSPLIT), 256, 0, s>>>(a); }
 
 static size_t tail_smem(int A) {
   return sizeof(float) * (S_NW * H * LD + 2 * H * A + 2 * A + 3 * (H + 1) + MET_COUNT + 1 + 8 +
