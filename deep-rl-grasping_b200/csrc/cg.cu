@@ -161,7 +161,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {    // lo -
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1)
-cg_kernel(const __grid_constant__ CgPack pk, int nprob, int total_tiles, const CUtensorMap* __restrict__ maps, int slot_bytes, int nstages,
+cg_kernel(const __grid_constant__ CgPack pk, int nprob, int total_tiles, const CUtensorMap* __restrict__ maps, int max_stages,
           int dbg, long long* __restrict__ trace, int epi_tiles) {
   const CgProblem* __restrict__ probs = pk.p;
   extern __shared__ uint8_t smem_raw[];
@@ -172,7 +172,7 @@ cg_kernel(const __grid_constant__ CgPack pk, int nprob, int total_tiles, const C
   const int trace_cta = dbg >> 8;                    // bring-up: the CTA whose roles write clock stamps
   const bool dbg_noload = dbg & 1, dbg_nomma = dbg & 2, dbg_nostore = dbg & 4, dbg_nost = dbg & 16;    // 16: epilogue math without the global stores
   if (tid == 0) {
-    for (int s = 0; s < nstages; ++s) { mbar_init(smem_u32(&bar_full[s]), 1); mbar_init(smem_u32(&bar_empty[s]), 1); }
+    for (int s = 0; s < max_stages; ++s) { mbar_init(smem_u32(&bar_full[s]), 1); mbar_init(smem_u32(&bar_empty[s]), 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&bar_acc_full[b]), 1); mbar_init(smem_u32(&bar_acc_empty[b]), epi_tiles ? NEPI_WARPS / 2 : NEPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -191,7 +191,10 @@ cg_kernel(const __grid_constant__ CgPack pk, int nprob, int total_tiles, const C
   if (warp < NPROD_WARPS) {
     // ============================================================================================ TMA producers
     {
-      uint32_t gc = 0, s = 0, ph = 0;                    // ring slot and its phase, advanced without divisions
+      // Ring slot s and the phase parity of every slot (bit s of ph): the partition of the ring (slot size, slot count) belongs
+      // to the problem, so a slot's barrier may have completed a different number of phases than its neighbours'.
+      uint32_t gc = 0, s = 0, ph = 0;
+      int slot_bytes = 0, nstages = 1;
       Walker w;
       int n2 = 1, nloads = 0, planes = 0, tx = 0;
       const int* tab = nullptr;
@@ -199,6 +202,12 @@ cg_kernel(const __grid_constant__ CgPack pk, int nprob, int total_tiles, const C
         if (w.advance(probs, nprob, tile)) {
           const CgProblem& P = probs[w.p];
           n2 = P.n2; nloads = P.nloads; planes = P.planes; tx = P.tx_bytes; tab = P.tm_tab;
+          if (P.slot_bytes != slot_bytes || P.nstages != nstages) {
+            // new partition: every slot of the old one must have been consumed before its bytes are overwritten (a fresh
+            // barrier passes the parity-1 wait at once, so never-used slots cost nothing)
+            for (int q = 0; q < nstages; ++q) mbar_wait(smem_u32(&bar_empty[q]), ((ph >> q) & 1u) ^ 1u);
+            slot_bytes = P.slot_bytes; nstages = P.nstages; s = 0;
+          }
         }
         const Tile ti = w.tile(tile);
         const CgProblem& P = probs[ti.p];
@@ -232,7 +241,7 @@ cg_kernel(const __grid_constant__ CgPack pk, int nprob, int total_tiles, const C
         for (int c = ti.c_begin; c < ti.c_end; ++c, ++gc) {
           const bool tr = trace && blockIdx.x == trace_cta && warp == 0 && gc < 64 && lane == 0;
           if (tr) trace[gc * 8 + 0] = clock64();
-          if (gc >= (uint32_t)nstages) mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1);
+          mbar_wait(smem_u32(&bar_empty[s]), ((ph >> s) & 1u) ^ 1u);
           if (tr) trace[gc * 8 + 1] = clock64();
           const uint32_t full = smem_u32(&bar_full[s]);
           const bool leader = elect_one();
@@ -264,7 +273,8 @@ cg_kernel(const __grid_constant__ CgPack pk, int nprob, int total_tiles, const C
           }
           if (tr) { trace[gc * 8 + 2] = clock64(); trace[gc * 8 + 6] = ti.p * 100000 + ti.tm * 10 + ti.tn; }
           if (++c2 == n2) { c2 = 0; ++c1; }
-          if (++s == (uint32_t)nstages) { s = 0; ph ^= 1; }
+          ph ^= 1u << s;
+          if (++s == (uint32_t)nstages) s = 0;
         }
       }
     }
@@ -272,6 +282,7 @@ cg_kernel(const __grid_constant__ CgPack pk, int nprob, int total_tiles, const C
     // ============================================================================================ MMA issuer
     {
       uint32_t it = 0, s = 0, ph = 0, gcm = 0;
+      int slot_bytes = 0, nstages = 1;
       Walker w;
       bool mnm = false;
       uint32_t idesc[3] = {0, 0, 0}, a_off = 0, b_off = 0, a_ks = 0, b_ks = 0, a_lbo = 0, b_lbo = 0, a_ps = 0, ncol = 0;
@@ -285,6 +296,7 @@ cg_kernel(const __grid_constant__ CgPack pk, int nprob, int total_tiles, const C
           for (int j = 0; j < 3; ++j) idesc[j] = make_idesc(128, P.umma_n * (j + 1), mnm);      // N = n, 2n, 3n
           ksteps = P.ksteps; nprod = P.nprod; a_ps = (uint32_t)P.a_pstride;
           a_off = P.a_off; b_off = P.b_off; a_ks = P.a_kstep; b_ks = P.b_kstep; a_lbo = P.a_lbo; b_lbo = P.b_lbo;
+          if (P.slot_bytes != slot_bytes || P.nstages != nstages) { slot_bytes = P.slot_bytes; nstages = P.nstages; s = 0; }
         }
         const Tile ti = w.tile(tile);
         if (ti.c_end <= ti.c_begin) continue;
@@ -295,7 +307,7 @@ cg_kernel(const __grid_constant__ CgPack pk, int nprob, int total_tiles, const C
         for (int c = ti.c_begin; c < ti.c_end; ++c) {
           const bool tr = trace && blockIdx.x == trace_cta && gcm < 64 && lane == 0;
           if (tr) trace[gcm * 8 + 3] = clock64();
-          mbar_wait(smem_u32(&bar_full[s]), ph);
+          mbar_wait(smem_u32(&bar_full[s]), (ph >> s) & 1u);
           if (tr) trace[gcm * 8 + 4] = clock64();
           tc_fence_after();
           const uint32_t sbase = ring + s * (uint32_t)slot_bytes;
@@ -333,7 +345,8 @@ cg_kernel(const __grid_constant__ CgPack pk, int nprob, int total_tiles, const C
           __syncwarp();
           if (tr) trace[gcm * 8 + 5] = clock64();
           ++gcm;
-          if (++s == (uint32_t)nstages) { s = 0; ph ^= 1; }
+          ph ^= 1u << s;
+          if (++s == (uint32_t)nstages) s = 0;
         }
         if (elect_one()) umma_commit(smem_u32(&bar_acc_full[buf]));
         __syncwarp();
@@ -592,14 +605,24 @@ int cg_finalize(CgGroup& g, int smem_budget) {
       if (L.plane_box && L.box_bytes != L.plane_stride) return -2;      // stacked planes must land where the MMA descriptors look
     }
     const int need = P.b_off + P.planes * P.b_pstride;
-    slot = slot > need ? slot : need;
+    P.slot_bytes = (need + 1023) / 1024 * 1024;
+    slot = slot > P.slot_bytes ? slot : P.slot_bytes;
   }
   g.total_tiles = start;
-  g.slot_bytes = (slot + 1023) / 1024 * 1024;
   const int avail = smem_budget - 1024 /* alignment slack */;
-  g.nstages = g.slot_bytes > 0 ? avail / g.slot_bytes : 0;
-  if (g.nstages > CG_MAX_STAGES) g.nstages = CG_MAX_STAGES;
-  return g.nstages >= 2 ? 0 : -1;
+  g.slot_bytes = slot; g.nstages = 0;              // (largest slot; the most stages any problem uses)
+  int ring = 0;
+  for (int i = 0; i < g.n; ++i) {
+    CgProblem& P = g.host[i];
+    P.nstages = P.slot_bytes > 0 ? avail / P.slot_bytes : 0;
+    if (P.nstages > CG_MAX_STAGES) P.nstages = CG_MAX_STAGES;
+    if (P.nstages < 2) return -1;
+    P.slot_bytes = avail / P.nstages / 1024 * 1024;        // one slot size per stage count: problems with equal depth share the partition
+    g.nstages = g.nstages > P.nstages ? g.nstages : P.nstages;
+    ring = ring > P.nstages * P.slot_bytes ? ring : P.nstages * P.slot_bytes;
+  }
+  g.ring_bytes = ring;
+  return 0;
 }
 
 long long* g_cg_trace = nullptr;      // bring-up: clock64 stamps of CTA 0 (set by tools through b2g_debug_cg_trace)
@@ -614,13 +637,13 @@ cudaError_t cg_launch(const CgGroup& g, const CUtensorMap* dev_maps, int num_sms
   }
   static int epi_tiles = -1;
   if (epi_tiles < 0) { const char* e = getenv("B2G_EPI_TILES"); epi_tiles = (e && e[0] == '1') ? 1 : 0; }
-  const int smem = 1024 + g.nstages * g.slot_bytes;
+  const int smem = 1024 + g.ring_bytes;
   const int grid = g.total_tiles < num_sms ? g.total_tiles : num_sms;
   CgPack pk;              // (host staging; the launch copies it into the parameter buffer)
   static_assert(sizeof(CgPack) < 16 * 1024, "problem list must fit the kernel parameter space");
   for (int i = 0; i < g.n; ++i) pk.p[i] = g.host[i];
-  cudaError_t e = launch_pdl(cg_kernel, dim3(grid), dim3(NTHREADS), (size_t)smem, s, pdl, pk, g.n, g.total_tiles, dev_maps, g.slot_bytes, g.nstages, debug_flags, g_cg_trace, epi_tiles);
-  if (e != cudaSuccess) fprintf(stderr, "cg_launch %s: %s (grid %d, %d threads, smem %d = %d stages x %d)\n", g.name, cudaGetErrorString(e), grid, NTHREADS, smem, g.nstages, g.slot_bytes);
+  cudaError_t e = launch_pdl(cg_kernel, dim3(grid), dim3(NTHREADS), (size_t)smem, s, pdl, pk, g.n, g.total_tiles, dev_maps, g.nstages, debug_flags, g_cg_trace, epi_tiles);
+  if (e != cudaSuccess) fprintf(stderr, "cg_launch %s: %s (grid %d, %d threads, smem %d)\n", g.name, cudaGetErrorString(e), grid, NTHREADS, smem);
   return e;
 }
 

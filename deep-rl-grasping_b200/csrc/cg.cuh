@@ -46,6 +46,8 @@ struct CgProblem {
   int a_pstride, b_pstride;   // stage layout: [A plane 0 | A plane 1 | ..][B plane 0 | B plane 1 | ..]; bytes of one A / B plane.
                               // The B planes are CONTIGUOUS so that one UMMA descriptor spans [B0|B1|B2] (see nprod)
   int tx_bytes;               // bytes all boxes of one stage deliver (planes x sum of box bytes)
+  int slot_bytes, nstages;    // stage ring geometry of THIS problem (cg_finalize): the problems of a launch share the ring's bytes, not
+                              // its partition -- the ring is drained when the partition changes
   CgLoad ld[CG_MAX_LOADS];
   const int* tm_tab;          // optional [tiles_m][CG_MAX_LOADS][2]: extra offsets of coordinates 1 and 2 per (tm, load)
   // ---- MMA
@@ -97,7 +99,7 @@ struct CgGroup {               // one launch
   CgProblem host[CG_MAX_PROBLEMS];
   int n = 0;
   int total_tiles = 0;
-  int slot_bytes = 0, nstages = 0;
+  int slot_bytes = 0, nstages = 0, ring_bytes = 0;     // largest slot / most stages of any problem; bytes of the ring
   const char* name = "";
   double flops = 0;
 };

@@ -378,6 +378,12 @@ int fuse_groups(b2g_sac* h, const std::vector<const CgGroup*>& parts, const std:
     const int pi = first[w.prod] + w.pi, qi = first[w.cons] + w.ci;
     CgProblem& Pp = f.host[pi];
     CgProblem& Pc = f.host[qi];
+    if (Pc.dep_ctr && ctr_of[pi] < 0) {
+      // a second producer of the same consumer (the two nets' conv2 dgrads both write dZ1): it signals the first one's counters
+      ctr_of[pi] = (int)(intptr_t)Pc.dep_ctr - 1;
+      Pc.dep_expect += Pp.tiles_n * Pp.splits;
+      continue;
+    }
     if (ctr_of[pi] < 0) { ctr_of[pi] = n_ctr; n_ctr += Pp.tiles_m; }
     Pc.dep_rows = w.dep_rows; Pc.dep_rows_tile = w.dep_rows_tile; Pc.dep_tiles = Pp.tiles_m; Pc.dep_by_chunk = w.by_chunk;
     Pc.dep_expect = Pp.tiles_n * Pp.splits;                      // x the signalling epilogue warps per tile (kernel side)
@@ -831,7 +837,7 @@ int v2_create(b2g_sac* h) {
   // One persistent launch for the forward chain (conv1 -> conv2 -> conv3 -> cnn_fc1 -> head fc0) and one for the backward chain up
   // to the conv2 dgrad: a launch boundary costs ~7 us of an ~20 us layer (launch + TMEM allocation, first-fetch latency, the last
   // tile's epilogue and the ragged last wave: profiles/cg_trace_r2.txt), a counter wait between dependent TILES costs nothing
-  // once the pipeline is full.  The conv wgrad launch stays separate (its 108 KB stages would halve every other problem's ring).
+  // once the pipeline is full.  The stage ring is re-partitioned per problem (the conv2 wgrad needs 108 KB stages, the rest 64 - 72 KB).
   {
     const char* ef = getenv("B2G_FUSE");
     v.fuse = !(ef && ef[0] == '0');
@@ -852,7 +858,7 @@ int v2_create(b2g_sac* h) {
     }
     if (v.bwd) {
       std::vector<const CgGroup*> parts;
-      for (auto& g : v.bwd_groups) if (std::string(g.name) != "conv_wgrad") parts.push_back(&g);   // heads_dgrad, fc1_bwd, conv3_bwd, conv2_dgrad
+      for (auto& g : v.bwd_groups) parts.push_back(&g);          // heads_dgrad, fc1_bwd, conv3_bwd, conv2_dgrad, conv_wgrad
       std::vector<Wire> w;
       for (int n = 0; n < 2; ++n) {
         w.push_back({1, 2 * n, 0, n, 128, 128, 0});              // fc1 dgrad tile: 128 rows of dZ4
@@ -860,8 +866,26 @@ int v2_create(b2g_sac* h) {
         w.push_back({2, 2 * n, 1, 2 * n, 3, 128, 0});            // conv3 dgrad tile: 3 samples of dZ3 (fc1 dgrad rows are samples)
         w.push_back({2, 2 * n + 1, 1, 2 * n, 4, 128, 1});        // conv3 wgrad chunk: 4 samples of dZ3
         w.push_back({3, n, 2, 2 * n, 72, 108, 0});               // conv2 dgrad tile: 2 samples of dZ2 (36 rows each; conv3 dgrad tiles are 3 samples)
+        w.push_back({4, n, 2, 2 * n, 144, 108, 1});              // conv2 wgrad chunk: 4 samples of dZ2
       }
+      // conv1 wgrad chunk: 64 rows of dZ1 [B*225][pi | vf]; a conv2 dgrad tile (of EITHER net: both must be done) covers 2 samples = 450 rows
+      w.push_back({4, 2, 3, 0, 64, 450, 1});
+      w.push_back({4, 2, 3, 1, 64, 450, 1});
       if (int rc = fuse_groups(h, parts, w, "bwd_fused", v.bwd_fused, n_ctr)) return rc;
+      // data parallel: the same chain cut after cnn_fc1, where the gradients of [cnn_fc1 .. end] (84 % of the bytes) are final
+      // and their all-reduce starts on the side stream underneath the conv backward
+      std::vector<const CgGroup*> pa(parts.begin(), parts.begin() + 2), pb(parts.begin() + 2, parts.end());     // pb: conv3_bwd, conv2_dgrad, conv_wgrad
+      std::vector<Wire> wa, wb;
+      for (int n = 0; n < 2; ++n) {
+        wa.push_back({1, 2 * n, 0, n, 128, 128, 0});
+        wa.push_back({1, 2 * n + 1, 0, n, 64, 128, 1});
+        wb.push_back({1, n, 0, 2 * n, 72, 108, 0});
+        wb.push_back({2, n, 0, 2 * n, 144, 108, 1});
+      }
+      wb.push_back({2, 2, 1, 0, 64, 450, 1});
+      wb.push_back({2, 2, 1, 1, 64, 450, 1});
+      if (int rc = fuse_groups(h, pa, wa, "bwd_fused_fc", v.bwd_fused, n_ctr)) return rc;
+      if (int rc = fuse_groups(h, pb, wb, "bwd_fused_conv", v.bwd_fused, n_ctr)) return rc;
     }
     if (int rc = valloc(h, &v.dep_ctr, (size_t)n_ctr)) return rc;
     v.n_dep_ctr = n_ctr;

@@ -958,20 +958,48 @@ int issue_step(b2g_sac* h, bool sampled, bool apply, bool want_per_sample, Prof*
         heads_wgrad_launch(wa, lx); ++n; if (!fork) mark("heads_wgrad");
       } else if (int rc = run_group(g, lx)) return rc;
     }
-    // single GPU: the chain heads_dgrad .. conv2_dgrad is one fused launch; both bias-sum launches then overlap the conv wgrads
-    const bool fused_bwd = fused && !h->v2.bwd_fused.empty() && !ov;
+    // single GPU: the chain heads_dgrad .. conv2_dgrad is one fused launch.  Data parallel: two (cut after cnn_fc1, where the
+    // early all-reduce starts).
+    const bool fused_bwd = fused && h->v2.bwd_fused.size() == 3;
+    auto early_allreduce = [&]() -> int {
+      CK(cudaMemcpyAsync(h->G + h->n_train, h->metrics, MET_GN_PI * sizeof(float), cudaMemcpyDeviceToDevice, s)); ++n;
+      CK(cudaEventRecord(h->ev_fork, s));
+      CK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+      if (fork) { CK(cudaEventRecord(h->ev_aux[4], ax)); CK(cudaStreamWaitEvent(h->side, h->ev_aux[4], 0)); }   // heads_wgrad (+ fc1 bias sums)
+      if (int rc = nccl_ck(g_nccl.GroupStart())) return rc;
+      if (int rc = nccl_ck(g_nccl.AllReduce(h->G + pi_fc1, h->G + pi_fc1, (size_t)(h->n_pi - pi_fc1), 7, 0, h->nccl_comm2, h->side))) return rc;
+      if (int rc = nccl_ck(g_nccl.AllReduce(h->G + v_fc1, h->G + v_fc1, (size_t)(h->n_train + MET_COUNT - v_fc1), 7, 0, h->nccl_comm2, h->side))) return rc;
+      if (int rc = nccl_ck(g_nccl.GroupEnd())) return rc;
+      ++n;
+      CK(cudaEventRecord(h->ev_join, h->side));
+      h->v2.sm_reserve = h->ar_sms;
+      return 0;
+    };
     if (fused_bwd) {
-      if (int rc = v2_launch(h, h->v2.bwd_fused[0], s)) return rc;
-      ++n; mark("bwd_fused");
-      if (fork) { CK(cudaEventRecord(h->ev_aux[3], s)); CK(cudaStreamWaitEvent(ax, h->ev_aux[3], 0)); }
+      if (!ov) {
+        if (int rc = v2_launch(h, h->v2.bwd_fused[0], s)) return rc;
+        ++n; mark("bwd_fused");
+      } else {
+        if (int rc = v2_launch(h, h->v2.bwd_fused[1], s)) return rc;
+        ++n; mark("bwd_fused_fc");
+        if (!h->v2.epi_colsum) {
+          if (fork) { CK(cudaEventRecord(h->ev_aux[3], s)); CK(cudaStreamWaitEvent(ax, h->ev_aux[3], 0)); }
+          if (int rc = v2_colsum(h, lx, 0)) return rc;
+          ++n;
+        }
+        if (int rc = early_allreduce()) return rc;
+        if (int rc = v2_launch(h, h->v2.bwd_fused[2], s)) return rc;
+        ++n; mark("bwd_fused_conv");
+      }
       if (!h->v2.epi_colsum) {
-        if (int rc = v2_colsum(h, lx, 0)) return rc;
+        if (fork) { CK(cudaEventRecord(h->ev_aux[0], s)); CK(cudaStreamWaitEvent(ax, h->ev_aux[0], 0)); }
+        if (!ov) { if (int rc = v2_colsum(h, lx, 0)) return rc; ++n; }
         if (int rc = v2_colsum(h, lx, 1)) return rc;
-        n += 2; if (!fork) mark("bias_grads");
+        ++n; if (!fork) mark("bias_grads");
       }
     }
     for (auto& g : h->v2.bwd_groups) {
-      if (fused_bwd && std::string(g.name) != "conv_wgrad") continue;
+      if (fused_bwd) break;
       if (int rc = v2_launch(h, g, s)) return rc;
       ++n; mark(g.name);
       const std::string gn(g.name);
@@ -980,19 +1008,7 @@ int issue_step(b2g_sac* h, bool sampled, bool apply, bool want_per_sample, Prof*
         if (int rc = v2_colsum(h, lx, 0)) return rc;
         if (!h->v2.epi_colsum) { ++n; if (!fork) mark("bias_grads_fc1"); }
       }
-      if (gn == "fc1_bwd" && ov) {
-        CK(cudaMemcpyAsync(h->G + h->n_train, h->metrics, MET_GN_PI * sizeof(float), cudaMemcpyDeviceToDevice, s)); ++n;
-        CK(cudaEventRecord(h->ev_fork, s));
-        CK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
-        if (fork) { CK(cudaEventRecord(h->ev_aux[4], ax)); CK(cudaStreamWaitEvent(h->side, h->ev_aux[4], 0)); }   // heads_wgrad + fc1 bias sums
-        if (int rc = nccl_ck(g_nccl.GroupStart())) return rc;
-        if (int rc = nccl_ck(g_nccl.AllReduce(h->G + pi_fc1, h->G + pi_fc1, (size_t)(h->n_pi - pi_fc1), 7, 0, h->nccl_comm2, h->side))) return rc;
-        if (int rc = nccl_ck(g_nccl.AllReduce(h->G + v_fc1, h->G + v_fc1, (size_t)(h->n_train + MET_COUNT - v_fc1), 7, 0, h->nccl_comm2, h->side))) return rc;
-        if (int rc = nccl_ck(g_nccl.GroupEnd())) return rc;
-        ++n;
-        CK(cudaEventRecord(h->ev_join, h->side));
-        h->v2.sm_reserve = h->ar_sms;
-      }
+      if (gn == "fc1_bwd" && ov) { if (int rc = early_allreduce()) return rc; }
       if (gn == "conv2_dgrad") {            // every gradient map exists: conv bias sums overlap the conv wgrads
         if (fork) { CK(cudaEventRecord(h->ev_aux[0], s)); CK(cudaStreamWaitEvent(ax, h->ev_aux[0], 0)); }
         if (int rc = v2_colsum(h, lx, 1)) return rc;
