@@ -23,16 +23,24 @@ import time
 
 import numpy as np
 
-os.environ.setdefault("NCCL_DEBUG", "WARN")        # no "NCCL version" banner on stdout: the driver reads ONE JSON line
+# The driver reads ONE JSON line on stdout.  NCCL (and anything else native) prints its banners to fd 1, so fd 1 is pointed at stderr
+# for the whole run and the JSON line goes to the saved descriptor.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: str):
+    os.write(_REAL_STDOUT, (line.rstrip("\n") + "\n").encode())
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 GOLD = os.path.join(ROOT, "tests", "golden")
 FLOP_PER_STEP_B256 = 2 * 256 * 18_923_328          # 9.689 GFLOP
 LR = 3e-4
-KERNEL_DESC = ("cg_kernel (TMA-fed tcgen05 contraction engine, csrc/cg.cu: one elected thread issues cp.async.bulk.tensor boxes -- "
-               "implicit-im2col / shifted-window / zero-bordered tensor-map views of the BF16 activation planes -- into a 128B-swizzled "
-               "smem ring; tcgen05.mma kind::f16 with fp32 TMEM accumulators; forward = 6-product 3-plane split, backward = "
-               "3-product 2-plane split; 10 launches per step) + gg_tc_kernel for the four small head wgrads")
+KERNEL_DESC = ("cg_kernel (TMA-fed tcgen05 contraction engine, csrc/cg.cu): converged producer warps issue cp.async.bulk.tensor boxes -- "
+               "implicit-im2col / shifted-window / zero-bordered tensor-map views of the BF16 activation planes, all planes of an operand in one "
+               "box -- into a 128B-swizzled smem ring; tcgen05.mma kind::f16 with fp32 TMEM accumulators, one wide MMA per operand plane; "
+               "forward = 6-product 3-plane split, backward = 3-product 2-plane split; TWO persistent launches per step (forward chain "
+               "conv1..fc0, backward chain heads dgrad..conv wgrads), layers chained tile by tile through arrival counters")
 WORKLOAD = "SAC depth CNN (config/gripper_grasp.yaml), batch 256/GPU, 64x64x2 obs, 1M-slot replay"
 
 
@@ -161,7 +169,7 @@ def run_reference(args):
                          "sample": f"{n} full B=256 gradient steps in {el:.1f}s; torch intra-op threads calibrated to {cores} of {os.cpu_count()}"},
         "e2e": {"value": rate, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(json.dumps(line))
 
 
 def numa_bind(dev):
@@ -215,6 +223,8 @@ def main():
     ap.add_argument("--regions", type=int, default=7, help="timed K-step regions; the MEDIAN region is reported")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dp", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: p2p = the optimiser launch reduces / updates / broadcasts over NVLink peer memory; nccl = all-reduce + replicated Adam")
     ap.add_argument("--no-c3", action="store_true", help="skip the RGB-D B=1024 extra measurement (config.extra.c3)")
     ap.add_argument("--precision", default="bf16x3", choices=["fp32", "bf16x3", "bf16"],
                     help="bf16x3 = tcgen05 BF16 hi/lo split, the mode that passes the 1e-4 parity tests (default)")
@@ -249,6 +259,8 @@ def main():
     prec = {"fp32": 0, "bf16x3": 1, "bf16": 2}[args.precision]
     L = b200grasp.Learner((64, 64, 2), n_act=5, batch_size=B, buffer_size=args.buffer_size, seed=1234, device=local,
                           rank=rank, nranks=world, nccl_id=nccl_id, precision=prec)
+    if world > 1 and args.dp == "p2p":
+        L.dp_connect_torch()
     L.load_parameters(raw_params)      # identical replicas on every rank
     L.set_norm_stats(vn["obs_mean"], vn["obs_var"], float(vn["ret_var"]), float(vn["clip_obs"]), float(vn["clip_reward"]),
                      float(vn["epsilon"]))
@@ -400,8 +412,8 @@ def main():
         L3.close()
 
     if rank == 0:
-        gemm_groups = {k: v for k, v in prof.items() if k.startswith("conv") or k.startswith("cnn_") or k.startswith("fc1_") or k.startswith("heads_fc0")
-                       or k in ("heads_wgrad", "heads_dgrad")}
+        gemm_groups = {k: v for k, v in prof.items() if "fused" in k or k.startswith("conv") or k.startswith("cnn_") or k.startswith("fc1_")
+                       or k.startswith("heads_fc0") or k == "heads_dgrad" or (k == "heads_wgrad" and "fwd_fused" not in prof)}
         gemm_serial = sum(gemm_groups.values())
         share = gemm_serial / sum(prof.values())
         ms_step = ms / args.steps
@@ -439,7 +451,7 @@ def main():
                        "global_batch": B * world, "replay_capacity": args.buffer_size, "replay_filled": args.replay_filled,
                        "l2": f"inputs larger than L2: replay working set {args.replay_filled * 2 * 32768 / 2**30:.1f} GiB >> 126 MB; minibatch slots are random per step",
                        "timing": f"median of {args.regions} regions of {args.steps} steps (CUDA events on the learner's stream, max over ranks per region); regions_ms={[round(x, 3) for x in region_ms]}",
-                       "precision": {"fp32": "fp32 FFMA (B2G_PREC_FP32_SIMT)", "bf16x3": "tcgen05 BF16 hi/lo split x3, fp32 TMEM accumulate (B2G_PREC_BF16X3; passes 1e-4 parity)", "bf16": "tcgen05 single-pass BF16 (fast mode, ~5e-4 on Q)"}[args.precision], "parallelism": f"dp{world}",
+                       "precision": {"fp32": "fp32 FFMA (B2G_PREC_FP32_SIMT)", "bf16x3": "tcgen05 BF16 hi/lo split x3, fp32 TMEM accumulate (B2G_PREC_BF16X3; passes 1e-4 parity)", "bf16": "tcgen05 single-pass BF16 (fast mode, ~5e-4 on Q)"}[args.precision], "parallelism": f"dp{world}" + ("" if world == 1 else (" (gradients reduced, slices updated and parameters broadcast by one kernel over NVLink peer memory)" if args.dp == "p2p" else " (NCCL all-reduce, replicated Adam)")),
                        "sync_steps_per_s": sync_steps_per_s, "numa": numa,
                        "extra": {"c3": c3}},
             "clocks": clk.summary(),
@@ -456,7 +468,7 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     if line is not None:
-        print(json.dumps(line))
+        emit(json.dumps(line))
 
 
 if __name__ == "__main__":

@@ -195,6 +195,24 @@ struct OptimArgs {
 };
 void optim_launch(const OptimArgs& a, cudaStream_t s);
 
+// Data-parallel optimiser step over NVLink peer memory (optim.cu): reduce-scatter of the gradient arena, Adam / Polyak on the
+// owned shard and all-gather of the updated parameters in ONE kernel.  Rank r owns the r-th 1/N of the arena: every rank pushes
+// that slice of its gradients into r's receive arena (peer stores), r sums the N copies in fixed rank order (replicas stay
+// bit-identical), updates its slice of P / m / v (the moments exist only on the owner) and stores the new parameters -- and the
+// Polyak-averaged target slice -- into every rank's arena, again through peer stores.  Ranks meet twice through epoch flags in each other's memory (release /
+// acquire at system scope): "my gradients are final" before the loads, "my slice is written everywhere" before the kernel ends.
+constexpr int DP_MAX_RANKS = 8;
+struct DpArgs {
+  OptimArgs o;                         // local arenas, step sizes, metrics
+  int rank, nranks;
+  float* R_peer[DP_MAX_RANKS];         // receive arena of every rank: [src rank][slice] floats (slices pushed by their producers)
+  float* P_peer[DP_MAX_RANKS];         // parameter arena of every rank
+  int* x_peer[DP_MAX_RANKS];           // exchange block of every rank: int flags[2][8] (G ready, slice written), float part[8][2], loss[8][16]
+  const long long* counters;           // counters[3] = optimiser step = flag epoch
+  int* sync;                           // local: [0], [1] CTA arrival counters, [2..3] squared-norm accumulators (as float), [8..] bring-up stamps
+};
+void dp_optim_launch(const DpArgs& a, int ctas, cudaStream_t s);
+
 // weights -> BF16 hi/lo planes, original [R,N] layout and transposed [N,R] (optim.cu)
 struct PlaneJob {
   const float* src;            // [R, N] row-major fp32 (TF layout: HWIO filters flattened, dense [in,out])

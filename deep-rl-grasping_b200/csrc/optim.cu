@@ -199,6 +199,152 @@ void planes_launch(const PlaneJob* dev_jobs, int njobs, int total_tiles, cudaStr
 
 void prep_launch(const PrepArgs& a, cudaStream_t s) { prep_kernel<<<1, 256, 0, s>>>(a); }
 
+namespace {
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ void st_release_sys(int* p, int v) { asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+// All cross-GPU traffic is STORES (posted, ~3x the throughput of peer loads measured here: tools/dp_trace.py): every rank first pushes
+// the slices of its gradient buffer it does not own into the owners' receive arenas, the owners then read only local memory.
+// One CTA per SM (all resident: phases A and B are separated by a grid-wide arrival counter and by flags from the other GPUs).
+template <int NR>
+__global__ void __launch_bounds__(1024) dp_optim_kernel(DpArgs d) {
+  const OptimArgs& a = d.o;
+  const int N = d.nranks, me = d.rank, tid = threadIdx.x;
+  const int epoch = (int)d.counters[3];
+  // exchange block of a rank (ints): [0,8) "gradients of rank q have landed here", [8,16) "slice of rank q written here", [16,32)
+  // squared-norm partials part[q][2], [32,160) loss scalars loss[q][16]
+  int* xl = d.x_peer[me];
+  long long* stamp = reinterpret_cast<long long*>(d.sync + 8);      // bring-up: %globaltimer at the phase boundaries (tools/dp_trace.py)
+  if (blockIdx.x == 0 && tid == 0) stamp[0] = gtime();
+  const int n_train4 = (a.n_pi + a.n_values + a.n_ent) >> 2;
+  const int per4 = (n_train4 + N - 1) / N, lo4 = me * per4, hi4 = min(n_train4, lo4 + per4);
+  const int nthr = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + tid;
+  __shared__ int s_last;
+  // ---- A. push: slice q of my gradients -> receive arena of rank q, row `me`; my loss scalars -> everybody's exchange block
+  for (int q = 0; q < N; ++q) {
+    if (q == me) continue;
+    const int qlo = q * per4, qhi = min(n_train4, qlo + per4);
+    float4* dst = reinterpret_cast<float4*>(d.R_peer[q]) + (size_t)me * per4;
+    const float4* src = reinterpret_cast<const float4*>(a.G);
+    for (int i4 = qlo + gtid; i4 < qhi; i4 += nthr) dst[i4 - qlo] = __ldcs(src + i4);
+  }
+  if (blockIdx.x == 0 && tid < N * MET_GN_PI) {
+    const int q = tid / MET_GN_PI, k = tid - q * MET_GN_PI;
+    reinterpret_cast<float*>(d.x_peer[q] + 32)[me * 16 + k] = a.metrics[k];
+  }
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence_system();                        // this CTA's peer stores before its arrival
+    s_last = atomicAdd(d.sync, 1) == (int)gridDim.x - 1;
+  }
+  __syncthreads();
+  if (s_last && tid < N) { __threadfence_system(); st_release_sys(d.x_peer[tid] + me, epoch); }   // everything of mine has landed
+  if (tid < N) { while (ld_acquire_sys(xl + tid) < epoch) __nanosleep(100); }
+  __syncthreads();
+  if (blockIdx.x == 0 && tid == 0) stamp[1] = gtime();
+  if (blockIdx.x == 0 && tid < MET_GN_PI) {        // loss scalars: sums in fixed rank order, identical on every rank
+    const float* loss = reinterpret_cast<const float*>(xl + 32);
+    float v = 0.f;
+    for (int q = 0; q < N; ++q) v += __ldcg(loss + q * 16 + tid);
+    a.metrics[tid] = v;
+  }
+  // ---- B. my slice: sum the N copies (mine from the gradient buffer, the others from my receive arena; fixed rank order: every
+  //         replica of a parameter sees the same sum), Adam / Polyak, push the new values into every replica
+  const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
+  const float lrt[3] = {(float)a.step_consts[0], (float)a.step_consts[1], (float)a.step_consts[2]};
+  float ss[2] = {0.f, 0.f};
+  const float4* R = reinterpret_cast<const float4*>(d.R_peer[me]);
+  for (int i4 = lo4 + gtid; i4 < hi4; i4 += nthr) {
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int q = 0; q < NR; ++q)
+      if (q < N) {
+        const float4 v = q == me ? reinterpret_cast<const float4*>(a.G)[i4] : __ldcg(R + (size_t)q * per4 + (i4 - lo4));
+        g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
+      }
+    const int i = i4 << 2;
+    const int grp = i < a.n_pi ? 0 : (i < a.n_pi + a.n_values ? 1 : 2);
+    g.x *= a.grad_scale; g.y *= a.grad_scale; g.z *= a.grad_scale; g.w *= a.grad_scale;
+    if (grp < 2) ss[grp] += g.x * g.x + g.y * g.y + g.z * g.z + g.w * g.w;
+    float4 m = reinterpret_cast<float4*>(a.Mo)[i4], v = reinterpret_cast<float4*>(a.Vo)[i4];
+    float4 p = reinterpret_cast<float4*>(a.P)[i4];
+    const float lr = lrt[grp];
+#define B2G_ADAM(c)                                   \
+  m.c = b1 * m.c + (1.f - b1) * g.c;                  \
+  v.c = b2 * v.c + (1.f - b2) * (g.c * g.c);          \
+  p.c = p.c - lr * m.c / (sqrtf(v.c) + eps);
+    B2G_ADAM(x) B2G_ADAM(y) B2G_ADAM(z) B2G_ADAM(w)
+#undef B2G_ADAM
+    reinterpret_cast<float4*>(a.Mo)[i4] = m;
+    reinterpret_cast<float4*>(a.Vo)[i4] = v;
+    for (int q = 0; q < N; ++q) reinterpret_cast<float4*>(d.P_peer[q])[i4] = p;
+    const int j = i - a.n_pi;
+    if (grp == 1 && j < a.n_target) {
+      const int t4 = n_train4 + (j >> 2);         // target block sits behind the trainable arena
+      float4 tg = reinterpret_cast<float4*>(a.P)[t4];
+      const float tau = a.tau, om = 1.f - a.tau;
+      tg.x = om * tg.x + tau * p.x; tg.y = om * tg.y + tau * p.y;
+      tg.z = om * tg.z + tau * p.z; tg.w = om * tg.w + tau * p.w;
+      for (int q = 0; q < N; ++q) reinterpret_cast<float4*>(d.P_peer[q])[t4] = tg;
+    }
+  }
+  if (blockIdx.x == 0 && tid == 0) stamp[2] = gtime();
+  // ---- C. squared gradient norms of my slice, then: the last CTA publishes them and "my slice is written everywhere"
+  __shared__ float red[2][32];
+  for (int k = 0; k < 2; ++k) {
+    float v = ss[k];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((tid & 31) == 0) red[k][tid >> 5] = v;
+  }
+  __syncthreads();
+  float* acc = reinterpret_cast<float*>(d.sync + 2);
+  if (tid < 2) {
+    float v = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += red[tid][w];
+    atomicAdd(acc + tid, v);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence_system();
+    s_last = atomicAdd(d.sync + 1, 1) == (int)gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  if (tid == 0) stamp[3] = gtime();
+  __threadfence();
+  if (tid < N) {
+    float* part = reinterpret_cast<float*>(d.x_peer[tid] + 16) + 2 * me;
+    part[0] = __ldcg(acc); part[1] = __ldcg(acc + 1);
+    __threadfence_system();
+    st_release_sys(d.x_peer[tid] + 8 + me, epoch);
+  }
+  if (tid < N) { while (ld_acquire_sys(xl + 8 + tid) < epoch) __nanosleep(100); }
+  __syncthreads();
+  if (tid < 2) {                                   // fixed order again: identical metrics on every rank
+    const float* part = reinterpret_cast<const float*>(xl + 16);
+    float v = 0.f;
+    for (int q = 0; q < N; ++q) v += __ldcg(part + 2 * q + tid);
+    a.metrics[MET_GN_PI + tid] += v;
+  }
+  if (tid == 0) {
+    stamp[4] = gtime();
+    d.sync[0] = 0; d.sync[1] = 0; acc[0] = 0.f; acc[1] = 0.f;
+    if (a.bump_counter) *a.bump_counter += 1;
+  }
+}
+}  // namespace
+
+void dp_optim_launch(const DpArgs& a, int ctas, cudaStream_t s) {
+  if (a.nranks <= 2) dp_optim_kernel<2><<<ctas, 1024, 0, s>>>(a);
+  else if (a.nranks <= 4) dp_optim_kernel<4><<<ctas, 1024, 0, s>>>(a);
+  else dp_optim_kernel<8><<<ctas, 1024, 0, s>>>(a);
+}
+
 void optim_launch(const OptimArgs& a, cudaStream_t s) {
   int n4 = (a.n_pi + a.n_values + a.n_ent) >> 2;
   if (a.r_hi[0] > 0 || a.r_hi[1] > 0) n4 = ((a.r_hi[0] - a.r_lo[0]) + (a.r_hi[1] - a.r_lo[1])) >> 2;

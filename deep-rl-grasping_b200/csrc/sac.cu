@@ -98,6 +98,10 @@ int nccl_comm_init(void** comm, int nranks, const void* id128, int rank, const c
   if (int rc = load_nccl(lib)) return rc;
   UId id;
   memcpy(id.b, id128, 128);
+  // (B2G_AR_SMS also caps NCCL's CTAs: a collective that overlaps the persistent GEMM grids -- one CTA per SM, 226 KB of shared
+  //  memory each, nothing fits beside them -- displaces every GEMM CTA beyond the reserve.  Measured at N = 2: capping at 8 CTAs
+  //  halves the all-reduce bandwidth and costs more than it saves, so the cap is opt-in.)
+  if (!getenv("NCCL_MAX_CTAS")) { if (const char* e = getenv("B2G_AR_SMS")) setenv("NCCL_MAX_CTAS", e, 0); }
   const int nrc = g_nccl.CommInitRank(comm, nranks, id, rank);
   if (nrc != 0) return fail(B2G_ENCCL, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "?"));
   return 0;
@@ -921,7 +925,7 @@ int issue_step(b2g_sac* h, bool sampled, bool apply, bool want_per_sample, Prof*
     oa.metrics = h->metrics; oa.apply = apply ? 1 : 0;
     return oa;
   };
-  const bool overlap = h->overlap_ar && h->cnn && h->cfg.nranks > 1 && last_fc1 >= 0 && last_fc1 + 1 < (int)h->bwd_groups.size();
+  const bool overlap = h->overlap_ar && h->cnn && h->cfg.nranks > 1 && !(h->dp_p2p && apply) && last_fc1 >= 0 && last_fc1 + 1 < (int)h->bwd_groups.size();
   const int64_t pi_fc1 = h->tensors[h->tindex.at("model/pi/" + std::string(h->cnn ? "cnn_fc1/w" : "fc0/kernel"))].off;
   const int64_t v_fc1 = h->tensors[h->tindex.at("model/values_fn/" + std::string(h->cnn ? "cnn_fc1/w" : "vf/fc0/kernel"))].off;
   const bool early_opt = !h->v2.bwd && fork && h->early_opt && h->cfg.nranks == 1 && h->cnn && last_fc1 >= 0 && last_fc1 + 1 < (int)h->bwd_groups.size() &&
@@ -930,13 +934,14 @@ int issue_step(b2g_sac* h, bool sampled, bool apply, bool want_per_sample, Prof*
     if (rc != 0) return fail(B2G_ENCCL, std::string("nccl: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
     return 0;
   };
+  bool dp_early_opt = false;
   if (h->v2.bwd) {
     // backward chain on engine v2; the small head wgrads (fc0 / fc1 kernels and biases: fp32 operands, register-staged) stay
     // on the v1 engine and, like the bias column sums, run on the leaf branch.
     // N > 1: the gradients of [cnn_fc1 .. end] of both trainable blocks (+ log_ent_coef + the loss scalars: 84 % of the
     // bytes) are final after fc1_bwd, so their all-reduce runs on a side stream / second communicator underneath the conv
     // backward (the GEMM grids leave ar_sms SMs to it); only the conv ranges (0.6 MB) are reduced on the critical chain.
-    const bool ov = h->overlap_ar && h->cfg.nranks > 1;
+    const bool ov = h->overlap_ar && h->cfg.nranks > 1 && !(h->dp_p2p && apply);
     h->v2.sm_reserve = 0;
     cudaStream_t lx = fork ? ax : s;
     for (auto& g : h->bwd_groups) {
@@ -971,6 +976,15 @@ int issue_step(b2g_sac* h, bool sampled, bool apply, bool want_per_sample, Prof*
       if (int rc = nccl_ck(g_nccl.AllReduce(h->G + v_fc1, h->G + v_fc1, (size_t)(h->n_train + MET_COUNT - v_fc1), 7, 0, h->nccl_comm2, h->side))) return rc;
       if (int rc = nccl_ck(g_nccl.GroupEnd())) return rc;
       ++n;
+      if ((pi_fc1 & 3) == 0 && (v_fc1 & 3) == 0 && (h->n_pi & 3) == 0) {
+        // the reduced ranges get their Adam / Polyak pass right behind the collective, still underneath the conv backward; the
+        // closing optimiser launch only sweeps the conv kernels (after the late, 0.6 MB all-reduce)
+        OptimArgs oe = make_optim();
+        oe.r_lo[0] = (int)pi_fc1; oe.r_hi[0] = (int)h->n_pi;
+        oe.r_lo[1] = (int)v_fc1; oe.r_hi[1] = (int)(h->n_pi + h->n_values + h->n_ent);
+        optim_launch(oe, h->side); ++n;
+        dp_early_opt = true;
+      }
       CK(cudaEventRecord(h->ev_join, h->side));
       h->v2.sm_reserve = h->ar_sms;
       return 0;
@@ -1061,7 +1075,7 @@ int issue_step(b2g_sac* h, bool sampled, bool apply, bool want_per_sample, Prof*
   }
   if (planes_bias && !fork && !h->v2.bwd) { colsum_launch(h->d_colsum, h->n_colsum, h->colsum_ctas, s); ++n; mark("bias_grads"); }
   if (fork) { CK(cudaEventRecord(h->ev_aux[5], ax)); CK(cudaStreamWaitEvent(s, h->ev_aux[5], 0)); }
-  if (h->cfg.nranks > 1) {
+  if (h->cfg.nranks > 1 && !(h->dp_p2p && apply)) {
     if (overlap) {
       // late all-reduce: the conv gradients of both blocks (0.29 MB each), then join the early one
       if (int rc = nccl_ck(g_nccl.GroupStart())) return rc;
@@ -1081,11 +1095,21 @@ int issue_step(b2g_sac* h, bool sampled, bool apply, bool want_per_sample, Prof*
   }
   OptimArgs oa = make_optim();
   oa.bump_counter = (fork && sampled) ? h->counters + 4 : nullptr;
-  if (early_opt) {
+  if (early_opt || dp_early_opt) {
     oa.r_lo[0] = 0; oa.r_hi[0] = (int)pi_fc1;
     oa.r_lo[1] = (int)h->n_pi; oa.r_hi[1] = (int)v_fc1;
   }
-  optim_launch(oa, s); ++n; mark("adam_polyak");
+  if (h->dp_p2p && apply) {
+    // the optimiser launch is the collective (common.cuh: DpArgs); it also sums the loss scalars across the ranks
+    DpArgs da{};
+    da.o = oa; da.rank = h->cfg.rank; da.nranks = h->cfg.nranks;
+    for (int q = 0; q < h->cfg.nranks; ++q) { da.R_peer[q] = h->dp_G[q]; da.P_peer[q] = h->dp_P[q]; da.x_peer[q] = h->dp_X[q]; }
+    da.counters = h->counters; da.sync = h->dp_sync;
+    dp_optim_launch(da, h->num_sms, s); ++n;
+    mark("adam_polyak_dp");
+  } else {     // (a gradient-only step of a connected learner takes the NCCL path above)
+    optim_launch(oa, s); ++n; mark("adam_polyak");
+  }
   if (h->use_planes && apply && !h->v2.bwd) {
     // with fork: refreshed on the aux branch at the head of the next step (the API entry points mark them stale)
     if (!fork) { planes_launch(h->d_jobs, h->n_jobs, h->job_tiles, s); ++n; mark("weight_planes"); }
@@ -1176,11 +1200,60 @@ int b2g_nccl_unique_id(void* out128, const char* nccl_lib) {
   return 0;
 }
 
+int b2g_sac_dp_export(b2g_sac* h, void* out192) {
+  if (!h || !out192) return fail(B2G_EINVAL, "b2g_sac_dp_export: null argument");
+  cudaSetDevice(h->cfg.device);
+  if (!h->dp_x) {
+    if (int rc = dalloc(h, &h->dp_x, 256)) return rc;
+    if (int rc = dalloc(h, &h->dp_recv, h->n_train + 64 * DP_MAX_RANKS)) return rc;      // [src rank][my slice], slices <= ceil(n/N) + pad
+    if (int rc = dalloc(h, &h->dp_sync, 64)) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  cudaIpcMemHandle_t hd[3];
+  CK(cudaIpcGetMemHandle(&hd[0], h->P));
+  CK(cudaIpcGetMemHandle(&hd[1], h->dp_recv));
+  CK(cudaIpcGetMemHandle(&hd[2], h->dp_x));
+  static_assert(sizeof(hd) == B2G_DP_EXPORT_BYTES, "export blob size");
+  memcpy(out192, hd, sizeof(hd));
+  return 0;
+}
+
+int b2g_debug_dp_stamps(b2g_sac* h, long long* out5) {     /* bring-up: phase timestamps of the last peer-memory optimiser launch */
+  if (!h || !h->dp_sync) return fail(B2G_EINVAL, "b2g_debug_dp_stamps: not connected");
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaMemcpy(out5, h->dp_sync + 8, 5 * sizeof(long long), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int b2g_sac_dp_connect(b2g_sac* h, const void* all_exports, int nranks) {
+  if (!h || !all_exports) return fail(B2G_EINVAL, "b2g_sac_dp_connect: null argument");
+  if (nranks != h->cfg.nranks || nranks < 2 || nranks > DP_MAX_RANKS) return fail(B2G_EINVAL, "b2g_sac_dp_connect: nranks must equal the learner's (2..8)");
+  if (!h->dp_x) return fail(B2G_EINVAL, "b2g_sac_dp_connect: call b2g_sac_dp_export first");
+  if (((h->n_pi | h->n_values | h->n_ent | h->n_target) & 3) != 0) return fail(B2G_EINVAL, "b2g_sac_dp_connect: arena segments are not float4 aligned");
+  cudaSetDevice(h->cfg.device);
+  CK(cudaStreamSynchronize(h->stream));
+  for (int q = 0; q < nranks; ++q) {
+    if (q == h->cfg.rank) { h->dp_P[q] = h->P; h->dp_G[q] = h->dp_recv; h->dp_X[q] = h->dp_x; continue; }
+    cudaIpcMemHandle_t hd[3];
+    memcpy(hd, (const char*)all_exports + (size_t)q * B2G_DP_EXPORT_BYTES, sizeof(hd));
+    void* p[3] = {nullptr, nullptr, nullptr};
+    for (int k = 0; k < 3; ++k) {
+      CK(cudaIpcOpenMemHandle(&p[k], hd[k], cudaIpcMemLazyEnablePeerAccess));
+      h->dp_opened.push_back(p[k]);
+    }
+    h->dp_P[q] = (float*)p[0]; h->dp_G[q] = (float*)p[1]; h->dp_X[q] = (int*)p[2];
+  }
+  h->dp_p2p = true;
+  if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }     // the step changes shape
+  return 0;
+}
+
 int b2g_sac_destroy(b2g_sac* h) {
   if (!h) return 0;
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+  for (void* q : h->dp_opened) cudaIpcCloseMemHandle(q);
   if (h->nccl_comm2 && g_nccl.CommDestroy) g_nccl.CommDestroy(h->nccl_comm2);
   if (h->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->nccl_comm);
   if (h->side) cudaStreamDestroy(h->side);

@@ -154,6 +154,14 @@ struct b2g_sac {
   bool use_graph = true;
   void* nccl_comm = nullptr;
   void* nccl_comm2 = nullptr;          // second communicator: early all-reduce on the side stream
+  // peer-memory data parallelism (b2g_sac_dp_export / _connect): every rank maps the others' parameter arena, gradient buffer and
+  // exchange block through CUDA IPC; the optimiser kernel then IS the collective (optim.cu: dp_optim_kernel)
+  bool dp_p2p = false;
+  int* dp_x = nullptr;                 // exchange block: int flags[2][8], float part[8][2]
+  int* dp_sync = nullptr;              // local CTA counter + norm accumulators
+  float* dp_recv = nullptr;            // receive arena: [src rank][my slice] gradient copies pushed by the other ranks
+  float* dp_P[8]{}; float* dp_G[8]{}; int* dp_X[8]{};     // every rank's parameter arena, receive arena, exchange block (own = local)
+  std::vector<void*> dp_opened;        // cudaIpcOpenMemHandle results
   cudaStream_t side = nullptr;
   cudaStream_t aux = nullptr;              // leaf work off the critical chain (zeroing, weight planes, leaf wgrads, bias sums)
   cudaEvent_t ev_aux[7]{};

@@ -74,6 +74,31 @@ class Learner:
         except Exception:
             pass
 
+    # ---- peer-memory data parallelism (include/b200grasp.h: b2g_sac_dp_export / b2g_sac_dp_connect)
+    DP_EXPORT_BYTES = 192
+
+    def dp_export(self) -> bytes:
+        buf = C.create_string_buffer(self.DP_EXPORT_BYTES)
+        _lib.check(self.lib.b2g_sac_dp_export(self.h, C.cast(buf, C.c_void_p)))
+        return buf.raw
+
+    def dp_connect(self, exports: "list[bytes]"):
+        """exports: the dp_export() blob of every rank, in rank order.  From here on the optimiser launch of each step reduces
+        the gradients, updates this rank's slice and writes the new parameters into every replica through NVLink peer memory."""
+        blob = b"".join(exports)
+        if len(blob) != self.DP_EXPORT_BYTES * len(exports):
+            raise ValueError("every export blob must be DP_EXPORT_BYTES long")
+        buf = C.create_string_buffer(blob, len(blob))
+        _lib.check(self.lib.b2g_sac_dp_connect(self.h, C.cast(buf, C.c_void_p), len(exports)))
+
+    def dp_connect_torch(self):
+        """dp_export + all_gather over the initialised torch.distributed process group + dp_connect."""
+        import torch.distributed as dist
+        blobs = [None] * dist.get_world_size()
+        dist.all_gather_object(blobs, self.dp_export())
+        self.dp_connect(blobs)
+        dist.barrier()
+
     @staticmethod
     def nccl_unique_id() -> bytes:
         lib = _lib.load()

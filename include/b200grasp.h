@@ -75,6 +75,17 @@ int b2g_nccl_unique_id(void* out128, const char* nccl_lib);
 
 int b2g_sac_create(const b2g_sac_cfg* cfg, b2g_sac** out);
 int b2g_sac_destroy(b2g_sac* h);
+/* Peer-memory data parallelism (nranks > 1, one process per GPU of one NVLink node).  Every rank exports B2G_DP_EXPORT_BYTES
+ * (CUDA IPC handles of its parameter arena, gradient receive arena and exchange block), the caller gathers the nranks blobs in rank
+ * order (any out-of-band channel: the Python layer uses torch.distributed) and hands the concatenation to every rank.
+ * From then on the optimiser launch of each gradient step is the collective: reduce-scatter of the gradients through peer
+ * stores, Adam / Polyak on the owned slice, all-gather of the new parameters through peer stores -- no NCCL call on the path.
+ * Replaces the all-reduce the reference's data-parallel wrapper would issue (reference: none -- SB 2.10 SAC is single-process;
+ * SURVEY.md section 8e defines the N > 1 semantics this implements). */
+#define B2G_DP_EXPORT_BYTES 192
+int b2g_sac_dp_export(b2g_sac* h, void* out192);
+int b2g_sac_dp_connect(b2g_sac* h, const void* all_exports /* nranks x B2G_DP_EXPORT_BYTES, rank order */, int nranks);
+int b2g_debug_dp_stamps(b2g_sac* h, long long* out5);   /* bring-up: %globaltimer at the phase boundaries of the last launch */
 int b2g_sync(b2g_sac* h);
 
 /* ---- parameters: SB-zip variable names without the ":0" suffix (get_parameters / load_parameters,

@@ -33,14 +33,26 @@ def main():
                           nccl_id=ids[0], precision=prec)
     L.set_norm_stats(vn["obs_mean"], vn["obs_var"], float(vn["ret_var"]), float(vn["clip_obs"]), float(vn["clip_reward"]),
                      float(vn["epsilon"]))
+    dp = os.environ.get("DP", "nccl")
+    if dp == "p2p":
+        L.dp_connect_torch()       # the optimiser launch becomes the collective (peer-memory reduce-scatter + Adam + all-gather)
     L.load_parameters(params)
     sl = slice(rank * B, (rank + 1) * B)
     out = L.step_explicit(raw["obs"][sl], raw["act"][sl], raw["rew"][sl], raw["next_obs"][sl], raw["done"][sl], eps[sl], lr=3e-4)
     ref, grads, newp, _ = R.sac_step(params, R.OptState.zeros(params), norm, eps, 3e-4, cfg, torch.float64)
     errs = {k: abs(out[k] - float(ref[k])) / abs(float(ref[k])) for k in
             ("policy_loss", "qf1_loss", "qf2_loss", "value_loss", "grad_norm_pi", "grad_norm_values")}
-    g = L.get_gradients()
-    gerr = max(rel_err(g[n], grads[n]) for n in grads)
+    if dp == "p2p":
+        # the gradients are never materialised as a whole: compare the updated parameters (what the step produces) instead,
+        # as the UPDATE each one received -- lr * m / (sqrt(v) + eps) of the first Adam step is +-lr wherever the gradient is not ~0
+        newd = L.get_parameters()
+        upd_ref = np.concatenate([(np.asarray(newp[n], np.float64) - np.asarray(params[n], np.float64)).reshape(-1) for n in grads])
+        upd_dev = np.concatenate([(newd[n].astype(np.float64) - np.asarray(params[n], np.float64)).reshape(-1) for n in grads])
+        big = np.concatenate([np.abs(np.asarray(grads[n], np.float64)).reshape(-1) for n in grads]) > 1e-7     # Adam's first step is sign-like
+        gerr = float(np.linalg.norm((upd_dev - upd_ref)[big]) / np.linalg.norm(upd_ref[big]))
+    else:
+        g = L.get_gradients()
+        gerr = max(rel_err(g[n], grads[n]) for n in grads)
     # replicas must stay bit-identical
     mine = np.concatenate([a.reshape(-1) for a in L.get_parameters().values()])
     allp = [None] * world
