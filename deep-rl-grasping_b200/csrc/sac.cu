@@ -18,6 +18,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <map>
 #include <tuple>
 #include <string>
@@ -1715,17 +1716,58 @@ int b2g_sac_step_host_pipelined(b2g_sac* h, const float* obs, const float* act, 
   const size_t B = h->B, E = h->E, A = h->A;
   const long long k = h->pipe_k++;
   const int j = (int)(k & 1);
+  // bring-up: B2G_PIPE_TRACE=1 prints, per call, when the copies and the kernels of the step two calls back ran on the device
+  static const bool ptrace = getenv("B2G_PIPE_TRACE") != nullptr;
+  static cudaEvent_t te[2][4], t_origin;
+  static bool te_init = false;
+  if (ptrace && !te_init) {
+    for (auto& r : te) for (auto& e : r) cudaEventCreate(&e);
+    cudaEventCreate(&t_origin); cudaEventRecord(t_origin, h->stream);
+    te_init = true;
+  }
+  if (ptrace && k >= 2) {
+    float c0, c1, k0, k1;
+    cudaEventSynchronize(te[j][3]);
+    cudaEventElapsedTime(&c0, t_origin, te[j][0]); cudaEventElapsedTime(&c1, t_origin, te[j][1]);
+    cudaEventElapsedTime(&k0, t_origin, te[j][2]); cudaEventElapsedTime(&k1, t_origin, te[j][3]);
+    fprintf(stderr, "pipe step %lld: copies %.3f .. %.3f ms (%.3f), kernels %.3f .. %.3f ms (%.3f)\n", k - 2, c0, c1, c1 - c0, k0, k1, k1 - k0);
+  }
   // (1) copy stream: this step's observations into staging slot j (free once the gather of step k-2 has run)
   if (k >= 2) CK(cudaStreamWaitEvent(h->cstream, h->ev_consumed[j], 0));
+  // Copy k+1 may or may not overlap the kernels of step k.  Measured on B200 boxes (tools/e2e_diag.py): on some, the 16.8 MB
+  // host-to-device copy and the step run side by side at full speed (2300 steps/s against 1140 back to back); on others they
+  // starve each other -- the copy takes 0.7 - 1.0 ms instead of 0.31, the step 0.45 - 0.70 ms instead of 0.26 -- and back to back
+  // wins (1750 against 1020).  So the first calls time both schedules (eight calls each, host clock, pipeline full) and the
+  // faster one stays.  B2G_PIPE_MODE=overlap|serial pins it.  Either way the HOST stays pipelined: a call returns while its
+  // copies and kernels are still queued.
+  {
+    static const char* pm = getenv("B2G_PIPE_MODE");
+    const double now = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    if (pm && pm[0] == 'o') h->pipe_serial = false;
+    else if (pm && pm[0] == 's') h->pipe_serial = true;
+    else if (h->pipe_tune < 22) {
+      const int c = h->pipe_tune++;
+      if (c == 4 || c == 14) h->pipe_t0 = now;
+      if (c == 12) { h->pipe_period[0] = (now - h->pipe_t0) / 8; h->pipe_serial = true; }
+      if (c == 21) {
+        h->pipe_period[1] = (now - h->pipe_t0) / 7; h->pipe_serial = h->pipe_period[1] < h->pipe_period[0];
+        if (getenv("B2G_PIPE_TRACE")) fprintf(stderr, "pipe schedule: overlapped %.3f ms/step, back to back %.3f ms/step -> %s\n", h->pipe_period[0] * 1e3, h->pipe_period[1] * 1e3, h->pipe_serial ? "back to back" : "overlapped");
+      }
+    }
+  }
+  if (h->pipe_serial && k >= 1) CK(cudaStreamWaitEvent(h->cstream, h->ev_met[j ^ 1], 0));
+  if (ptrace) cudaEventRecord(te[j][0], h->cstream);
   CK(cudaMemcpyAsync(h->ps_obs[j], obs, B * E * sizeof(float), cudaMemcpyHostToDevice, h->cstream));
   CK(cudaMemcpyAsync(h->ps_next[j], next_obs, B * E * sizeof(float), cudaMemcpyHostToDevice, h->cstream));
   CK(cudaEventRecord(h->ev_h2d[j], h->cstream));
+  if (ptrace) cudaEventRecord(te[j][1], h->cstream);
   // (2) compute stream: small tensors in order, then the step on slot j
   CK(cudaMemcpyAsync(h->s_act, act, B * A * sizeof(float), cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(h->s_rew, rew, B * sizeof(float), cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(h->s_done, done, B * sizeof(float), cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(h->eps, eps, B * A * sizeof(float), cudaMemcpyHostToDevice, h->stream));
   CK(cudaStreamWaitEvent(h->stream, h->ev_h2d[j], 0));
+  if (ptrace) cudaEventRecord(te[j][2], h->stream);
   float* keep_obs = h->s_obs; float* keep_next = h->s_next;
   h->s_obs = h->ps_obs[j]; h->s_next = h->ps_next[j];
   h->record_after_gather = h->ev_consumed[j];
@@ -1734,6 +1776,7 @@ int b2g_sac_step_host_pipelined(b2g_sac* h, const float* obs, const float* act, 
   h->record_after_gather = nullptr;
   h->s_obs = keep_obs; h->s_next = keep_next;
   if (rc) return rc;
+  if (ptrace) cudaEventRecord(te[j][3], h->stream);
   // (3) this step's losses -> pinned slot j (read back by the NEXT call, or by b2g_sac_pipeline_flush)
   CK(cudaMemcpyAsync(h->pm_met[j], h->metrics, MET_COUNT * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaMemcpyAsync(h->pm_met[j] + MET_COUNT, h->p("model/log_ent_coef"), sizeof(float), cudaMemcpyDeviceToHost, h->stream));

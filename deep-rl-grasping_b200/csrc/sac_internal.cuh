@@ -156,6 +156,8 @@ struct b2g_sac {
   void* nccl_comm2 = nullptr;          // second communicator: early all-reduce on the side stream
   // peer-memory data parallelism (b2g_sac_dp_export / _connect): every rank maps the others' parameter arena, gradient buffer and
   // exchange block through CUDA IPC; the optimiser kernel then IS the collective (optim.cu: dp_optim_kernel)
+  // host-pipelined steps: copy / kernel schedule picked by timing both (b2g_sac_step_host_pipelined)
+  bool pipe_serial = false; int pipe_tune = 0; double pipe_t0 = 0, pipe_period[2] = {0, 0};
   bool dp_p2p = false;
   int* dp_x = nullptr;                 // exchange block: int flags[2][8], float part[8][2]
   int* dp_sync = nullptr;              // local CTA counter + norm accumulators
