@@ -3,7 +3,7 @@
 set -e
 cd "$(dirname "$0")/deep-rl-grasping_b200"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
-FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall"
+FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall -Xcompiler -fopenmp"
 mkdir -p build
 objs=""
 for f in csrc/*.cu; do
@@ -18,5 +18,5 @@ for f in csrc/*.cu; do
   objs="$objs $o"
 done
 wait
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o libb200grasp.so $objs -ldl
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o libb200grasp.so $objs -ldl -lgomp
 echo "built $(pwd)/libb200grasp.so"

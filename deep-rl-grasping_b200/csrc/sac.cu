@@ -853,7 +853,9 @@ int issue_step(b2g_sac* h, bool sampled, bool apply, bool want_per_sample, Prof*
   if (h->v2.on) {
     if (!fork) { if (int rc = v2_planes(h, s)) return rc; ++n; mark("weight_planes_v2"); }
     if (h->compact) {
-      if (!sampled) {       // host-supplied batch (full layout): compact it like replay_add does
+      if (!sampled && h->staged_compact) {     // host-pipelined batch: compacted on the host, before the copy
+        ga.obs = h->s_obs; ga.next_obs = h->s_next;
+      } else if (!sampled) {       // host-supplied batch (full layout): compact it like replay_add does
         if (int rc = v2_compact_rows(h, h->s_obs, h->cs_obs, 0, h->B, h->B, s)) return rc;
         if (int rc = v2_compact_rows(h, h->s_next, h->cs_next, 0, h->B, h->B, s)) return rc;
         n += 2;
@@ -1246,6 +1248,7 @@ int b2g_sac_dp_connect(b2g_sac* h, const void* all_exports, int nranks) {
   }
   h->dp_p2p = true;
   if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }     // the step changes shape
+  for (auto& g : h->pipe_graph) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
   return 0;
 }
 
@@ -1254,6 +1257,7 @@ int b2g_sac_destroy(b2g_sac* h) {
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+  for (auto& g : h->pipe_graph) if (g) cudaGraphExecDestroy(g);
   for (void* q : h->dp_opened) cudaIpcCloseMemHandle(q);
   if (h->nccl_comm2 && g_nccl.CommDestroy) g_nccl.CommDestroy(h->nccl_comm2);
   if (h->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->nccl_comm);
@@ -1263,6 +1267,7 @@ int b2g_sac_destroy(b2g_sac* h) {
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   for (void* q : h->allocs) cudaFree(q);
+  for (int q = 0; q < 2; ++q) { if (h->hc_obs[q]) cudaFreeHost(h->hc_obs[q]); if (h->hc_next[q]) cudaFreeHost(h->hc_next[q]); }
   if (h->h_met) cudaFreeHost(h->h_met);
   if (h->h_cnt) cudaFreeHost(h->h_cnt);
   for (int k = 0; k < 2; ++k) { if (h->hp_stats[k]) cudaFreeHost(h->hp_stats[k]); if (h->ev_stats[k]) cudaEventDestroy(h->ev_stats[k]); }
@@ -1707,6 +1712,27 @@ int b2g_sac_step_explicit(b2g_sac* h, const float* obs, const float* act, const 
   return 0;
 }
 
+namespace {
+// full observations [n][HW][Cfull] -> compact replay rows [n][Ec] = image planes | value of the actuator plane at pixel [0,0] | pad
+// (same layout compact_kernel writes on the device).  The actuator plane is constant over the image and the network only ever reads
+// its first pixel (custom_obs_policy.py:20-23), so half of a depth observation never has to cross PCIe.
+void compact_host(const float* src, float* dst, int n, int HW, int Cfull, int Ec, int threads) {
+  const int Ci = Cfull - 1;
+#pragma omp parallel for num_threads(threads) schedule(static)
+  for (int b = 0; b < n; ++b) {
+    const float* s = src + (size_t)b * HW * Cfull;
+    float* d = dst + (size_t)b * Ec;
+    if (Ci == 1) {
+      for (int p = 0; p < HW; ++p) d[p] = s[2 * p];
+    } else {
+      for (int p = 0; p < HW; ++p)
+        for (int c = 0; c < Ci; ++c) d[p * Ci + c] = s[p * Cfull + c];
+    }
+    d[HW * Ci] = s[Ci]; d[HW * Ci + 1] = 0.f; d[HW * Ci + 2] = 0.f; d[HW * Ci + 3] = 0.f;
+  }
+}
+}  // namespace
+
 int b2g_sac_step_host_pipelined(b2g_sac* h, const float* obs, const float* act, const float* rew, const float* next_obs,
                                 const float* done, const float* eps, float lr, b2g_sac_metrics* prev_out, int* have_prev) {
   if (!h || !obs || !act || !rew || !next_obs || !done || !eps) return fail(B2G_EINVAL, "NULL argument");
@@ -1733,7 +1759,8 @@ int b2g_sac_step_host_pipelined(b2g_sac* h, const float* obs, const float* act, 
     fprintf(stderr, "pipe step %lld: copies %.3f .. %.3f ms (%.3f), kernels %.3f .. %.3f ms (%.3f)\n", k - 2, c0, c1, c1 - c0, k0, k1, k1 - k0);
   }
   // (1) copy stream: this step's observations into staging slot j (free once the gather of step k-2 has run)
-  if (k >= 2) CK(cudaStreamWaitEvent(h->cstream, h->ev_consumed[j], 0));
+  // staging slot j is free once step k-2 has run (its losses' event: the step replays as a graph, so no event from inside it)
+  if (k >= 2) CK(cudaStreamWaitEvent(h->cstream, h->use_graph ? h->ev_met[j] : h->ev_consumed[j], 0));
   // Copy k+1 may or may not overlap the kernels of step k.  Measured on B200 boxes (tools/e2e_diag.py): on some, the 16.8 MB
   // host-to-device copy and the step run side by side at full speed (2300 steps/s against 1140 back to back); on others they
   // starve each other -- the copy takes 0.7 - 1.0 ms instead of 0.31, the step 0.45 - 0.70 ms instead of 0.26 -- and back to back
@@ -1757,8 +1784,27 @@ int b2g_sac_step_host_pipelined(b2g_sac* h, const float* obs, const float* act, 
   }
   if (h->pipe_serial && k >= 1) CK(cudaStreamWaitEvent(h->cstream, h->ev_met[j ^ 1], 0));
   if (ptrace) cudaEventRecord(te[j][0], h->cstream);
-  CK(cudaMemcpyAsync(h->ps_obs[j], obs, B * E * sizeof(float), cudaMemcpyHostToDevice, h->cstream));
-  CK(cudaMemcpyAsync(h->ps_next[j], next_obs, B * E * sizeof(float), cudaMemcpyHostToDevice, h->cstream));
+  static const bool host_compact = !(getenv("B2G_HOST_COMPACT") && getenv("B2G_HOST_COMPACT")[0] == '0');
+  const bool hc = h->compact && host_compact;
+  if (hc) {
+    // compact on the host (a few threads, ~0.1 ms) into pinned staging, copy half the bytes; the caller's arrays need not be
+    // pinned and are free again when this call returns
+    if (!h->hc_obs[0]) {
+      for (int q = 0; q < 2; ++q) {
+        CK(cudaHostAlloc((void**)&h->hc_obs[q], B * h->Ec * sizeof(float), cudaHostAllocDefault));
+        CK(cudaHostAlloc((void**)&h->hc_next[q], B * h->Ec * sizeof(float), cudaHostAllocDefault));
+      }
+      if (const char* e = getenv("B2G_HOST_THREADS")) h->host_threads = std::max(1, atoi(e));
+    }
+    if (k >= 2) CK(cudaEventSynchronize(h->ev_h2d[j]));          // the copy out of this staging slot two calls ago
+    compact_host(obs, h->hc_obs[j], (int)B, h->Hi * h->Wi, h->Cimg + 1, h->Ec, h->host_threads);
+    CK(cudaMemcpyAsync(h->ps_obs[j], h->hc_obs[j], B * h->Ec * sizeof(float), cudaMemcpyHostToDevice, h->cstream));     // flies while next_obs is compacted
+    compact_host(next_obs, h->hc_next[j], (int)B, h->Hi * h->Wi, h->Cimg + 1, h->Ec, h->host_threads);
+    CK(cudaMemcpyAsync(h->ps_next[j], h->hc_next[j], B * h->Ec * sizeof(float), cudaMemcpyHostToDevice, h->cstream));
+  } else {
+    CK(cudaMemcpyAsync(h->ps_obs[j], obs, B * E * sizeof(float), cudaMemcpyHostToDevice, h->cstream));
+    CK(cudaMemcpyAsync(h->ps_next[j], next_obs, B * E * sizeof(float), cudaMemcpyHostToDevice, h->cstream));
+  }
   CK(cudaEventRecord(h->ev_h2d[j], h->cstream));
   if (ptrace) cudaEventRecord(te[j][1], h->cstream);
   // (2) compute stream: small tensors in order, then the step on slot j
@@ -1770,10 +1816,32 @@ int b2g_sac_step_host_pipelined(b2g_sac* h, const float* obs, const float* act, 
   if (ptrace) cudaEventRecord(te[j][2], h->stream);
   float* keep_obs = h->s_obs; float* keep_next = h->s_next;
   h->s_obs = h->ps_obs[j]; h->s_next = h->ps_next[j];
-  h->record_after_gather = h->ev_consumed[j];
-  int n = 0;
-  int rc = issue_step(h, false, true, false, nullptr, &n);
-  h->record_after_gather = nullptr;
+  h->staged_compact = hc;
+  int n = 0, rc = 0;
+  if (h->use_graph) {
+    // one graph per staging slot (the slot's buffers are baked into the nodes): the ~30 runtime calls of an eagerly issued step
+    // were the bottleneck of this path once the copy had shrunk
+    if (h->pipe_graph[j] && h->pipe_graph_compact[j] != hc) { cudaGraphExecDestroy(h->pipe_graph[j]); h->pipe_graph[j] = nullptr; }
+    if (!h->pipe_graph[j]) {
+      cudaGraph_t graph = nullptr;
+      CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+      rc = issue_step(h, false, true, false, nullptr, &n);
+      cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+      if (!rc && e != cudaSuccess) rc = fail(B2G_ECUDA, std::string("graph capture failed: ") + cudaGetErrorString(e));
+      if (!rc) {
+        e = cudaGraphInstantiate(&h->pipe_graph[j], graph, 0);
+        if (e != cudaSuccess) rc = fail(B2G_ECUDA, std::string("graph instantiate failed: ") + cudaGetErrorString(e));
+      }
+      if (graph) cudaGraphDestroy(graph);
+      h->pipe_graph_compact[j] = hc;
+    }
+    if (!rc && cudaGraphLaunch(h->pipe_graph[j], h->stream) != cudaSuccess) rc = fail(B2G_ECUDA, "graph launch failed");
+  } else {
+    h->record_after_gather = h->ev_consumed[j];
+    rc = issue_step(h, false, true, false, nullptr, &n);
+    h->record_after_gather = nullptr;
+  }
+  h->staged_compact = false;
   h->s_obs = keep_obs; h->s_next = keep_next;
   if (rc) return rc;
   if (ptrace) cudaEventRecord(te[j][3], h->stream);

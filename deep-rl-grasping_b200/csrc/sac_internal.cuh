@@ -137,6 +137,12 @@ struct b2g_sac {
   float *s_obs = nullptr, *s_next = nullptr, *s_act = nullptr, *s_rew = nullptr, *s_done = nullptr;  // staged explicit batch
   // pipelined host-batch path: the big obs / next_obs copies ping-pong on a copy stream
   float *ps_obs[2]{}, *ps_next[2]{};
+  // host-pipelined steps, compact transfer: the constant actuator plane never crosses PCIe (b2g_sac_step_host_pipelined)
+  float *hc_obs[2]{}, *hc_next[2]{};   // pinned host staging, compact rows [B][Ec]
+  bool staged_compact = false;         // the staged batch already is in compact rows
+  cudaGraphExec_t pipe_graph[2]{};     // the step on staging slot j, captured once (b2g_sac_step_host_pipelined)
+  bool pipe_graph_compact[2]{};
+  int host_threads = 16;
   cudaStream_t cstream = nullptr;
   cudaEvent_t ev_h2d[2]{}, ev_consumed[2]{}, ev_met[2]{};
   float* pm_met[2]{};            // pinned: MET_COUNT floats + [log_alpha, grad log_alpha]
