@@ -56,7 +56,10 @@ __global__ void __launch_bounds__(512) gather2_kernel(Gather2Args a) {
   const double clip_obs = g.normc[1];
   const bool norm_obs = g.normc[3] != 0.0;
   const float scale = g.scale;
-  uint16_t* s0 = sm_planes; uint16_t* s1 = s0 + npx; uint16_t* s2 = s1 + npx;
+  // shared-memory planes with a padded row pitch (+8 elements = +4 banks per image row): the patch pass below reads 16-byte runs
+  // of 8 consecutive image rows at once, which a 128-byte pitch puts on the same four banks (8-way conflicts: 2.5 M conflict
+  // cycles per launch in profiles/ncu_aux_r2.md)
+  const int rowe = g.W * Ci, pitch = rowe + 8, plane_e = g.H * pitch;
   uint16_t* xh = a.xp[which][0]; uint16_t* xl = a.xp[which][1];
   (void)Cfull;
   // image block: exactly the NHWC image with Ci channels -> no index arithmetic; float64 VecNormalize chain per element
@@ -77,7 +80,8 @@ __global__ void __launch_bounds__(512) gather2_kernel(Gather2Args a) {
 #pragma unroll
     for (int pl = 0; pl < 3; ++pl) {
       const uint2 w = make_uint2((uint32_t)p[pl][0] | ((uint32_t)p[pl][1] << 16), (uint32_t)p[pl][2] | ((uint32_t)p[pl][3] << 16));
-      reinterpret_cast<uint2*>(sm_planes + pl * npx)[e4] = w;
+      const int e = 4 * e4, row = e / rowe, col = e - row * rowe;          // (rowe is a multiple of 4: a group never straddles rows)
+      *reinterpret_cast<uint2*>(sm_planes + pl * plane_e + row * pitch + col) = w;
       if (xh && pl < 2) reinterpret_cast<uint2*>((pl ? xl : xh) + (size_t)b * npx)[e4] = w;
     }
   }
@@ -104,11 +108,11 @@ __global__ void __launch_bounds__(512) gather2_kernel(Gather2Args a) {
     const int part = i % (seg / 8), run = i / (seg / 8);      // 16-byte pieces of a run
     const int ky = run & 7, patch = run >> 3;
     const int oy = patch / a.OW, ox = patch - oy * a.OW;
-    const int so = ((4 * oy + ky) * g.W + 4 * ox) * Ci + 8 * part;         // 8-byte aligned at least
+    const int so = (4 * oy + ky) * pitch + 4 * ox * Ci + 8 * part;         // 8-byte aligned at least
     const size_t go = img + (size_t)patch * K1 + ky * seg + 8 * part;
 #pragma unroll
     for (int pl = 0; pl < 3; ++pl) {
-      const uint16_t* sp = sm_planes + pl * npx + so;
+      const uint16_t* sp = sm_planes + pl * plane_e + so;
       const uint2 lo = *reinterpret_cast<const uint2*>(sp), hi = *reinterpret_cast<const uint2*>(sp + 4);
       *reinterpret_cast<uint4*>(a.a1[which][pl] + go) = make_uint4(lo.x, lo.y, hi.x, hi.y);
     }
@@ -158,11 +162,11 @@ struct Plane2Job {
 
 // 64 (r) x 32 (n) source tile per CTA.  Loads are float4 along n; the transposed copy is written as 16-byte runs of 8
 // consecutive r values per plane (the 2-byte scattered stores of the first version made this the longest leaf kernel).
-__global__ void __launch_bounds__(256) planes2_kernel(const Plane2Job* __restrict__ jobs, int njobs) {
+__global__ void __launch_bounds__(256) planes2_kernel(const Plane2Job* __restrict__ jobs, const int* __restrict__ cta_job) {
   __shared__ float tile[64][33];
-  int j = 0;
-  while (j + 1 < njobs && (int)blockIdx.x >= jobs[j + 1].tile_start) ++j;
-  const Plane2Job job = jobs[j];
+  // (the job of a CTA comes from a table: walking the job list cost up to 30 DEPENDENT global loads before the first useful one --
+  //  19.5 long-scoreboard stalls per issue in profiles/ncu_aux_r2.md)
+  const Plane2Job job = jobs[cta_job[blockIdx.x]];
   const int t = blockIdx.x - job.tile_start;
   const int tiles_n = (job.N + 31) / 32;
   const int r0 = (t / tiles_n) * 64, n0 = (t % tiles_n) * 32;
@@ -504,6 +508,15 @@ int v2_create(b2g_sac* h) {
   B2G_CK(cudaMemcpyAsync(dj, jobs.data(), jobs.size() * sizeof(Plane2Job), cudaMemcpyHostToDevice, h->stream));
   B2G_CK(cudaStreamSynchronize(h->stream));
   v.plane_jobs = dj;
+  {
+    std::vector<int> cj((size_t)start);
+    for (size_t k = 0; k < jobs.size(); ++k)
+      for (int t = jobs[k].tile_start; t < (k + 1 < jobs.size() ? jobs[k + 1].tile_start : start); ++t) cj[t] = (int)k;
+    int* dcj = nullptr;
+    if (int rc = valloc(h, &dcj, cj.size())) return rc;
+    B2G_CK(cudaMemcpy(dcj, cj.data(), cj.size() * sizeof(int), cudaMemcpyHostToDevice));
+    v.plane_cta_job = dcj;
+  }
 
   // ================================================================================ forward problems (6-product mode)
   const int NP = 3;
@@ -901,7 +914,7 @@ int v2_create(b2g_sac* h) {
 // ================================================================================================ step pieces
 int v2_planes(b2g_sac* h, cudaStream_t s) {
   V2State& v = h->v2;
-  planes2_kernel<<<v.plane_ctas, 256, 0, s>>>((const Plane2Job*)v.plane_jobs, v.n_plane_jobs);
+  planes2_kernel<<<v.plane_ctas, 256, 0, s>>>((const Plane2Job*)v.plane_jobs, v.plane_cta_job);
   return 0;
 }
 
@@ -920,7 +933,7 @@ int v2_gather(b2g_sac* h, const GatherArgs& ga, cudaStream_t s) {
   }
   for (int n = 0; n < 3; ++n) for (int p = 0; p < 3; ++p) a.fp[n][p] = v.F[n][p];
   a.KF = v.KF; a.Ci = h->Cimg; a.OH = h->H1; a.OW = h->W1;
-  const size_t smem = (size_t)3 * h->Hi * h->Wi * h->Cimg * sizeof(uint16_t);
+  const size_t smem = (size_t)3 * h->Hi * (h->Wi * h->Cimg + 8) * sizeof(uint16_t);
   static size_t attr = 0;
   if (smem > attr) {
     B2G_CK(cudaFuncSetAttribute(gather2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -62,6 +62,7 @@ struct V2State {
   uint16_t* K0n[2][2]{};         // [0] pi [513 -> 576 rows][64], [1] values packed [576 rows][192]
   float* z0v = nullptr;          // fc0 pre-activations of vf|q1|q2: [B][192]
   void* plane_jobs = nullptr; int n_plane_jobs = 0, plane_ctas = 0;
+  int* plane_cta_job = nullptr;  // job index of every CTA of the planes launch
   void* colsum_part[2]{}; int n_colsum_part[2]{}, colsum_ctas_part[2]{};   // [0] cnn_fc1 biases (early), [1] conv biases
   int sm_reserve = 0;            // SMs left to a collective that runs concurrently with the persistent GEMM grids
   std::vector<CUtensorMap> maps; // host copy
