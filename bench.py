@@ -362,9 +362,12 @@ def main():
     # the learn() loop of the SB-shaped front end: one new transition enters the device replay per gradient step
     one = {k: v[:1] for k, v in pin.items() if k != "eps"}
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
+    for it in range(e2e_steps):
         L.replay_add(one["obs"], one["act"], one["rew"], one["next_obs"], one["done"])
-        L.step(1, lr=LR)
+        L.step_async(1, lr=LR)                    # what SAC.learn does: enqueue, read the losses back when they are logged
+        if it % 100 == 99:
+            L.step(0, lr=LR)
+    L.step(0, lr=LR)
     e2e_learn = world * e2e_steps / (time.perf_counter() - t0)
 
     # ---- replica identity after everything above (hundreds of updates): byte-identical parameters on every rank

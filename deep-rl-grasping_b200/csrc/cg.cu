@@ -478,6 +478,16 @@ cg_kernel(const __grid_constant__ CgPack pk, int nprob, int total_tiles, const C
 #pragma unroll
               for (int j = 0; j < 8; ++j)
                 *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(x[4 * j] * sc, x[4 * j + 1] * sc, x[4 * j + 2] * sc, x[4 * j + 3] * sc);
+              if (P.dp_n > 1) {                          // final values: push them to their owner now (posted NVLink stores)
+                const int i4 = (int)((dst - P.dp_gbase) >> 2), per4 = P.dp_per4;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const int owner = (i4 + j) / per4;
+                  if (owner != P.dp_rank)
+                    reinterpret_cast<float4*>(P.dp_recv[owner])[(size_t)P.dp_rank * per4 + (i4 + j - owner * per4)] =
+                        make_float4(x[4 * j] * sc, x[4 * j + 1] * sc, x[4 * j + 2] * sc, x[4 * j + 3] * sc);
+                }
+              }
             }
           }
           continue;
@@ -640,7 +650,7 @@ cudaError_t cg_launch(const CgGroup& g, const CUtensorMap* dev_maps, int num_sms
   const int smem = 1024 + g.ring_bytes;
   const int grid = g.total_tiles < num_sms ? g.total_tiles : num_sms;
   CgPack pk;              // (host staging; the launch copies it into the parameter buffer)
-  static_assert(sizeof(CgPack) < 16 * 1024, "problem list must fit the kernel parameter space");
+  static_assert(sizeof(CgPack) < 28 * 1024, "problem list must fit the kernel parameter space (32,764 B on sm_100)");
   for (int i = 0; i < g.n; ++i) pk.p[i] = g.host[i];
   cudaError_t e = launch_pdl(cg_kernel, dim3(grid), dim3(NTHREADS), (size_t)smem, s, pdl, pk, g.n, g.total_tiles, dev_maps, g.nstages, debug_flags, g_cg_trace, epi_tiles);
   if (e != cudaSuccess) fprintf(stderr, "cg_launch %s: %s (grid %d, %d threads, smem %d)\n", g.name, cudaGetErrorString(e), grid, NTHREADS, smem);

@@ -92,6 +92,12 @@ struct CgProblem {
   int* done_ctr;              // arrival counters of THIS problem, one per tm (nullptr: nobody waits on it); zeroed before the launch
   const int* dep_ctr;         // counters of the producing problem (nullptr: no dependency)
   int dep_rows, dep_rows_tile, dep_tiles, dep_expect;
+  // ---- data parallel (N > 1): a weight gradient that is FINAL when its tile is stored (no split-K) is also pushed, float4 by float4,
+  //      into the receive arena of the rank that owns that part of the gradient arena (optim.cu: dp_optim_kernel) -- 80 % of the
+  //      gradient bytes leave while the backward pass is still running
+  float* dp_recv[8];          // receive arenas (nullptr entries: none)
+  const float* dp_gbase;      // base of the local gradient arena (owner of float4 i4 = i4 / dp_per4)
+  int dp_rank, dp_n, dp_per4;
   int dep_by_chunk;           // 1: the rows are indexed by the tile's K-chunk range [c_begin, c_end) instead of its tm (weight gradients)
 };
 

@@ -208,6 +208,7 @@ struct DpArgs {
   float* R_peer[DP_MAX_RANKS];         // receive arena of every rank: [src rank][slice] floats (slices pushed by their producers)
   float* P_peer[DP_MAX_RANKS];         // parameter arena of every rank
   int* x_peer[DP_MAX_RANKS];           // exchange block of every rank: int flags[2][8] (G ready, slice written), float part[8][2], loss[8][16]
+  int skip_lo4[2], skip_hi4[2];        // float4 ranges of the arena whose slices were already pushed by the backward epilogues
   const long long* counters;           // counters[3] = optimiser step = flag epoch
   int* sync;                           // local: [0], [1] CTA arrival counters, [2..3] squared-norm accumulators (as float), [8..] bring-up stamps
 };

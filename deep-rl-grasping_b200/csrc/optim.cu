@@ -231,7 +231,10 @@ __global__ void __launch_bounds__(1024) dp_optim_kernel(DpArgs d) {
     const int qlo = q * per4, qhi = min(n_train4, qlo + per4);
     float4* dst = reinterpret_cast<float4*>(d.R_peer[q]) + (size_t)me * per4;
     const float4* src = reinterpret_cast<const float4*>(a.G);
-    for (int i4 = qlo + gtid; i4 < qhi; i4 += nthr) dst[i4 - qlo] = __ldcs(src + i4);
+    for (int i4 = qlo + gtid; i4 < qhi; i4 += nthr) {
+      if ((i4 >= d.skip_lo4[0] && i4 < d.skip_hi4[0]) || (i4 >= d.skip_lo4[1] && i4 < d.skip_hi4[1])) continue;   // pushed by the cnn_fc1 wgrad epilogue
+      dst[i4 - qlo] = __ldcs(src + i4);
+    }
   }
   if (blockIdx.x == 0 && tid < N * MET_GN_PI) {
     const int q = tid / MET_GN_PI, k = tid - q * MET_GN_PI;

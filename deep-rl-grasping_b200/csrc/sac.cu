@@ -1108,6 +1108,7 @@ int issue_step(b2g_sac* h, bool sampled, bool apply, bool want_per_sample, Prof*
     da.o = oa; da.rank = h->cfg.rank; da.nranks = h->cfg.nranks;
     for (int q = 0; q < h->cfg.nranks; ++q) { da.R_peer[q] = h->dp_G[q]; da.P_peer[q] = h->dp_P[q]; da.x_peer[q] = h->dp_X[q]; }
     da.counters = h->counters; da.sync = h->dp_sync;
+    for (int k = 0; k < 2; ++k) { da.skip_lo4[k] = h->dp_skip[k][0]; da.skip_hi4[k] = h->dp_skip[k][1]; }
     dp_optim_launch(da, h->num_sms, s); ++n;
     mark("adam_polyak_dp");
   } else {     // (a gradient-only step of a connected learner takes the NCCL path above)
@@ -1245,6 +1246,29 @@ int b2g_sac_dp_connect(b2g_sac* h, const void* all_exports, int nranks) {
       h->dp_opened.push_back(p[k]);
     }
     h->dp_P[q] = (float*)p[0]; h->dp_G[q] = (float*)p[1]; h->dp_X[q] = (int*)p[2];
+  }
+  // the cnn_fc1 weight gradients (80 % of the gradient bytes) are final when their tiles are stored: their epilogues push them
+  h->dp_skip[0][0] = h->dp_skip[0][1] = h->dp_skip[1][0] = h->dp_skip[1][1] = 0;
+  if (h->v2.bwd && h->cnn && !getenv("B2G_DP_NO_EPI_PUSH")) {
+    const int n_train4 = (int)((h->n_pi + h->n_values + h->n_ent) >> 2), per4 = (n_train4 + nranks - 1) / nranks;
+    const char* names[2] = {"model/pi/cnn_fc1/w", "model/values_fn/cnn_fc1/w"};
+    for (int k = 0; k < 2; ++k) {
+      const float* gp = h->g(names[k]);
+      const auto& t = h->tensors[h->tindex.at(names[k])];
+      bool found = false;
+      auto patch = [&](std::vector<CgGroup>& groups) {
+        for (CgGroup& g : groups)
+          for (int i = 0; i < g.n; ++i) {
+            CgProblem& P = g.host[i];
+            if (P.epi != CG_EPI_WGRAD || P.atomic || P.out_f != gp) continue;
+            for (int q = 0; q < nranks; ++q) P.dp_recv[q] = h->dp_G[q];
+            P.dp_gbase = h->G; P.dp_rank = h->cfg.rank; P.dp_n = nranks; P.dp_per4 = per4;
+            found = true;
+          }
+      };
+      patch(h->v2.bwd_groups); patch(h->v2.bwd_fused);
+      if (found && (t.off & 3) == 0) { h->dp_skip[k][0] = (int)(t.off >> 2); h->dp_skip[k][1] = (int)((t.off + 1024 * 512) >> 2); }
+    }
   }
   h->dp_p2p = true;
   if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }     // the step changes shape

@@ -171,6 +171,7 @@ struct b2g_sac {
   float* dp_recv = nullptr;            // receive arena: [src rank][my slice] gradient copies pushed by the other ranks
   float* dp_P[8]{}; float* dp_G[8]{}; int* dp_X[8]{};     // every rank's parameter arena, receive arena, exchange block (own = local)
   std::vector<void*> dp_opened;        // cudaIpcOpenMemHandle results
+  int dp_skip[2][2]{};                 // float4 ranges of the gradient arena pushed by the cnn_fc1 wgrad epilogues
   cudaStream_t side = nullptr;
   cudaStream_t aux = nullptr;              // leaf work off the critical chain (zeroing, weight planes, leaf wgrads, bias sums)
   cudaEvent_t ev_aux[7]{};

@@ -227,11 +227,16 @@ class SAC:
                         self._sync_norm_stats()              # statistics current at sample time ([SB2] ReplayBuffer.sample(env=))
                     frac = 1.0 - step / total_timesteps
                     lr = float(lr_fn(frac))
-                    infos_values = self.learner.step(self.gradient_steps, lr)
-                    self.n_updates = int(infos_values["n_updates"])
+                    # enqueue only: the gradient step runs on the device while the host goes on to the next env.step(); the losses
+                    # (SB's infos_values, used for logging alone) are read back when something is actually logged
+                    self.learner.step_async(self.gradient_steps, lr)
+                    self.n_updates += self.gradient_steps
+                    self._last_lr = lr
                 callback.on_rollout_start()
             if self.verbose >= 1 and done.any() and log_interval and len(self.episode_rewards) % log_interval == 0:
                 fps = int(step / max(1e-9, time.time() - t_start))
+                if self.n_updates:
+                    infos_values = self.learner.step(0, getattr(self, "_last_lr", 3e-4))       # 0 steps: just fetch the latest losses
                 print({"episodes": len(self.episode_rewards), "mean 100 episode reward": round(float(np.mean(self.episode_rewards[-101:-1] or [0])), 1),
                        "n_updates": self.n_updates, "fps": fps, "total timesteps": self.num_timesteps,
                        **{k: infos_values.get(k) for k in ("policy_loss", "qf1_loss", "qf2_loss", "value_loss", "entropy", "ent_coef")}})
