@@ -15,7 +15,7 @@ B2G_PREC_FP32_SIMT, B2G_PREC_BF16X3, B2G_PREC_BF16 = 0, 1, 2
 
 #: every symbol include/b200grasp.h declares (tests check the .so exports each of them)
 SYMBOLS = [
-    "b2g_last_error", "b2g_version", "b2g_nccl_unique_id", "b2g_sac_create", "b2g_sac_destroy", "b2g_sac_dp_export", "b2g_sac_dp_connect", "b2g_debug_dp_stamps", "b2g_sync",
+    "b2g_last_error", "b2g_version", "b2g_nccl_unique_id", "b2g_sac_create", "b2g_sac_destroy", "b2g_sac_dp_export", "b2g_sac_dp_connect", "b2g_debug_dp_stamps", "b2g_debug_compact_host", "b2g_sync",
     "b2g_param_count", "b2g_param_info", "b2g_get_param", "b2g_set_param", "b2g_get_grad", "b2g_get_adam",
     "b2g_reset_optimizer", "b2g_replay_add", "b2g_replay_size", "b2g_replay_get", "b2g_get_last_batch", "b2g_set_norm_stats", "b2g_sac_step",
     "b2g_sac_step_async", "b2g_sac_step_explicit", "b2g_sac_step_host_pipelined", "b2g_sac_pipeline_flush", "b2g_sac_act", "b2g_launches_per_step", "b2g_last_step_ms",
@@ -98,6 +98,7 @@ def load():
     lib.b2g_sac_dp_export.argtypes = [vp, vp]
     lib.b2g_sac_dp_connect.argtypes = [vp, vp, C.c_int]
     lib.b2g_debug_dp_stamps.argtypes = [vp, C.POINTER(C.c_longlong)]
+    lib.b2g_debug_compact_host.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.b2g_sync.argtypes = [vp]
     lib.b2g_param_count.argtypes = [vp]
     lib.b2g_param_info.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int64), C.POINTER(C.c_int32),

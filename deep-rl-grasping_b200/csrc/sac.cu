@@ -809,7 +809,9 @@ struct Prof {
 // Issues every launch of one gradient step on h->stream.  Returns the number of launches.
 int issue_step(b2g_sac* h, bool sampled, bool apply, bool want_per_sample, Prof* prof, int* n_launch) {
   cudaStream_t s = h->stream;
-  int n = 0;
+  int n = 0;            // kernels (ours and, N > 1 on the NCCL path, the collective's)
+  int n_copy = 0;       // memset / copy nodes: not counted as launches
+  (void)n_copy;
   auto mark = [&](const char* name) {
     if (prof && prof->on) {
       cudaEvent_t e;
@@ -840,12 +842,12 @@ int issue_step(b2g_sac* h, bool sampled, bool apply, bool want_per_sample, Prof*
     CK(cudaStreamWaitEvent(ax, h->ev_aux[0], 0));
     if (h->use_planes && !h->v2.bwd) { planes_launch(h->d_jobs, h->n_jobs, h->job_tiles, ax); ++n; }
     if (h->v2.on) { if (int rc = v2_planes(h, ax)) return rc; ++n; }
-    if (h->fc0_split || h->v2.on) { CK(cudaMemsetAsync(h->z0[0], 0, (size_t)5 * h->B * h->H * sizeof(float), ax)); ++n; }
-    if (h->v2.on) { CK(cudaMemsetAsync(h->v2.z0v, 0, (size_t)3 * h->B * h->H * sizeof(float), ax)); ++n; }
-    if (h->fuse_fwd) { CK(cudaMemsetAsync(h->sync_ctr, 0, 32 * sizeof(unsigned), ax)); ++n; }
+    if (h->fc0_split || h->v2.on) { CK(cudaMemsetAsync(h->z0[0], 0, (size_t)5 * h->B * h->H * sizeof(float), ax)); ++n_copy; }
+    if (h->v2.on) { CK(cudaMemsetAsync(h->v2.z0v, 0, (size_t)3 * h->B * h->H * sizeof(float), ax)); ++n_copy; }
+    if (h->fuse_fwd) { CK(cudaMemsetAsync(h->sync_ctr, 0, 32 * sizeof(unsigned), ax)); ++n_copy; }
     CK(cudaEventRecord(h->ev_aux[1], ax));
     prep_launch(pa, ax); ++n;
-    CK(cudaMemsetAsync(h->G, 0, (size_t)(h->n_train + MET_COUNT) * sizeof(float), ax)); ++n;
+    CK(cudaMemsetAsync(h->G, 0, (size_t)(h->n_train + MET_COUNT) * sizeof(float), ax)); ++n_copy;
     CK(cudaEventRecord(h->ev_aux[6], ax));
   } else {
     prep_launch(pa, s); ++n; mark("prep");
@@ -869,10 +871,10 @@ int issue_step(b2g_sac* h, bool sampled, bool apply, bool want_per_sample, Prof*
   if (h->record_after_gather) CK(cudaEventRecord(h->record_after_gather, s));   // staged batch consumed
   if (fork) CK(cudaStreamWaitEvent(s, h->ev_aux[1], 0));
   else {
-    CK(cudaMemsetAsync(h->G, 0, (size_t)(h->n_train + MET_COUNT) * sizeof(float), s)); ++n;
-    if (h->fc0_split || h->v2.on) { CK(cudaMemsetAsync(h->z0[0], 0, (size_t)5 * h->B * h->H * sizeof(float), s)); ++n; }
-    if (h->v2.on) { CK(cudaMemsetAsync(h->v2.z0v, 0, (size_t)3 * h->B * h->H * sizeof(float), s)); ++n; }
-    if (h->fuse_fwd) { CK(cudaMemsetAsync(h->sync_ctr, 0, 32 * sizeof(unsigned), s)); ++n; }
+    CK(cudaMemsetAsync(h->G, 0, (size_t)(h->n_train + MET_COUNT) * sizeof(float), s)); ++n_copy;
+    if (h->fc0_split || h->v2.on) { CK(cudaMemsetAsync(h->z0[0], 0, (size_t)5 * h->B * h->H * sizeof(float), s)); ++n_copy; }
+    if (h->v2.on) { CK(cudaMemsetAsync(h->v2.z0v, 0, (size_t)3 * h->B * h->H * sizeof(float), s)); ++n_copy; }
+    if (h->fuse_fwd) { CK(cudaMemsetAsync(h->sync_ctr, 0, 32 * sizeof(unsigned), s)); ++n_copy; }
     mark("zero_grads");
   }
   int x3 = h->cfg.precision == B2G_PREC_BF16X3 ? 1 : 0;
@@ -904,7 +906,7 @@ int issue_step(b2g_sac* h, bool sampled, bool apply, bool want_per_sample, Prof*
   };
   const bool fused = h->v2.on && h->v2.fuse && !h->v2.fwd_fused.empty();
   if (fused) {
-    CK(cudaMemsetAsync(h->v2.dep_ctr, 0, (size_t)h->v2.n_dep_ctr * sizeof(int), s)); ++n;
+    CK(cudaMemsetAsync(h->v2.dep_ctr, 0, (size_t)h->v2.n_dep_ctr * sizeof(int), s)); ++n_copy;
     if (int rc = v2_launch(h, h->v2.fwd_fused[0], s)) return rc;
     ++n; mark("fwd_fused");
   } else if (h->v2.on) {
@@ -970,7 +972,7 @@ int issue_step(b2g_sac* h, bool sampled, bool apply, bool want_per_sample, Prof*
     // early all-reduce starts).
     const bool fused_bwd = fused && h->v2.bwd_fused.size() == 3;
     auto early_allreduce = [&]() -> int {
-      CK(cudaMemcpyAsync(h->G + h->n_train, h->metrics, MET_GN_PI * sizeof(float), cudaMemcpyDeviceToDevice, s)); ++n;
+      CK(cudaMemcpyAsync(h->G + h->n_train, h->metrics, MET_GN_PI * sizeof(float), cudaMemcpyDeviceToDevice, s)); ++n_copy;
       CK(cudaEventRecord(h->ev_fork, s));
       CK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
       if (fork) { CK(cudaEventRecord(h->ev_aux[4], ax)); CK(cudaStreamWaitEvent(h->side, h->ev_aux[4], 0)); }   // heads_wgrad (+ fc1 bias sums)
@@ -1063,7 +1065,7 @@ int issue_step(b2g_sac* h, bool sampled, bool apply, bool want_per_sample, Prof*
       }
       if (overlap) {
         // early all-reduce on the side stream / second communicator, overlapping the conv backward
-        CK(cudaMemcpyAsync(h->G + h->n_train, h->metrics, MET_GN_PI * sizeof(float), cudaMemcpyDeviceToDevice, s)); ++n;
+        CK(cudaMemcpyAsync(h->G + h->n_train, h->metrics, MET_GN_PI * sizeof(float), cudaMemcpyDeviceToDevice, s)); ++n_copy;
         CK(cudaEventRecord(h->ev_fork, s));
         CK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
         if (int rc = nccl_ck(g_nccl.GroupStart())) return rc;
@@ -1089,11 +1091,11 @@ int issue_step(b2g_sac* h, bool sampled, bool apply, bool want_per_sample, Prof*
       CK(cudaStreamWaitEvent(s, h->ev_join, 0));
     } else {
       // losses/means ride behind the gradients in the same buffer
-      CK(cudaMemcpyAsync(h->G + h->n_train, h->metrics, MET_GN_PI * sizeof(float), cudaMemcpyDeviceToDevice, s)); ++n;
+      CK(cudaMemcpyAsync(h->G + h->n_train, h->metrics, MET_GN_PI * sizeof(float), cudaMemcpyDeviceToDevice, s)); ++n_copy;
       if (int rc = nccl_ck(g_nccl.AllReduce(h->G, h->G, (size_t)(h->n_train + MET_COUNT), /*ncclFloat32*/ 7, /*ncclSum*/ 0, h->nccl_comm, s))) return rc;
       ++n;
     }
-    CK(cudaMemcpyAsync(h->metrics, h->G + h->n_train, MET_GN_PI * sizeof(float), cudaMemcpyDeviceToDevice, s)); ++n;
+    CK(cudaMemcpyAsync(h->metrics, h->G + h->n_train, MET_GN_PI * sizeof(float), cudaMemcpyDeviceToDevice, s)); ++n_copy;
     mark("allreduce");
   }
   OptimArgs oa = make_optim();
@@ -1756,6 +1758,13 @@ void compact_host(const float* src, float* dst, int n, int HW, int Cfull, int Ec
   }
 }
 }  // namespace
+
+int b2g_debug_compact_host(const float* src, float* dst, int n, int hw, int cfull, int threads) {
+  /* host-only (no device needed): the row compaction b2g_sac_step_host_pipelined applies before its copy */
+  if (!src || !dst || n < 0 || hw < 1 || cfull < 2) return fail(B2G_EINVAL, "b2g_debug_compact_host: bad argument");
+  compact_host(src, dst, n, hw, cfull, hw * (cfull - 1) + 4, threads > 0 ? threads : 1);
+  return 0;
+}
 
 int b2g_sac_step_host_pipelined(b2g_sac* h, const float* obs, const float* act, const float* rew, const float* next_obs,
                                 const float* done, const float* eps, float lr, b2g_sac_metrics* prev_out, int* have_prev) {

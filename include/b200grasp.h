@@ -85,7 +85,10 @@ int b2g_sac_destroy(b2g_sac* h);
 #define B2G_DP_EXPORT_BYTES 192
 int b2g_sac_dp_export(b2g_sac* h, void* out192);
 int b2g_sac_dp_connect(b2g_sac* h, const void* all_exports /* nranks x B2G_DP_EXPORT_BYTES, rank order */, int nranks);
-int b2g_debug_dp_stamps(b2g_sac* h, long long* out5);   /* bring-up: %globaltimer at the phase boundaries of the last launch */
+int b2g_debug_dp_stamps(b2g_sac* h, long long* out5);
+/* host-only: [n][hw][cfull] observations -> compact replay rows [n][hw*(cfull-1)+4] (image planes | actuator value | 3 x 0), the layout
+ * b2g_replay_add / b2g_sac_step_host_pipelined store and copy; needs no device */
+int b2g_debug_compact_host(const float* src, float* dst, int n, int hw, int cfull, int threads);   /* bring-up: %globaltimer at the phase boundaries of the last launch */
 int b2g_sync(b2g_sac* h);
 
 /* ---- parameters: SB-zip variable names without the ":0" suffix (get_parameters / load_parameters,

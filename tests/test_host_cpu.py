@@ -320,3 +320,21 @@ def test_world_size_2_gloo_host_path(tmp_path):
                        env=dict(os.environ, OMP_NUM_THREADS="2"))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "ok 0" in r.stdout and "ok 1" in r.stdout
+
+
+@pytest.mark.parametrize("cfull,threads", [(2, 1), (2, 7), (5, 4)])
+def test_host_compaction_matches_numpy(cfull, threads):
+    """b2g_sac_step_host_pipelined compacts observations on the host before the copy (the constant actuator plane never crosses
+    PCIe): rows = image planes | value of the last plane at pixel [0,0] | three zeros -- the layout of the device replay
+    (custom_obs_policy.py:20-23 reads that one pixel).  Host-only entry point, no device needed."""
+    import ctypes as C
+    from b200grasp import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(5)
+    n, hw = 37, 64 * 64
+    src = rng.standard_normal((n, hw, cfull)).astype(np.float32)
+    dst = np.full((n, hw * (cfull - 1) + 4), np.nan, np.float32)
+    rc = lib.b2g_debug_compact_host(src.ctypes.data_as(C.c_void_p), dst.ctypes.data_as(C.c_void_p), n, hw, cfull, threads)
+    assert rc == 0
+    ref = np.concatenate([src[:, :, :cfull - 1].reshape(n, -1), src[:, 0, cfull - 1:cfull], np.zeros((n, 3), np.float32)], axis=1)
+    assert np.array_equal(dst, ref)
