@@ -394,6 +394,20 @@ cg_kernel(const __grid_constant__ CgPack pk, int nprob, int total_tiles, const C
       mbar_wait(smem_u32(&bar_acc_full[buf]), (it >> 1) & 1);
       if (tre) trace[512 + it * 4 + 1] = clock64();
       tc_fence_after();
+      const bool split_fin = P.ws != nullptr;          // split-K tile of an ACT problem: partial sums first, the last arriver finishes
+      float* __restrict__ wsrow = split_fin ? P.ws + ((size_t)(ti.tm * w.tiles_n + ti.tn) * 128 + r) * umma_n : nullptr;
+      bool last_arriver = !split_fin;
+      for (int pass = 0; pass < (split_fin ? 2 : 1); ++pass) {
+      if (pass == 1) {
+        __syncwarp();
+        int old = 0;
+        if (lane == 0) { __threadfence(); old = atomicAdd(P.ws_cnt + (ti.tm * w.tiles_n + ti.tn) * NEPI_WARPS + ew, 1); }
+        old = __shfl_sync(0xffffffffu, old, 0);
+        last_arriver = old == w.splits - 1;
+        if (!last_arriver) break;
+        __threadfence();
+        if (lane == 0) P.ws_cnt[(ti.tm * w.tiles_n + ti.tn) * NEPI_WARPS + ew] = 0;     // next step starts from zero
+      }
       for (int g = epi_tiles ? 0 : half; g < ngroups; g += epi_tiles ? 1 : 2) {
         const int ng = n0 + 32 * g;                      // first problem column of the group
         // ---- everything that does not depend on the accumulator is fetched BEFORE the TMEM loads are waited for: the epilogue of
@@ -416,6 +430,8 @@ cg_kernel(const __grid_constant__ CgPack pk, int nprob, int total_tiles, const C
 #pragma unroll
           for (int j = 0; j < 4; ++j) mk[j] = valid ? __ldg(reinterpret_cast<const uint4*>(mask + moff + ng) + j) : make_uint4(0, 0, 0, 0);
         }
+        float x[32];
+        if (pass == 0) {
         uint32_t v[32], u[32], t[32];
         const uint32_t taddr = tmem + buf * 256u + ((uint32_t)(q * 32) << 16) + (uint32_t)(32 * g);
 #define CG_TMEM_LD32(dst, addr)                                                                                                              \
@@ -434,7 +450,6 @@ cg_kernel(const __grid_constant__ CgPack pk, int nprob, int total_tiles, const C
         if (tre && g == 0) trace[576 + it * 4 + 0] = clock64();
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (tre && g == 0) trace[576 + it * 4 + 1] = clock64();
-        float x[32];
         if (ngrp_acc > 2) {                                // correction column groups, smallest order first
 #pragma unroll
           for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) + (__uint_as_float(u[j]) + __uint_as_float(t[j]));
@@ -444,6 +459,22 @@ cg_kernel(const __grid_constant__ CgPack pk, int nprob, int total_tiles, const C
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+        }
+        if (split_fin) {                                   // partial sums of this split -> workspace
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(wsrow + 32 * g + 4 * j), "f"(x[4 * j]), "f"(x[4 * j + 1]), "f"(x[4 * j + 2]),
+                         "f"(x[4 * j + 3])
+                         : "memory");
+          continue;
+        }
+        } else {                                           // last arriver: the complete sums, and a clean workspace for the next step
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 sum = __ldcg(reinterpret_cast<const float4*>(wsrow + 32 * g) + j);
+            x[4 * j] = sum.x; x[4 * j + 1] = sum.y; x[4 * j + 2] = sum.z; x[4 * j + 3] = sum.w;
+            __stcg(reinterpret_cast<float4*>(wsrow + 32 * g) + j, make_float4(0.f, 0.f, 0.f, 0.f));
+          }
         }
         if (!live) continue;
         // Every lane owns one output row and writes its 32 columns itself (64 B per BF16 plane, 128 B of fp32): 16-byte vector
@@ -556,11 +587,12 @@ cg_kernel(const __grid_constant__ CgPack pk, int nprob, int total_tiles, const C
           }
         }
       }
+      }   // pass
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(smem_u32(&bar_acc_empty[buf]));
-        if (P.done_ctr) {                                                // this warp's rows of the tile are in global memory
+        if (P.done_ctr && last_arriver) {                                // this warp's rows of the tile are in global memory
           __threadfence();
           atomicAdd(P.done_ctr + ti.tm, 1);
         }

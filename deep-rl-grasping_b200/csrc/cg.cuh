@@ -92,6 +92,12 @@ struct CgProblem {
   int* done_ctr;              // arrival counters of THIS problem, one per tm (nullptr: nobody waits on it); zeroed before the launch
   const int* dep_ctr;         // counters of the producing problem (nullptr: no dependency)
   int dep_rows, dep_rows_tile, dep_tiles, dep_expect;
+  // ---- split-K with in-kernel finalisation (ACT problems with splits > 1; the late layers have too few tiles for 148 SMs): every
+  //      split tile adds its fp32 partial sums into ws[tile][128][umma_n] (red.add), then each epilogue warp bumps its own arrival
+  //      counter of the tile; the warp that arrives LAST reads the sums back, clears them for the next step, and runs the normal
+  //      bias / ReLU / plane-split / store path (and alone signals done_ctr)
+  float* ws;                  // nullptr: splits are plain (RAW / WGRAD atomics)
+  int* ws_cnt;                // [tiles_m * tiles_n][CG_EPI_WARPS]
   // ---- data parallel (N > 1): a weight gradient that is FINAL when its tile is stored (no split-K) is also pushed, float4 by float4,
   //      into the receive arena of the rank that owns that part of the gradient arena (optim.cu: dp_optim_kernel) -- 80 % of the
   //      gradient bytes leave while the backward pass is still running

@@ -385,12 +385,13 @@ int fuse_groups(b2g_sac* h, const std::vector<const CgGroup*>& parts, const std:
     if (Pc.dep_ctr && ctr_of[pi] < 0) {
       // a second producer of the same consumer (the two nets' conv2 dgrads both write dZ1): it signals the first one's counters
       ctr_of[pi] = (int)(intptr_t)Pc.dep_ctr - 1;
-      Pc.dep_expect += Pp.tiles_n * Pp.splits;
+      Pc.dep_expect += Pp.ws ? Pp.tiles_n : Pp.tiles_n * Pp.splits;
       continue;
     }
     if (ctr_of[pi] < 0) { ctr_of[pi] = n_ctr; n_ctr += Pp.tiles_m; }
     Pc.dep_rows = w.dep_rows; Pc.dep_rows_tile = w.dep_rows_tile; Pc.dep_tiles = Pp.tiles_m; Pc.dep_by_chunk = w.by_chunk;
-    Pc.dep_expect = Pp.tiles_n * Pp.splits;                      // x the signalling epilogue warps per tile (kernel side)
+    Pc.dep_expect = Pp.ws ? Pp.tiles_n : Pp.tiles_n * Pp.splits;   // x the signalling epilogue warps per tile (kernel side); split-K
+                                                                   // tiles with finalisation are signalled by their last arriver only
     Pc.dep_ctr = (const int*)(intptr_t)(ctr_of[pi] + 1);        // counter index + 1; turned into pointers once the array exists
   }
   for (int i = 0; i < f.n; ++i) f.host[i].done_ctr = (int*)(intptr_t)(ctr_of[i] + 1);
@@ -518,6 +519,7 @@ int v2_create(b2g_sac* h) {
     v.plane_cta_job = dcj;
   }
 
+  { const char* e = getenv("B2G_SPLIT_FC1"); v.split_fc1 = e ? std::max(1, atoi(e)) : 3; }
   // ================================================================================ forward problems (6-product mode)
   const int NP = 3;
   const long long h1_net = (long long)3 * n1;       // element distance between the same plane of consecutive nets
@@ -605,6 +607,13 @@ int v2_create(b2g_sac* h) {
       for (int p = 0; p < 3; ++p) P.out_p[p] = v.F[n][p];
       P.bias = h->p(std::string(nets[n]) + "/cnn_fc1/b"); P.bias_grp = 32;
       P.out_f = h->F[n]; P.f_tm = (long long)128 * FS; P.f0 = FS; P.f_grp = 32;
+      if (v.split_fc1 > 1) {
+        // 48 tiles of 16 K-chunks would hold 48 of the 148 SMs for the longest stretch of the forward launch: three K-splits per
+        // tile, fp32 partial sums in a workspace, the last split to arrive finishes the tile (cg.cuh: ws)
+        P.splits = v.split_fc1;
+        if (int rc = valloc(h, &P.ws, (size_t)P.tiles_m * P.tiles_n * 128 * 64)) return rc;
+        if (int rc = valloc(h, &P.ws_cnt, (size_t)P.tiles_m * P.tiles_n * CG_EPI_WARPS)) return rc;
+      }
       g.host[g.n++] = P;
     }
     if (int rc = push_group(h, v.fwd, g, "fc1_fwd")) return rc;

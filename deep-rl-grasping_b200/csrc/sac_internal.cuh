@@ -73,6 +73,7 @@ struct V2State {
   // fused launches: the layer groups above concatenated into one persistent launch each, chained by arrival counters
   std::vector<CgGroup> fwd_fused, bwd_fused;
   bool fuse = false;
+  int split_fc1 = 3;             // K-splits of the cnn_fc1 forward tiles (1 = none)
   bool epi_colsum = true;        // conv / cnn_fc1 bias gradients come from the DGRAD epilogues (else: colsum2 launches over the planes)
   int* dep_ctr = nullptr; int n_dep_ctr = 0;
   std::vector<int*> tabs;
