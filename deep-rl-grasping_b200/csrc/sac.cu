@@ -1235,6 +1235,7 @@ int b2g_sac_dp_connect(b2g_sac* h, const void* all_exports, int nranks) {
   if (!h || !all_exports) return fail(B2G_EINVAL, "b2g_sac_dp_connect: null argument");
   if (nranks != h->cfg.nranks || nranks < 2 || nranks > DP_MAX_RANKS) return fail(B2G_EINVAL, "b2g_sac_dp_connect: nranks must equal the learner's (2..8)");
   if (!h->dp_x) return fail(B2G_EINVAL, "b2g_sac_dp_connect: call b2g_sac_dp_export first");
+  if (h->dp_p2p) return fail(B2G_ESTATE, "b2g_sac_dp_connect: already connected");
   if (((h->n_pi | h->n_values | h->n_ent | h->n_target) & 3) != 0) return fail(B2G_EINVAL, "b2g_sac_dp_connect: arena segments are not float4 aligned");
   cudaSetDevice(h->cfg.device);
   CK(cudaStreamSynchronize(h->stream));
