@@ -520,6 +520,7 @@ int v2_create(b2g_sac* h) {
   }
 
   { const char* e = getenv("B2G_SPLIT_FC1"); v.split_fc1 = e ? std::max(1, atoi(e)) : 3; }
+  { const char* e = getenv("B2G_SPLIT_FC1_DGRAD"); v.split_fc1_dgrad = e ? std::max(1, atoi(e)) : 1; }
   // ================================================================================ forward problems (6-product mode)
   const int NP = 3;
   const long long h1_net = (long long)3 * n1;       // element distance between the same plane of consecutive nets
@@ -686,6 +687,11 @@ int v2_create(b2g_sac* h) {
           for (int p = 0; p < 2; ++p) P.out_p[p] = v.dZ3[n][p];
           P.mask = v.H3[n][0]; P.m_tm = 128 * 1024; P.m0 = 1024;
           if (v.epi_colsum) { P.colsum = h->g(std::string(nets[n]) + "/cnn3/b"); P.colsum_mask = 63; }     // dZ3 row = [16 pixels][64 channels]
+          if (v.split_fc1_dgrad > 1) {         // 32 tiles of 8 K-chunks at the head of the backward chain: split-K with finalisation
+            P.splits = v.split_fc1_dgrad;
+            if (int rc = valloc(h, &P.ws, (size_t)P.tiles_m * P.tiles_n * 128 * 128)) return rc;
+            if (int rc = valloc(h, &P.ws_cnt, (size_t)P.tiles_m * P.tiles_n * CG_EPI_WARPS)) return rc;
+          }
           g.host[g.n++] = P;
         }
         {

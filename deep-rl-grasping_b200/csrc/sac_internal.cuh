@@ -74,6 +74,7 @@ struct V2State {
   std::vector<CgGroup> fwd_fused, bwd_fused;
   bool fuse = false;
   int split_fc1 = 3;             // K-splits of the cnn_fc1 forward tiles (1 = none)
+  int split_fc1_dgrad = 1;       // K-splits of the cnn_fc1 dgrad tiles (B2G_SPLIT_FC1_DGRAD; opt-in)
   bool epi_colsum = true;        // conv / cnn_fc1 bias gradients come from the DGRAD epilogues (else: colsum2 launches over the planes)
   int* dep_ctr = nullptr; int n_dep_ctr = 0;
   std::vector<int*> tabs;
