@@ -3,8 +3,9 @@
 // Every dense contraction of the step is a list of 128-row output tiles; the operands of a tile are fetched, K-chunk by
 // K-chunk, by cp.async.bulk.tensor (TMA) boxes over BF16 plane tensors straight into 128B-swizzled shared-memory UMMA
 // tiles.  Convolutions need no im2col buffer: their patches / shifted windows / zero borders are expressed as tensor-map
-// VIEWS (overlapping strides, element strides, out-of-bound zero fill) of the NHWC activation planes, so one elected
-// thread feeds the whole ring (tools/tma_probe.cu checks each view behaviour on the device).
+// VIEWS (overlapping strides, element strides, out-of-bound zero fill) of the NHWC activation planes, so two elected
+// lanes feed the whole ring (tools/tma_probe.cu checks each view behaviour on the device).  A launch is a list of problems;
+// problems of one launch may depend on each other tile by tile (fused layers) and may split K with in-kernel finalisation.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>

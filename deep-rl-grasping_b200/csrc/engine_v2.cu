@@ -1,14 +1,17 @@
 // Engine v2: the CNN / head contractions of the SAC step on the TMA-fed tcgen05 engine (cg.cu).
 //
 // This file owns (i) the BF16 plane tensors the engine reads and writes, (ii) the tensor-map VIEWS that turn NHWC
-// activation planes into implicit-im2col / shifted-window / zero-bordered operand tiles, (iii) the problem lists of every
-// grouped launch and (iv) the three HBM-bound helper kernels around them:
-//   gather2_kernel : replay slot draw + index gather + float64 VecNormalize + clip + /255 (replay.cu semantics,
-//                    [SB2] ReplayBuffer.sample(env=VecNormalize), observation_input(scale=True)) and -- new -- the
-//                    3-plane BF16 split and the conv1 patch matrix (8x8 stride-4 patches of the normalised image) so that
-//                    conv1 forward and its wgrad are plain 2-D TMA tiles;
+// activation planes into implicit-im2col / shifted-window / zero-bordered operand tiles (one map per tensor: plane = outermost
+// dimension), (iii) the problem lists of every layer group and the two FUSED launches built from them (forward chain, backward
+// chain: fuse_groups wires each consumer problem to the producer tiles it reads) and (iv) the HBM-bound helper kernels around them:
+//   gather2_kernel : replay slot draw + compact-row gather + float64 VecNormalize + clip + /255 (replay.cu semantics,
+//                    [SB2] ReplayBuffer.sample(env=VecNormalize), observation_input(scale=True)), the 3-plane BF16 split and the
+//                    conv1 patch rows (8x8 stride-4 patches of the normalised image; the one view TMA cannot express, see
+//                    profiles/tma_r2.md) so that conv1 forward and its wgrad are plain 2-D TMA tiles;
+//   compact_kernel : full observation rows -> compact replay rows (image planes | actuator value);
 //   planes2_kernel : weights -> BF16 planes in the layouts the tensor maps expect (transposed / packed per consumer);
-//   colsum2_kernel : bias gradients as column sums of the BF16 gradient-map planes.
+//   colsum2_kernel : bias gradients as column sums of the gradient-map planes -- only with B2G_BIAS_EPI=0: by default the DGRAD
+//                    epilogues of cg.cu produce them.
 // Reference shapes: custom_obs_policy.py:34-40 (conv 8x8/4 -> 4x4/2 -> 3x3/1, fc 1024->512), SURVEY.md Appendix A.
 #include <cuda_bf16.h>
 
